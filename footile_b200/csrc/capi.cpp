@@ -1,0 +1,409 @@
+// capi.cpp — the C ABI of include/footile_b200.h over ftl::Engine.
+// Plain pointers and sizes only; never throws across the boundary.
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "engine.h"
+
+using namespace ftl;
+
+struct ftl_plotter {
+    Engine eng;
+    Geometry geo;
+    void *raster = nullptr;
+    float e[6] = {1, 0, 0, 0, 1, 0};  // Transform::default (plotter.rs:110)
+    float tol_sq = 0.3f * 0.3f;       // plotter.rs:97,111
+    float s_width = 1.0f;             // plotter.rs:112
+    int join = FTL_JOIN_MITER;        // JoinStyle::Miter(4.0) (plotter.rs:113)
+    float miter_limit = 4.0f;
+    explicit ftl_plotter(int device) : eng(device) {}
+};
+
+struct ftl_batch {
+    Engine eng;
+    Geometry geo;
+    uint32_t capacity = 0;
+    void *rasters = nullptr;
+    float tol_sq = 0.3f * 0.3f;
+    explicit ftl_batch(int device) : eng(device) {}
+};
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                       \
+    }                                                   \
+    catch (const std::bad_alloc &) {                    \
+        set_error("host allocation failed");            \
+        return FTL_ERR_NOMEM;                           \
+    }                                                   \
+    catch (...) {                                       \
+        set_error("unexpected host exception");         \
+        return FTL_ERR_INVALID;                         \
+    }
+
+static int bad(const char *msg) {
+    set_error(msg);
+    return FTL_ERR_INVALID;
+}
+static bool fmt_ok(int f) { return f == FTL_MATTE8 || f == FTL_GRAYA8P || f == FTL_RGBA8P; }
+
+extern "C" {
+
+int ftl_abi_version(void) { return FTL_ABI_VERSION; }
+const char *ftl_last_error(void) { return last_error(); }
+
+int ftl_device_count(int *count) {
+    GUARD_BEGIN
+    if (!count) return bad("count is null");
+    return Engine::device_count(count);
+    GUARD_END
+}
+
+int ftl_plotter_new_band(uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end, int format, const void *init_pixels,
+                         int device, ftl_plotter **out) {
+    GUARD_BEGIN
+    if (!out) return bad("out is null");
+    *out = nullptr;
+    if (!fmt_ok(format)) return bad("unknown pixel format");
+    if (row_begin > row_end || row_end > height) return bad("row band outside the raster");
+    if (width > 0x3FFFFFFFu || height > 0x3FFFFFFFu) return bad("raster too large");
+    ftl_plotter *p = new ftl_plotter(device);
+    p->geo.width = width; p->geo.height = height; p->geo.row_begin = row_begin; p->geo.row_end = row_end; p->geo.format = format;
+    int rc = p->eng.alloc_raster(p->geo.bytes(), &p->raster);
+    if (!rc && p->geo.bytes()) {
+        if (init_pixels) rc = p->eng.copy_in(p->raster, init_pixels, p->geo.bytes());
+        else rc = p->eng.memset_async(p->raster, 0, p->geo.bytes());
+    }
+    if (rc) {
+        delete p;
+        return rc;
+    }
+    *out = p;
+    return FTL_OK;
+    GUARD_END
+}
+
+int ftl_plotter_new(uint32_t width, uint32_t height, int format, const void *init_pixels, int device, ftl_plotter **out) {
+    return ftl_plotter_new_band(width, height, 0, height, format, init_pixels, device, out);
+}
+
+int ftl_plotter_free(ftl_plotter *p) {
+    GUARD_BEGIN
+    if (!p) return FTL_OK;
+    p->eng.free_raster(p->raster);
+    delete p;
+    return FTL_OK;
+    GUARD_END
+}
+
+uint32_t ftl_width(const ftl_plotter *p) { return p ? p->geo.width : 0; }
+uint32_t ftl_height(const ftl_plotter *p) { return p ? p->geo.height : 0; }
+float ftl_pen_width(const ftl_plotter *p) { return p ? p->s_width : 0.0f; }
+
+int ftl_set_tolerance(ftl_plotter *p, float t) {
+    if (!p) return bad("null plotter");
+    float tol = t > 0.01f ? t : 0.01f;  // t.max(0.01) (plotter.rs:134); NaN.max(0.01) = 0.01 as well
+    p->tol_sq = tol * tol;
+    return FTL_OK;
+}
+int ftl_set_transform(ftl_plotter *p, const float e[6]) {
+    if (!p || !e) return bad("null argument");
+    for (int k = 0; k < 6; k++)
+        if (!(e[k] - e[k] == 0.0f)) {
+            set_error("non-finite transform");
+            return FTL_ERR_NONFINITE;
+        }
+    memcpy(p->e, e, sizeof(p->e));
+    return FTL_OK;
+}
+int ftl_set_join(ftl_plotter *p, int join, float miter_limit) {
+    if (!p) return bad("null plotter");
+    if (join < FTL_JOIN_MITER || join > FTL_JOIN_ROUND) return bad("unknown join style");
+    p->join = join;
+    p->miter_limit = miter_limit;
+    return FTL_OK;
+}
+
+static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
+    if (rule != FTL_NONZERO && rule != FTL_EVENODD) return bad("unknown fill rule");
+    if (n_ops && !ops) return bad("ops is null");
+    // PenWidth persists on the plotter across calls (plotter.rs:151-153)
+    for (size_t i = 0; i < n_ops; i++)
+        if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
+    std::vector<HostJob> jobs(1);
+    HostJob &j = jobs[0];
+    j.op_begin = 0; j.op_end = (uint32_t)n_ops;
+    memcpy(j.e, p->e, sizeof(j.e));
+    j.tol_sq = p->tol_sq;
+    j.rule = rule;
+    if (color) memcpy(j.color, color, p->geo.bpp());
+    j.raster = p->raster;
+    return p->eng.fill(p->geo, jobs, ops, n_ops);
+}
+
+int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    return plot_fill(p, rule, ops, n_ops, color);
+    GUARD_END
+}
+
+static int stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, std::vector<ftl_path_op> *outline) {
+    std::vector<float> opw;
+    float final_w = stroke_widths(p->s_width, ops, n_ops, &opw);
+    WideFlat flat;
+    int rc = p->eng.flatten_wide(p->e, p->tol_sq, ops, n_ops, opw.data(), &flat);
+    if (rc) return rc;
+    p->s_width = final_w;
+    StrokeParams sp;
+    sp.join = p->join; sp.miter_limit = p->miter_limit; sp.tol_sq = p->tol_sq;
+    stroke_outline(sp, ops, n_ops, flat, outline);
+    return FTL_OK;
+}
+
+int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    if (n_ops && !ops) return bad("ops is null");
+    std::vector<ftl_path_op> outline;
+    int rc = stroke_ops(p, ops, n_ops, &outline);
+    if (rc) return rc;
+    // self.fill(FillRule::NonZero, ops.iter(), clr) (plotter.rs:364): the outline goes through the
+    // plotter's transform a second time, exactly as in the reference.
+    return plot_fill(p, FTL_NONZERO, outline.data(), outline.size(), color);
+    GUARD_END
+}
+
+int ftl_read_raster(ftl_plotter *p, void *dst, size_t nbytes) {
+    GUARD_BEGIN
+    if (!p || (!dst && nbytes)) return bad("null argument");
+    if (nbytes != p->geo.bytes()) return bad("nbytes does not match rows*width*bpp");
+    if (!nbytes) return p->eng.sync();
+    return p->eng.copy_out(dst, p->raster, nbytes);
+    GUARD_END
+}
+int ftl_write_raster(ftl_plotter *p, const void *src, size_t nbytes) {
+    GUARD_BEGIN
+    if (!p || (!src && nbytes)) return bad("null argument");
+    if (nbytes != p->geo.bytes()) return bad("nbytes does not match rows*width*bpp");
+    if (!nbytes) return FTL_OK;
+    return p->eng.copy_in(p->raster, src, nbytes);
+    GUARD_END
+}
+int ftl_sync(ftl_plotter *p) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    return p->eng.sync();
+    GUARD_END
+}
+int ftl_raster_device_ptr(ftl_plotter *p, void **dptr, size_t *nbytes) {
+    if (!p || !dptr) return bad("null argument");
+    *dptr = p->raster;
+    if (nbytes) *nbytes = p->geo.bytes();
+    return FTL_OK;
+}
+
+// ---- batch ----
+int ftl_batch_new(uint32_t width, uint32_t height, int format, uint32_t capacity, int device, ftl_batch **out) {
+    GUARD_BEGIN
+    if (!out) return bad("out is null");
+    *out = nullptr;
+    if (!fmt_ok(format)) return bad("unknown pixel format");
+    if (capacity == 0) return bad("capacity is zero");
+    if (width > 0x3FFFFFFFu || height > 0x3FFFFFFFu) return bad("raster too large");
+    ftl_batch *b = new ftl_batch(device);
+    b->geo.width = width; b->geo.height = height; b->geo.row_begin = 0; b->geo.row_end = height; b->geo.format = format;
+    b->capacity = capacity;
+    int rc = b->eng.alloc_raster(b->geo.bytes() * capacity, &b->rasters);
+    if (!rc && b->geo.bytes()) rc = b->eng.memset_async(b->rasters, 0, b->geo.bytes() * capacity);
+    if (rc) {
+        delete b;
+        return rc;
+    }
+    *out = b;
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_batch_free(ftl_batch *b) {
+    GUARD_BEGIN
+    if (!b) return FTL_OK;
+    b->eng.free_raster(b->rasters);
+    delete b;
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_batch_set_tolerance(ftl_batch *b, float t) {
+    if (!b) return bad("null batch");
+    float tol = t > 0.01f ? t : 0.01f;
+    b->tol_sq = tol * tol;
+    return FTL_OK;
+}
+int ftl_batch_clear(ftl_batch *b, uint32_t first, uint32_t count) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    if ((uint64_t)first + count > b->capacity) return bad("raster range outside the batch");
+    if (!count || !b->geo.bytes()) return FTL_OK;
+    return b->eng.memset_async((uint8_t *)b->rasters + b->geo.bytes() * first, 0, b->geo.bytes() * count);
+    GUARD_END
+}
+
+static int batch_jobs(ftl_batch *b, uint32_t n_jobs, const uint64_t *op_offsets, const uint8_t *rules, const float *transforms,
+                      const uint8_t *colors, std::vector<HostJob> *jobs) {
+    if (n_jobs > b->capacity) return bad("more jobs than rasters in the batch");
+    if (n_jobs && !op_offsets) return bad("op_offsets is null");
+    jobs->resize(n_jobs);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        HostJob &h = (*jobs)[j];
+        if (op_offsets[j + 1] < op_offsets[j] || op_offsets[j + 1] > 0x7FFFFFFFull) return bad("op_offsets must be non-decreasing");
+        h.op_begin = (uint32_t)op_offsets[j];
+        h.op_end = (uint32_t)op_offsets[j + 1];
+        if (transforms) memcpy(h.e, transforms + 6 * (size_t)j, sizeof(h.e));
+        h.tol_sq = b->tol_sq;
+        h.rule = rules ? rules[j] : FTL_NONZERO;
+        if (h.rule != FTL_NONZERO && h.rule != FTL_EVENODD) return bad("unknown fill rule");
+        if (colors) memcpy(h.color, colors + 4 * (size_t)j, 4);
+        h.raster = (uint8_t *)b->rasters + b->geo.bytes() * j;
+    }
+    return FTL_OK;
+}
+
+int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const uint8_t *rules,
+                   const float *transforms, const uint8_t *colors) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    if (n_jobs == 0) return FTL_OK;
+    std::vector<HostJob> jobs;
+    int rc = batch_jobs(b, n_jobs, op_offsets, rules, transforms, colors, &jobs);
+    if (rc) return rc;
+    size_t n_ops = (size_t)op_offsets[n_jobs];
+    if (n_ops && !ops) return bad("ops is null");
+    return b->eng.fill(b->geo, jobs, ops, n_ops);
+    GUARD_END
+}
+int ftl_batch_upload(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const uint8_t *rules,
+                     const float *transforms, const uint8_t *colors) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    std::vector<HostJob> jobs;
+    int rc = batch_jobs(b, n_jobs, op_offsets, rules, transforms, colors, &jobs);
+    if (rc) return rc;
+    size_t n_ops = n_jobs ? (size_t)op_offsets[n_jobs] : 0;
+    if (n_ops && !ops) return bad("ops is null");
+    return b->eng.upload(b->geo, jobs, ops, n_ops);
+    GUARD_END
+}
+int ftl_batch_run(ftl_batch *b) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    return b->eng.replay();
+    GUARD_END
+}
+int ftl_batch_read(ftl_batch *b, uint32_t first, uint32_t count, void *dst, size_t nbytes) {
+    GUARD_BEGIN
+    if (!b || (!dst && nbytes)) return bad("null argument");
+    if ((uint64_t)first + count > b->capacity) return bad("raster range outside the batch");
+    if (nbytes != b->geo.bytes() * count) return bad("nbytes does not match count*height*width*bpp");
+    if (!nbytes) return b->eng.sync();
+    return b->eng.copy_out(dst, (uint8_t *)b->rasters + b->geo.bytes() * first, nbytes);
+    GUARD_END
+}
+int ftl_batch_checksums(ftl_batch *b, uint32_t first, uint32_t count, uint64_t *out) {
+    GUARD_BEGIN
+    if (!b || (!out && count)) return bad("null argument");
+    if ((uint64_t)first + count > b->capacity) return bad("raster range outside the batch");
+    return b->eng.checksums((uint8_t *)b->rasters + b->geo.bytes() * first, b->geo.bytes(), count, out);
+    GUARD_END
+}
+int ftl_batch_sync(ftl_batch *b) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    return b->eng.sync();
+    GUARD_END
+}
+int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes) {
+    if (!b || !dptr) return bad("null argument");
+    *dptr = b->rasters;
+    if (nbytes) *nbytes = b->geo.bytes() * b->capacity;
+    return FTL_OK;
+}
+
+// ---- instrumentation ----
+uint64_t ftl_launch_count(void) { return Engine::launch_count(); }
+int ftl_set_profiling(int enabled) {
+    Engine::set_profiling(enabled != 0);
+    return FTL_OK;
+}
+int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches) {
+    Engine::tile_kernel_time(reset != 0, ms, launches);
+    return FTL_OK;
+}
+
+// ---- parity probes ----
+int ftl_debug_flatten(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, int32_t *xy, size_t cap, size_t *n_points, uint32_t *subs,
+                      size_t sub_cap, size_t *n_subs) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    std::vector<int32_t> v;
+    std::vector<uint32_t> s;
+    int rc = p->eng.debug_flatten(p->e, p->tol_sq, ops, n_ops, &v, &s);
+    if (rc) return rc;
+    size_t np = v.size() / 2, ns = s.size() / 2;
+    if (n_points) *n_points = np;
+    if (n_subs) *n_subs = ns;
+    if (xy) memcpy(xy, v.data(), sizeof(int32_t) * 2 * (np < cap ? np : cap));
+    if (subs) memcpy(subs, s.data(), sizeof(uint32_t) * 2 * (ns < sub_cap ? ns : sub_cap));
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]) {
+    GUARD_BEGIN
+    if (!p || !info) return bad("null argument");
+    FillInfo fi;
+    int rc = p->eng.last_fill_info(&fi);
+    if (rc) return rc;
+    info[0] = fi.dir; info[1] = fi.top_row; info[2] = (int32_t)fi.n_points;
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap, size_t *n_out) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    float keep = p->s_width;
+    std::vector<ftl_path_op> outline;
+    int rc = stroke_ops(p, ops, n_ops, &outline);
+    p->s_width = keep;  // a probe must not change plotter state
+    if (rc) return rc;
+    if (n_out) *n_out = outline.size();
+    if (out) memcpy(out, outline.data(), sizeof(ftl_path_op) * (outline.size() < cap ? outline.size() : cap));
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_debug_stroke_outline(int join, float miter_limit, float tol_sq, const ftl_path_op *ops, size_t n_ops, const uint32_t *counts,
+                             const float *xyw, ftl_path_op *out, size_t cap, size_t *n_out) {
+    GUARD_BEGIN
+    if (n_ops && (!ops || !counts)) return bad("null argument");
+    WideFlat flat;
+    flat.counts.assign(counts, counts + n_ops);
+    size_t np = 0;
+    for (size_t i = 0; i < n_ops; i++) np += counts[i];
+    if (np && !xyw) return bad("xyw is null");
+    flat.xyw.assign(xyw, xyw + 3 * np);
+    StrokeParams sp;
+    sp.join = join; sp.miter_limit = miter_limit; sp.tol_sq = tol_sq;
+    std::vector<ftl_path_op> outline;
+    stroke_outline(sp, ops, n_ops, flat, &outline);
+    if (n_out) *n_out = outline.size();
+    if (out) memcpy(out, outline.data(), sizeof(ftl_path_op) * (outline.size() < cap ? outline.size() : cap));
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_debug_accumulate(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows, int device) {
+    GUARD_BEGIN
+    if ((!src || !dst) && n && rows) return bad("null argument");
+    Engine eng(device);
+    return eng.accumulate_rows(rule, src, dst, n, rows);
+    GUARD_END
+}
+
+}  // extern "C"

@@ -1,0 +1,1268 @@
+// engine.cu — the device pipeline of the footile hot path for sm_100a.
+//
+// Stages (reference functions they replace are cited per kernel):
+//   (a) flatten_ops      per-PathOp adaptive De Casteljau -> Fixed vertices
+//                        (plotter.rs:175-332, fig.rs:428-461)
+//   (b) vtx_topkey / edge_build / job_finalize / bin_count / bin_fill
+//                        ring edges, Edge::new, global winding + top row,
+//                        counting sort of edges by row band
+//                        (fig.rs:143-210,402-411,464-502,576-617)
+//   (c)+(d) raster_tiles per (raster,row band) tile: scatter signed coverage
+//                        deltas of every (edge,row) into a shared-memory row
+//                        tile, warp-scan each row, apply the fill rule, store
+//                        the matte / blend the colour (fig.rs:238-321,536-573,
+//                        621-682; imgbuf.rs:22-199)
+//
+// There is no active-edge list and no per-row serial dependency: every
+// (edge,row) contribution is evaluated in closed form,
+// which tests/test_oracle_orderfree.py proves equal to the reference's scan.
+//
+// Build flags: -fmad=false (Rust never fuses a*b+c), no fast-math.
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <algorithm>
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "engine.h"
+#include "fixed.cuh"
+#include "pix_compat.cuh"
+#include "pointy_compat.cuh"
+
+namespace ftl {
+
+// ---------------------------------------------------------------------------
+// error plumbing
+// ---------------------------------------------------------------------------
+static thread_local std::string g_err;
+void set_error(const std::string &msg) { g_err = msg; }
+const char *last_error() { return g_err.c_str(); }
+
+#define CK(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess) {                                                                   \
+            set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                         \
+            return (e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver) ? FTL_ERR_NO_DEVICE \
+                   : (e_ == cudaErrorMemoryAllocation ? FTL_ERR_NOMEM : FTL_ERR_CUDA);             \
+        }                                                                                          \
+    } while (0)
+
+static std::atomic<uint64_t> g_launches{0};
+static std::atomic<bool> g_profiling{false};
+#define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+// ---------------------------------------------------------------------------
+// device data layout (all arrays live in the engine's scratch arena in HBM)
+// ---------------------------------------------------------------------------
+constexpr uint32_t NONE32 = 0xFFFFFFFFu;
+constexpr int MAX_DEPTH = 24;  // subdivision depth cap (the reference recurses without bound)
+constexpr int TILE_THREADS = 256;
+
+struct __align__(16) JobDesc {  // 64 B, host-filled
+    uint32_t op_begin, op_end;
+    float e[6];
+    float tol_sq;
+    uint32_t rule;
+    uint32_t color;  // bytes r,g,b,a little-endian (or gray,alpha / alpha)
+    uint32_t pad0;
+    unsigned long long raster;  // device address of row `row_begin`
+    unsigned long long pad1;
+};
+static_assert(sizeof(JobDesc) == 64, "JobDesc layout");
+
+struct __align__(16) JobState {  // 32 B, device-written
+    unsigned long long top_key;  // min over vertices of (y,x), sign-biased
+    uint32_t top_vid;
+    int32_t dir;        // 0 Forward, 1 Reverse (fig.rs:402-411)
+    int32_t top_row;    // row_of(y of top-left vertex) (fig.rs:496)
+    int32_t first_row;  // max(top_row, 0): first raster row the fill touches (fig.rs:497)
+    int32_t shift;      // min(top_row, 0): geometry row r lands on raster row r - shift
+    uint32_t pad;
+};
+
+struct __align__(16) Vtx {  // 16 B
+    int32_t x, y;   // Fixed 16.16
+    uint32_t sub;   // index of the first vertex of this vertex's sub-figure
+    uint32_t job;
+};
+
+struct __align__(16) EdgeRec {  // 32 B: one per ring segment whose end points differ in y (fig.rs:47-66,179-201)
+    int32_t x_bot0;     // X at the bottom of the edge's first row
+    int32_t inv_slope;  // dx/dy
+    int32_t step_pix;   // min(|dy/dx|, 1), 0 when vertical
+    int32_t y0, y1;     // upper / lower Y
+    uint32_t job;
+    uint32_t flags;     // bit0 valid, bit1 direction upper->lower (0 Forward, 1 Reverse)
+    uint32_t pad;
+};
+
+struct __align__(8) SumHead {  // scan element over ops: vertex count + position of the last sub-figure head
+    uint32_t sum, head;
+};
+
+struct Counters {
+    uint32_t nv;         // vertices after intake
+    uint32_t n_entries;  // (edge,band) pairs after binning
+    uint32_t n_popped;   // closing vertices dropped by the sub-figure close rule (fig.rs:376-380)
+    uint32_t pad;
+};
+
+struct Params {  // per-call constants, passed by value
+    uint32_t W, H, row_begin, row_end;
+    uint32_t fmt, bpp, pitch;
+    uint32_t log2R, R, n_bands, WP;  // rows per tile, bands per job, padded smem row (cells)
+    uint32_t n_jobs, n_ops, n_tiles;
+};
+
+// ---------------------------------------------------------------------------
+// generic 3-phase scan (reduce / scan partials / apply), exclusive, n+1 outputs
+// ---------------------------------------------------------------------------
+struct AddU32 {
+    typedef uint32_t T;
+    static __device__ __forceinline__ T identity() { return 0u; }
+    static __device__ __forceinline__ T combine(T a, T b) { return a + b; }
+    static __device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+};
+struct SumHeadOp {
+    typedef SumHead T;
+    static __device__ __forceinline__ T identity() { return {0u, NONE32}; }
+    static __device__ __forceinline__ T combine(T a, T b) { return {a.sum + b.sum, b.head != NONE32 ? a.sum + b.head : a.head}; }
+    static __device__ __forceinline__ T shfl_up(T v, int d) {
+        return {__shfl_up_sync(0xFFFFFFFFu, v.sum, d), __shfl_up_sync(0xFFFFFFFFu, v.head, d)};
+    }
+};
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+// Exclusive scan of one value per thread across the block; returns the
+// exclusive prefix and the block total (to all threads).
+template <class Op>
+__device__ typename Op::T block_exclusive(typename Op::T v, typename Op::T *total) {
+    typedef typename Op::T T;
+    __shared__ T warp_tot[SCAN_THREADS / 32];
+    __shared__ T blk_tot;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    T inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T o = Op::shfl_up(inc, d);
+        if (lane >= d) inc = Op::combine(o, inc);
+    }
+    if (lane == 31) warp_tot[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        T w = lane < SCAN_THREADS / 32 ? warp_tot[lane] : Op::identity();
+        T winc = w;
+#pragma unroll
+        for (int d = 1; d < SCAN_THREADS / 32; d <<= 1) {
+            T o = Op::shfl_up(winc, d);
+            if (lane >= d) winc = Op::combine(o, winc);
+        }
+        if (lane < SCAN_THREADS / 32) warp_tot[lane] = winc;  // inclusive over warps
+        if (lane == SCAN_THREADS / 32 - 1) blk_tot = winc;
+    }
+    __syncthreads();
+    T excl_in_warp = Op::shfl_up(inc, 1);
+    if (lane == 0) excl_in_warp = Op::identity();
+    T base = wid > 0 ? warp_tot[wid - 1] : Op::identity();
+    *total = blk_tot;
+    T r = Op::combine(base, excl_in_warp);
+    __syncthreads();
+    return r;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_reduce(const typename Op::T *in, uint32_t n, typename Op::T *partials) {
+    typedef typename Op::T T;
+    uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    T acc = Op::identity();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++)
+        if (base + i < n) acc = Op::combine(acc, in[base + i]);
+    T tot;
+    block_exclusive<Op>(acc, &tot);
+    if (threadIdx.x == 0) partials[blockIdx.x] = tot;
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_partials(typename Op::T *partials, uint32_t n_blocks) {
+    typedef typename Op::T T;
+    T carry = Op::identity();
+    for (uint32_t b0 = 0; b0 < n_blocks; b0 += SCAN_THREADS) {
+        uint32_t i = b0 + threadIdx.x;
+        T v = i < n_blocks ? partials[i] : Op::identity();
+        T tot;
+        T ex = block_exclusive<Op>(v, &tot);
+        if (i < n_blocks) partials[i] = Op::combine(carry, ex);
+        carry = Op::combine(carry, tot);
+    }
+}
+
+template <class Op>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const typename Op::T *in, uint32_t n, const typename Op::T *partials,
+                                                           typename Op::T *out) {
+    typedef typename Op::T T;
+    uint32_t base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+    T v[SCAN_ITEMS];
+    T acc = Op::identity();
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        v[i] = base + i < n ? in[base + i] : Op::identity();
+        acc = Op::combine(acc, v[i]);
+    }
+    T tot;
+    T ex = block_exclusive<Op>(acc, &tot);
+    T run = Op::combine(partials[blockIdx.x], ex);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; i++) {
+        if (base + i < n) out[base + i] = run;
+        run = Op::combine(run, v[i]);
+        if (base + i + 1 == n) out[n] = run;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (a) flatten — plotter.rs:175-332 + fig.rs:428-461
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t job_of_op(const JobDesc *jobs, uint32_t n_jobs, uint32_t i) {
+    uint32_t lo = 0, hi = n_jobs;  // last job with op_begin <= i
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (jobs[mid].op_begin <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct PenInfo {
+    pointy::Pt pen;
+    bool starts_sub;
+};
+// Pen position when op i runs: the end point of the previous drawing op, or
+// the origin after Close / at the start of the ops (plotter.rs:128-130,
+// 200-203); PenWidth does not move the pen.
+__device__ __forceinline__ PenInfo find_pen(const ftl_path_op *ops, uint32_t op_begin, uint32_t i) {
+    int64_t k = (int64_t)i - 1;
+    while (k >= (int64_t)op_begin && ops[k].tag >= FTL_OP_PENWIDTH) k--;
+    if (k < (int64_t)op_begin || ops[k].tag == FTL_OP_CLOSE) return {{0.0f, 0.0f}, true};
+    const ftl_path_op &o = ops[k];
+    int at = o.tag == FTL_OP_QUAD ? 2 : (o.tag == FTL_OP_CUBIC ? 4 : 0);
+    return {{o.v[at], o.v[at + 1]}, false};
+}
+
+struct WPt {
+    pointy::Pt p;
+    float w;
+};
+template <bool WIDE>
+__device__ __forceinline__ WPt wmid(WPt a, WPt b) {  // WidePt::midpoint (geom.rs:31-35)
+    WPt r;
+    r.p = pointy::midpoint(a.p, b.p);
+    r.w = WIDE ? (a.w + b.w) / 2.0f : 0.0f;
+    return r;
+}
+
+// Point sink of one op.  Fill mode converts to Fixed and drops a point equal
+// to its predecessor (fig.rs:436-440); wide mode keeps raw f32 + width for the
+// host stroker.
+template <bool WIDE, bool EMIT>
+struct OpSink {
+    uint32_t n = 0;
+    bool force;
+    int32_t px = 0, py = 0;
+    Vtx *vout = nullptr;
+    float *wout = nullptr;
+    uint32_t sub = 0, job = 0;
+    __device__ __forceinline__ void put(WPt q) {
+        if (WIDE) {
+            if (EMIT) {
+                wout[3 * (size_t)n] = q.p.x;
+                wout[3 * (size_t)n + 1] = q.p.y;
+                wout[3 * (size_t)n + 2] = q.w;
+            }
+            n++;
+        } else {
+            int32_t fx = fx_from_f32(q.p.x), fy = fx_from_f32(q.p.y);
+            if (force || fx != px || fy != py) {
+                if (EMIT) vout[n] = {fx, fy, sub, job};
+                n++;
+            }
+            force = false;
+            px = fx;
+            py = fy;
+        }
+    }
+};
+
+template <bool WIDE, bool EMIT>
+__device__ void flatten_quad(WPt a, WPt b, WPt c, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:248-265
+    WPt sb[MAX_DEPTH], sc[MAX_DEPTH];
+    uint8_t sd[MAX_DEPTH];
+    int sp = 0, depth = 0;
+    for (;;) {
+        WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), ab_bc = wmid<WIDE>(ab, bc), ac = wmid<WIDE>(a, c);
+        if (pointy::distance_sq(ab_bc.p, ac.p) <= tol_sq || depth >= MAX_DEPTH) {
+            sink.put(c);
+            if (sp == 0) break;
+            sp--;
+            a = c; b = sb[sp]; c = sc[sp]; depth = sd[sp];
+        } else {
+            sb[sp] = bc; sc[sp] = c; sd[sp] = (uint8_t)(depth + 1); sp++;
+            b = ab; c = ab_bc; depth++;
+        }
+    }
+}
+
+template <bool WIDE, bool EMIT>
+__device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:311-332
+    WPt sb[MAX_DEPTH], sc[MAX_DEPTH], sdd[MAX_DEPTH];
+    uint8_t sd[MAX_DEPTH];
+    int sp = 0, depth = 0;
+    for (;;) {
+        WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), cd = wmid<WIDE>(c, d);
+        WPt ab_bc = wmid<WIDE>(ab, bc), bc_cd = wmid<WIDE>(bc, cd);
+        WPt pe = wmid<WIDE>(ab_bc, bc_cd), ad = wmid<WIDE>(a, d);
+        if (pointy::distance_sq(pe.p, ad.p) <= tol_sq || depth >= MAX_DEPTH) {
+            sink.put(d);
+            if (sp == 0) break;
+            sp--;
+            a = d; b = sb[sp]; c = sc[sp]; d = sdd[sp]; depth = sd[sp];
+        } else {
+            sb[sp] = bc_cd; sc[sp] = cd; sdd[sp] = d; sd[sp] = (uint8_t)(depth + 1); sp++;
+            b = ab; c = ab_bc; d = pe; depth++;
+        }
+    }
+}
+
+// One thread per PathOp.  Pass 1 (EMIT=false) counts the vertices the op
+// contributes; after the scan, pass 2 (EMIT=true) repeats the identical
+// subdivision and writes them at the scanned offset, so the output order is
+// the reference's depth-first order.
+template <bool WIDE, bool EMIT>
+__global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
+                                                   const float *__restrict__ opw, SumHead *__restrict__ cnt,
+                                                   const SumHead *__restrict__ off, Vtx *__restrict__ vout,
+                                                   float *__restrict__ wout) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
+        const ftl_path_op op = ops[i];
+        OpSink<WIDE, EMIT> sink;
+        uint32_t j = job_of_op(jobs, P.n_jobs, i);
+        const JobDesc &jd = jobs[j];
+        bool starts = false;
+        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+            PenInfo pi = find_pen(ops, jd.op_begin, i);
+            starts = pi.starts_sub || op.tag == FTL_OP_MOVE;  // Move closes the current sub-figure (plotter.rs:210)
+            float e[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+            sink.force = starts;
+            if (EMIT) {
+                SumHead o = off[i];
+                if (WIDE) sink.wout = wout + 3 * (size_t)o.sum;
+                else {
+                    sink.vout = vout + o.sum;
+                    sink.sub = starts ? o.sum : o.head;
+                    sink.job = j;
+                }
+            }
+            float w_pen = WIDE ? opw[2 * (size_t)i] : 0.0f, w_now = WIDE ? opw[2 * (size_t)i + 1] : 0.0f;
+            WPt a = {pointy::transform(e, pi.pen), w_pen};
+            if (!WIDE && !starts) {
+                sink.px = fx_from_f32(a.p.x);
+                sink.py = fx_from_f32(a.p.y);
+            }
+            if (op.tag == FTL_OP_MOVE || op.tag == FTL_OP_LINE) {  // plotter.rs:208-224
+                sink.put({pointy::transform(e, {op.v[0], op.v[1]}), w_now});
+            } else if (op.tag == FTL_OP_QUAD) {  // plotter.rs:233-242
+                WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), WIDE ? (w_pen + w_now) / 2.0f : 0.0f};
+                WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w_now};
+                flatten_quad<WIDE, EMIT>(a, b, c, jd.tol_sq, sink);
+            } else {  // plotter.rs:286-305; float_lerp(a,b,t) = b + (a-b)*t (geom.rs:14-16)
+                float w0 = WIDE ? w_now + (w_pen - w_now) * (1.0f / 3.0f) : 0.0f;
+                float w1 = WIDE ? w_now + (w_pen - w_now) * (2.0f / 3.0f) : 0.0f;
+                WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), w0};
+                WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w1};
+                WPt d = {pointy::transform(e, {op.v[4], op.v[5]}), w_now};
+                flatten_cubic<WIDE, EMIT>(a, b, c, d, jd.tol_sq, sink);
+            }
+        }
+        if (!EMIT) cnt[i] = {sink.n, starts ? 0u : NONE32};
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (b) edge prep
+// ---------------------------------------------------------------------------
+// Sub-figure closing (fig.rs:373-383): the last vertex of a sub-figure is
+// dropped when it equals the first.  Dropped vertices stay in the array as
+// holes and are skipped.
+__device__ __forceinline__ bool vtx_is_last(const Vtx *V, uint32_t nv, uint32_t k) { return k + 1 >= nv || V[k + 1].sub == k + 1; }
+__device__ __forceinline__ bool vtx_same(const Vtx &a, const Vtx &b) { return a.x == b.x && a.y == b.y; }
+__device__ __forceinline__ unsigned long long vtx_key(const Vtx &v) {  // (y,x) order of fig.rs:464-472
+    return ((unsigned long long)((uint32_t)v.y ^ 0x80000000u) << 32) | (unsigned long long)((uint32_t)v.x ^ 0x80000000u);
+}
+// Forward ring neighbour of a live vertex (fig.rs:143-152)
+__device__ __forceinline__ uint32_t vtx_next_fwd(const Vtx *V, uint32_t nv, uint32_t k, const Vtx &v, bool last) {
+    if (last) return v.sub;
+    if (vtx_is_last(V, nv, k + 1) && vtx_same(V[k + 1], V[v.sub])) return v.sub;
+    return k + 1;
+}
+
+__global__ void init_job_state(JobState *JS, uint32_t n_jobs) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n_jobs) JS[j] = {~0ull, NONE32, 0, 0, 0x7FFFFFFF, 0, 0};
+}
+
+__global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        if (vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub])) continue;
+        atomicMin(&JS[v.job].top_key, vtx_key(v));
+    }
+}
+
+// Edge::new (fig.rs:179-210)
+__device__ __forceinline__ EdgeRec make_edge(const Vtx &p0, const Vtx &p1, uint32_t job, uint32_t dd) {
+    EdgeRec e;
+    fx_t dx = fx_sub(p1.x, p0.x), dy = fx_sub(p1.y, p0.y);
+    e.step_pix = dx != 0 ? fx_min(fx_abs(fx_div(dy, dx)), FX_ONE) : 0;
+    e.inv_slope = fx_div(dx, dy);
+    fx_t y_bot = fx_sub(fx_floor(fx_add(p0.y, FX_ONE)), p0.y);
+    e.x_bot0 = fx_add(p0.x, fx_mul(e.inv_slope, y_bot));
+    e.y0 = p0.y;
+    e.y1 = p1.y;
+    e.job = job;
+    e.flags = 1u | (dd << 1);
+    e.pad = 0;
+    return e;
+}
+
+// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most
+// one edge, directed from its upper to its lower vertex.  This is the same
+// set of edges the reference creates in update_edges/add_edge (fig.rs:576-600)
+// when it visits both neighbours of every vertex.
+__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, Counters *__restrict__ C, JobState *JS,
+                                                  EdgeRec *__restrict__ E, uint32_t *__restrict__ sub_last) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        bool last = vtx_is_last(V, nv, k);
+        bool pop = last && vtx_same(v, V[v.sub]);
+        if (last) sub_last[v.sub] = pop ? (k > v.sub ? k - 1 : NONE32) : k;
+        if (pop) atomicAdd(&C->n_popped, 1u);
+        EdgeRec e;
+        e.flags = 0;
+        if (!pop) {
+            if (vtx_key(v) == JS[v.job].top_key) atomicMin(&JS[v.job].top_vid, k);
+            uint32_t w = vtx_next_fwd(V, nv, k, v, last);
+            if (w != k) {
+                Vtx q = V[w];
+                if (q.y > v.y) e = make_edge(v, q, v.job, 0u);        // v is upper; w is v's Forward neighbour
+                else if (q.y < v.y) e = make_edge(q, v, v.job, 1u);   // w is upper; v is w's Reverse neighbour
+            }
+        }
+        if (e.flags) E[k] = e;
+        else E[k].flags = 0;
+    }
+}
+
+// Fig::get_dir on the top-left vertex + top_row (fig.rs:402-411,495-496)
+__global__ void job_finalize(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS, const uint32_t *__restrict__ sub_last,
+                             uint32_t n_jobs) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    uint32_t k = JS[j].top_vid;
+    if (k == NONE32) return;  // no vertices: first_row stays INT_MAX, nothing is drawn (fig.rs:491)
+    const uint32_t nv = C->nv;
+    Vtx v = V[k];
+    uint32_t f = vtx_next_fwd(V, nv, k, v, vtx_is_last(V, nv, k));
+    uint32_t r = k > v.sub ? k - 1 : sub_last[v.sub];
+    Vtx pf = V[f], pr = V[r];
+    fx_t ax = fx_sub(pr.x, v.x), ay = fx_sub(pr.y, v.y);
+    fx_t bx = fx_sub(pf.x, v.x), by = fx_sub(pf.y, v.y);
+    bool widdershins = fx_mul(ax, by) > fx_mul(bx, ay);  // fig.rs:116-119
+    int32_t top = fx_to_i32(v.y);
+    JS[j].dir = widdershins ? 0 : 1;
+    JS[j].top_row = top;
+    JS[j].first_row = top > 0 ? top : 0;
+    JS[j].shift = top < 0 ? top : 0;
+}
+
+// Band range of an edge inside this device's rows; returns false if none.
+__device__ __forceinline__ bool edge_bands(const EdgeRec &e, const JobState &js, const Params &P, uint32_t *b0, uint32_t *b1) {
+    int64_t ry0 = (int64_t)fx_to_i32(e.y0) - js.shift, ry1 = (int64_t)fx_to_i32(e.y1) - js.shift;
+    int64_t lo = ry0, hi = ry1;
+    if (lo < js.first_row) lo = js.first_row;
+    if (lo < (int64_t)P.row_begin) lo = P.row_begin;
+    if (hi > (int64_t)P.row_end - 1) hi = (int64_t)P.row_end - 1;
+    if (lo > hi) return false;
+    *b0 = (uint32_t)(lo - P.row_begin) >> P.log2R;
+    *b1 = (uint32_t)(hi - P.row_begin) >> P.log2R;
+    return true;
+}
+
+// Counting sort of edges by (job,row band): pass FILL=false counts, pass
+// FILL=true writes edge ids at the scanned offsets.  Short edges are handled
+// by their own thread; an edge crossing many bands is spread over the warp.
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
+                                                 const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
+                                                 const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ entries) {
+    const uint32_t nv = C->nv;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t span = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < nv; k0 += span) {
+        uint32_t k = k0 + lane;
+        uint32_t b0 = 0, nb = 0, tbase = 0;
+        if (k < nv) {
+            EdgeRec e = E[k];
+            uint32_t b1;
+            if ((e.flags & 1u) && edge_bands(e, JS[e.job], P, &b0, &b1)) {
+                nb = b1 - b0 + 1;
+                tbase = e.job * P.n_bands;
+            }
+        }
+        if (nb > 0 && nb <= 4) {
+            for (uint32_t b = b0; b < b0 + nb; b++) {
+                uint32_t slot = atomicAdd(&tile_count[tbase + b], 1u);
+                if (FILL) entries[tile_off[tbase + b] + slot] = k;
+            }
+        }
+        uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
+        while (tall) {
+            int src = __ffs(tall) - 1;
+            tall &= tall - 1;
+            uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src);
+            uint32_t stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
+            for (uint32_t b = lane; b < snb; b += 32) {
+                uint32_t t = stb + sb0 + b;
+                uint32_t slot = atomicAdd(&tile_count[t], 1u);
+                if (FILL) entries[tile_off[t] + slot] = k0 + src;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (c)+(d) tile raster kernel
+// ---------------------------------------------------------------------------
+// Signed coverage of one edge on one geometry row, scattered into the row's
+// shared-memory cells.  Closed form of Scanner::scan_continuing_edges /
+// add_edge + Edge::scan_area (fig.rs:238-321,557-600); SURVEY Appendix A.4.
+__device__ __forceinline__ void scatter_edge_row(const EdgeRec &e, int32_t ed, int32_t r, int32_t *row, int32_t W) {
+    const int32_t r0 = fx_to_i32(e.y0), r1 = fx_to_i32(e.y1);
+    const bool starting = r == r0, ending = r == r1;
+    // continuing_cov / starting_cov (fig.rs:238-241,252-259)
+    int32_t cov = (ending ? pixel_cov(fx_fract(e.y1)) : 256) - (starting ? pixel_cov(fx_fract(e.y0)) : 0);
+    if (cov <= 0) return;
+    // advance_edges in closed form (fig.rs:569-573)
+    fx_t x_bot = (fx_t)((uint32_t)e.x_bot0 + (uint32_t)(r - r0) * (uint32_t)e.inv_slope);
+    // calculate_x_limits_* / set_x_limits (fig.rs:244-249,262-278)
+    fx_t x0 = starting ? fx_sub(x_bot, fx_mul(e.inv_slope, fx_sub(FX_ONE, fx_fract(e.y0)))) : fx_sub(x_bot, e.inv_slope);
+    fx_t x1 = ending ? fx_sub(x_bot, fx_mul(e.inv_slope, fx_sub(fx_ceil(e.y1), e.y1))) : x_bot;
+    fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
+    int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
+    if (min_pix >= W) return;
+    // first_cov / step_cov (fig.rs:305-321); full_cov = cov/256 in Fixed = cov << 8
+    fx_t rr = min_pix == max_pix ? fx_mul(fx_sub(FX_ONE, fx_fract(fx_avg(max_x, min_x))), (fx_t)(cov << 8))
+                                 : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
+    fx_t first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
+    fx_t step = e.step_pix > 0 ? e.step_pix : FX_ONE;
+    // scan_area (fig.rs:285-302): X(k) = min(pixel_cov(min(first + k*step, 1)), cov);
+    // cell min_pix+k receives X(k)-X(k-1); cells left of 0 fold into cell 0.
+    int32_t c = min_pix > 0 ? min_pix : 0;
+    int64_t xc = (int64_t)first + (int64_t)(c - min_pix) * (int64_t)step;
+    int32_t prev = 0;
+    for (; c < W; c++) {
+        int32_t xk = pixel_cov((fx_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE));
+        if (xk > cov) xk = cov;
+        int32_t d = xk - prev;
+        if (d != 0) atomicAdd(&row[c], ed * d);
+        prev = xk;
+        if (xk >= cov) break;
+        xc += step;
+    }
+}
+
+// alpha of one pixel from the wrapped i16 sum (fig.rs:637-664; imgbuf.rs:54-66,157-167)
+__device__ __forceinline__ uint32_t rule_alpha(int32_t sum, bool even_odd) {
+    int32_t s = (int32_t)(int16_t)sum;
+    if (even_odd) {
+        int32_t c = (s & 0xFF) - (s & 0x100);
+        s = c < 0 ? -c : c;
+    }
+    return (uint32_t)(s < 0 ? 0 : (s > 255 ? 255 : s));
+}
+
+// Resolve one row held in shared memory by one warp: inclusive prefix sum of
+// the cells (zeroing them), fill rule, then store (Matte8) or SrcOver blend
+// (Graya8p / Rgba8p) into the raster row.  Each lane owns 4 consecutive
+// cells per 128-cell chunk: LDS.128, 3 adds, a 5-step shuffle scan.
+__device__ __forceinline__ void resolve_row(int32_t *row, uint8_t *dst, uint32_t W, uint32_t fmt, bool even_odd, uint32_t color) {
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t carry = 0;
+    const uint32_t clr_a = fmt == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    for (uint32_t x0 = 0; x0 < W; x0 += 128) {
+        const uint32_t x = x0 + lane * 4;
+        int4 v = *reinterpret_cast<int4 *>(row + x);
+        *reinterpret_cast<int4 *>(row + x) = make_int4(0, 0, 0, 0);
+        v.y += v.x; v.z += v.y; v.w += v.z;
+        int32_t inc = v.w;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        int32_t base = carry + inc - v.w;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        uint32_t a0 = rule_alpha(base + v.x, even_odd), a1 = rule_alpha(base + v.y, even_odd);
+        uint32_t a2 = rule_alpha(base + v.z, even_odd), a3 = rule_alpha(base + v.w, even_odd);
+        if (x >= W) continue;
+        if (fmt == FTL_MATTE8) {  // store, colour ignored (fig.rs:632-636; imgbuf.rs:59,93)
+            uint32_t packed = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
+            uint8_t *d = dst + x;
+            if (x + 4 <= W && ((uintptr_t)d & 3) == 0) *reinterpret_cast<uint32_t *>(d) = packed;
+            else
+                for (uint32_t i = 0; i < 4 && x + i < W; i++) d[i] = (uint8_t)(packed >> (8 * i));
+        } else if (fmt == FTL_RGBA8P) {  // fig.rs:641-642,662-663 via pix (pix_compat.cuh)
+            uint32_t al[4] = {a0, a1, a2, a3};
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
+            uint32_t px[4];
+            const bool vec = x + 4 <= W && ((uintptr_t)d & 15) == 0;
+            if (vec) {
+                uint4 t = *reinterpret_cast<uint4 *>(d);
+                px[0] = t.x; px[1] = t.y; px[2] = t.z; px[3] = t.w;
+            } else
+                for (uint32_t i = 0; i < 4; i++) px[i] = x + i < W ? d[i] : 0;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                uint32_t sa1 = 255u - pix::ch8_mul(al[i], clr_a);
+                uint32_t o = 0;
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++)
+                    o |= pix::src_over_ch((px[i] >> (8 * ch)) & 0xFF, (color >> (8 * ch)) & 0xFF, al[i], sa1) << (8 * ch);
+                px[i] = o;
+            }
+            if (vec) *reinterpret_cast<uint4 *>(d) = make_uint4(px[0], px[1], px[2], px[3]);
+            else
+                for (uint32_t i = 0; i < 4 && x + i < W; i++) d[i] = px[i];
+        } else {  // Graya8p
+            uint32_t al[4] = {a0, a1, a2, a3};
+            uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
+            for (uint32_t i = 0; i < 4 && x + i < W; i++) {
+                uint32_t p = d[i];
+                uint32_t sa1 = 255u - pix::ch8_mul(al[i], clr_a);
+                uint32_t o = pix::src_over_ch(p & 0xFF, color & 0xFF, al[i], sa1) |
+                             (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, al[i], sa1) << 8);
+                d[i] = (uint16_t)o;
+            }
+        }
+    }
+}
+
+// Persistent CTAs over (job, band) tiles.  Shared memory: R rows x WP i32
+// cells (i32 sums truncated to i16 at resolve are the reference's wrapping
+// i16 sums: truncation is a ring homomorphism).
+__global__ void __launch_bounds__(TILE_THREADS) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+                                                             const JobState *__restrict__ JS, Params P,
+                                                             const uint32_t *__restrict__ tile_off,
+                                                             const uint32_t *__restrict__ entries) {
+    extern __shared__ __align__(16) int32_t area[];
+    const uint32_t cells = P.R * P.WP;
+    for (uint32_t i = threadIdx.x * 4; i < cells; i += TILE_THREADS * 4) *reinterpret_cast<int4 *>(area + i) = make_int4(0, 0, 0, 0);
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5;
+    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+        const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
+        const JobState js = JS[j];
+        const int64_t row0 = (int64_t)P.row_begin + ((int64_t)band << P.log2R);
+        int64_t row_hi = row0 + P.R;
+        if (row_hi > (int64_t)P.row_end) row_hi = P.row_end;
+        if (row_hi <= (int64_t)js.first_row) continue;  // rows above the figure are untouched (fig.rs:497)
+        const JobDesc &jd = jobs[j];
+        const uint32_t e0 = tile_off[tile], ne = tile_off[tile + 1] - e0;
+        // ---- (c) scatter: one thread per (edge, row of the band) ----
+        for (uint32_t i = threadIdx.x; i < (ne << P.log2R); i += TILE_THREADS) {
+            const uint32_t rr = i & (P.R - 1);
+            const int64_t ry = row0 + rr;
+            if (ry < (int64_t)js.first_row || ry >= row_hi) continue;
+            const EdgeRec e = E[entries[e0 + (i >> P.log2R)]];
+            const int64_t r = ry + js.shift;
+            if (r < (int64_t)fx_to_i32(e.y0) || r > (int64_t)fx_to_i32(e.y1)) continue;
+            const int32_t ed = ((e.flags >> 1) & 1u) == (uint32_t)js.dir ? 1 : -1;  // fig.rs:286
+            scatter_edge_row(e, ed, (int32_t)r, area + rr * P.WP, (int32_t)P.W);
+        }
+        __syncthreads();
+        // ---- (d) resolve: one warp per row ----
+        for (uint32_t rr = warp; rr < P.R; rr += TILE_THREADS / 32) {
+            const int64_t ry = row0 + rr;
+            if (ry < (int64_t)js.first_row || ry >= row_hi) continue;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(jd.raster) + (size_t)(ry - P.row_begin) * P.pitch;
+            resolve_row(area + rr * P.WP, dst, P.W, P.fmt, jd.rule == FTL_EVENODD, jd.color);
+        }
+        __syncthreads();
+    }
+}
+
+// Kernel (d) alone, for the imgbuf.rs KATs: one CTA per row of i16 cells.
+__global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n,
+                                                             uint32_t WP, int even_odd) {
+    extern __shared__ __align__(16) int32_t area[];
+    const int16_t *s = src + (size_t)blockIdx.x * n;
+    for (uint32_t i = threadIdx.x; i < WP; i += 32) area[i] = i < n ? (int32_t)s[i] : 0;
+    __syncwarp();
+    resolve_row(area, dst + (size_t)blockIdx.x * n, n, FTL_MATTE8, even_odd != 0, 0);
+}
+
+// 64-bit FNV-1a per raster (parity checks of large batches): one CTA per
+// raster hashes 256 interleaved lanes, then lane digests are folded in order.
+__global__ void __launch_bounds__(256) fnv_rasters(const uint8_t *__restrict__ base, size_t raster_bytes, uint64_t *__restrict__ out) {
+    __shared__ uint64_t part[256];
+    const uint8_t *p = base + (size_t)blockIdx.x * raster_bytes;
+    uint64_t h = 0xcbf29ce484222325ull;
+    for (size_t i = threadIdx.x; i < raster_bytes; i += 256) h = (h ^ p[i]) * 0x100000001b3ull;
+    part[threadIdx.x] = h;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint64_t g = 0xcbf29ce484222325ull;
+        for (int i = 0; i < 256; i++)
+            for (int b = 0; b < 8; b++) g = (g ^ ((part[i] >> (8 * b)) & 0xFF)) * 0x100000001b3ull;
+        out[blockIdx.x] = g;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes, cudaStream_t st) {
+        if (bytes <= cap) return FTL_OK;
+        if (p) {
+            CK(cudaStreamSynchronize(st));
+            CK(cudaFree(p));
+            p = nullptr;
+            cap = 0;
+        }
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMalloc(&p, want));
+        cap = want;
+        return FTL_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+struct PinBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t bytes) {
+        if (bytes <= cap) return FTL_OK;
+        if (p) CK(cudaFreeHost(p));
+        p = nullptr;
+        size_t want = bytes + bytes / 4 + 256;
+        CK(cudaMallocHost(&p, want));
+        cap = want;
+        return FTL_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct ProfSpan {
+    cudaEvent_t a, b;
+};
+static std::vector<ProfSpan> g_spans;  // guarded by the single-threaded-per-process use in bench/tests
+static double g_tile_ms = 0.0;
+static uint64_t g_tile_launches = 0;
+
+struct Engine::Impl {
+    cudaStream_t st = nullptr;
+    int n_sms = 148;
+    size_t max_smem = 0;
+    DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc;
+    PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
+    // resident job set
+    Params P{};
+    bool have_jobs = false;
+    int smem_bytes = 0;
+};
+
+int Engine::device_count(int *count) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        *count = 0;
+        set_error(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return FTL_ERR_NO_DEVICE;
+    }
+    *count = n;
+    return FTL_OK;
+}
+uint64_t Engine::launch_count() { return g_launches.load(); }
+void Engine::set_profiling(bool on) { g_profiling.store(on); }
+void Engine::tile_kernel_time(bool reset, double *ms, uint64_t *launches) {
+    for (ProfSpan &s : g_spans) {
+        float t = 0.f;
+        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+            g_tile_ms += t;
+            g_tile_launches++;
+        }
+        cudaEventDestroy(s.a);
+        cudaEventDestroy(s.b);
+    }
+    g_spans.clear();
+    if (ms) *ms = g_tile_ms;
+    if (launches) *launches = g_tile_launches;
+    if (reset) {
+        g_tile_ms = 0.0;
+        g_tile_launches = 0;
+    }
+}
+
+Engine::Engine(int device) : impl_(new Impl()), device_(device), stream_(nullptr) {}
+
+Engine::~Engine() {
+    if (impl_) {
+        if (impl_->st) {
+            cudaSetDevice(device_);
+            cudaStreamSynchronize(impl_->st);
+            Impl &m = *impl_;
+            for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
+                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc})
+                b->release();
+            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc}) b->release();
+            cudaStreamDestroy(impl_->st);
+        }
+        delete impl_;
+    }
+}
+
+static int engine_init(Engine::Impl *m, int device, void **stream_out);
+
+#define ENSURE_INIT()                                                        \
+    do {                                                                     \
+        CK(cudaSetDevice(device_));                                          \
+        if (!impl_->st) {                                                    \
+            int rc_ = engine_init(impl_, device_, &stream_);                 \
+            if (rc_) return rc_;                                             \
+        }                                                                    \
+    } while (0)
+
+static int engine_init(Engine::Impl *m, int device, void **stream_out) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        set_error(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+        return FTL_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        set_error("device index out of range");
+        return FTL_ERR_INVALID;
+    }
+    CK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, device));
+    m->n_sms = prop.multiProcessorCount;
+    m->max_smem = prop.sharedMemPerBlockOptin;
+    CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
+    CK(cudaFuncSetAttribute(raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+    CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+    *stream_out = m->st;
+    return FTL_OK;
+}
+
+static inline uint32_t div_up(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+template <class Op>
+static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typename Op::T *out, DevBuf &partials) {
+    uint32_t nb = div_up(n > 0 ? n : 1, SCAN_BLOCK);
+    int rc = partials.ensure((size_t)nb * sizeof(typename Op::T), st);
+    if (rc) return rc;
+    typename Op::T *part = (typename Op::T *)partials.p;
+    scan_reduce<Op><<<nb, SCAN_THREADS, 0, st>>>(in, n, part); LAUNCHED();
+    scan_partials<Op><<<1, SCAN_THREADS, 0, st>>>(part, nb); LAUNCHED();
+    scan_apply<Op><<<nb, SCAN_THREADS, 0, st>>>(in, n, part, out); LAUNCHED();
+    CK(cudaGetLastError());
+    return FTL_OK;
+}
+
+static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
+    P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
+    P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
+    P->WP = ((g.width + 127u) & ~127u) + 4u;  // +4 cells staggers the banks of consecutive rows
+    size_t row_bytes = (size_t)P->WP * 4;
+    if (row_bytes > max_smem) {
+        set_error("raster width exceeds the shared-memory row tile");
+        return FTL_ERR_TOO_WIDE;
+    }
+    uint32_t log2R = 0;
+    while (log2R < 5 && (row_bytes << (log2R + 1)) <= 72 * 1024) log2R++;
+    while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
+    P->log2R = log2R; P->R = 1u << log2R;
+    P->n_bands = div_up(g.rows(), P->R);
+    return FTL_OK;
+}
+
+static int validate_ops(const ftl_path_op *ops, size_t n) {
+    for (size_t i = 0; i < n; i++) {
+        int nv = ops[i].tag == FTL_OP_CLOSE ? 0 : (ops[i].tag == FTL_OP_QUAD ? 4 : (ops[i].tag == FTL_OP_CUBIC ? 6 : (ops[i].tag == FTL_OP_PENWIDTH ? 1 : 2)));
+        if (ops[i].tag > FTL_OP_PENWIDTH) {
+            set_error("unknown path op tag");
+            return FTL_ERR_INVALID;
+        }
+        for (int k = 0; k < nv; k++) {
+            float f = ops[i].v[k];
+            if (!(f - f == 0.0f)) {
+                set_error("non-finite coordinate in path op");
+                return FTL_ERR_NONFINITE;
+            }
+        }
+    }
+    return FTL_OK;
+}
+
+int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (jobs.empty() || g.rows() == 0 || g.width == 0) {
+        m.have_jobs = false;
+        return FTL_OK;
+    }
+    if (n_ops >= 0x7FFFFFFFull || jobs.size() >= 0x7FFFFFFFull) {
+        set_error("too many ops/jobs for one call");
+        return FTL_ERR_INVALID;
+    }
+    int rc = validate_ops(ops, n_ops);
+    if (rc) return rc;
+    Params P{};
+    rc = choose_tiling(g, m.max_smem, &P);
+    if (rc) return rc;
+    P.n_jobs = (uint32_t)jobs.size();
+    P.n_ops = (uint32_t)n_ops;
+    uint64_t nt = (uint64_t)P.n_jobs * P.n_bands;
+    if (nt >= 0x7FFFFFFFull) {
+        set_error("too many tiles for one call");
+        return FTL_ERR_INVALID;
+    }
+    P.n_tiles = (uint32_t)nt;
+    // stage + upload ops and job descriptors
+    size_t ops_bytes = n_ops * sizeof(ftl_path_op), jobs_bytes = jobs.size() * sizeof(JobDesc);
+    if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
+    if ((rc = m.pin_jobs.ensure(jobs_bytes))) return rc;
+    // the previous call's async copies out of the pinned staging must be done before it is overwritten
+    CK(cudaStreamSynchronize(m.st));
+    if (ops_bytes) memcpy(m.pin_ops.p, ops, ops_bytes);
+    JobDesc *jd = (JobDesc *)m.pin_jobs.p;
+    for (size_t j = 0; j < jobs.size(); j++) {
+        const HostJob &h = jobs[j];
+        JobDesc d{};
+        d.op_begin = h.op_begin; d.op_end = h.op_end;
+        for (int k = 0; k < 6; k++) {
+            d.e[k] = h.e[k];
+            if (!(h.e[k] - h.e[k] == 0.0f)) {
+                set_error("non-finite transform");
+                return FTL_ERR_NONFINITE;
+            }
+        }
+        d.tol_sq = h.tol_sq;
+        d.rule = (uint32_t)h.rule;
+        d.color = (uint32_t)h.color[0] | ((uint32_t)h.color[1] << 8) | ((uint32_t)h.color[2] << 16) | ((uint32_t)h.color[3] << 24);
+        d.raster = (unsigned long long)(uintptr_t)h.raster;
+        jd[j] = d;
+    }
+    if ((rc = m.ops.ensure(ops_bytes ? ops_bytes : 1, m.st))) return rc;
+    if ((rc = m.jobs.ensure(jobs_bytes, m.st))) return rc;
+    if (ops_bytes) CK(cudaMemcpyAsync(m.ops.p, m.pin_ops.p, ops_bytes, cudaMemcpyHostToDevice, m.st));
+    CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
+    m.P = P;
+    m.smem_bytes = (int)((size_t)P.R * P.WP * 4);
+    m.have_jobs = true;
+    return FTL_OK;
+}
+
+int Engine::fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
+    int rc = upload(g, jobs, ops, n_ops);
+    if (rc) return rc;
+    return replay();
+}
+
+int Engine::replay() {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (!m.have_jobs) return FTL_OK;
+    const Params P = m.P;
+    cudaStream_t st = m.st;
+    int rc;
+    const ftl_path_op *d_ops = (const ftl_path_op *)m.ops.p;
+    const JobDesc *d_jobs = (const JobDesc *)m.jobs.p;
+    if ((rc = m.counters.ensure(sizeof(Counters), st))) return rc;
+    if ((rc = m.pin_small.ensure(64))) return rc;
+    if ((rc = m.jstate.ensure((size_t)P.n_jobs * sizeof(JobState), st))) return rc;
+    Counters *d_cnt = (Counters *)m.counters.p;
+    JobState *d_js = (JobState *)m.jstate.p;
+    init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, P.n_jobs); LAUNCHED();
+    CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
+    uint32_t nv = 0;
+    if (P.n_ops > 0) {
+        // ---- (a) flatten: count, scan, emit ----
+        if ((rc = m.cnt.ensure((size_t)P.n_ops * sizeof(SumHead), st))) return rc;
+        if ((rc = m.off.ensure(((size_t)P.n_ops + 1) * sizeof(SumHead), st))) return rc;
+        uint32_t fb = std::min<uint32_t>(div_up(P.n_ops, 128), (uint32_t)m.n_sms * 16);
+        flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
+        if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
+        CK(cudaMemcpyAsync(&d_cnt->nv, &((SumHead *)m.off.p)[P.n_ops].sum, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
+        CK(cudaMemcpyAsync(m.pin_small.p, &d_cnt->nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        nv = *(uint32_t *)m.pin_small.p;
+        if (nv > 0) {
+            if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
+            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr); LAUNCHED();
+        }
+    }
+    // ---- (b) edge prep + binning ----
+    if ((rc = m.tcount.ensure((size_t)P.n_tiles * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.toff.ensure(((size_t)P.n_tiles + 1) * sizeof(uint32_t), st))) return rc;
+    CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
+    uint32_t n_entries = 0;
+    if (nv > 0) {
+        if ((rc = m.edges.ensure((size_t)nv * sizeof(EdgeRec), st))) return rc;
+        if ((rc = m.sub_last.ensure((size_t)nv * sizeof(uint32_t), st))) return rc;
+        uint32_t vb = std::min<uint32_t>(div_up(nv, 256), (uint32_t)m.n_sms * 8);
+        vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
+        edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p, (uint32_t *)m.sub_last.p); LAUNCHED();
+        job_finalize<<<div_up(P.n_jobs, 128), 128, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (const uint32_t *)m.sub_last.p, P.n_jobs); LAUNCHED();
+        bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
+    }
+    if ((rc = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_tiles, (uint32_t *)m.toff.p, m.tpart))) return rc;
+    if (nv > 0) {
+        CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_tiles], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        n_entries = *(uint32_t *)m.pin_small.p;
+        if ((rc = m.entries.ensure((size_t)(n_entries ? n_entries : 1) * sizeof(uint32_t), st))) return rc;
+        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
+        uint32_t vb = std::min<uint32_t>(div_up(nv, 256), (uint32_t)m.n_sms * 8);
+        bin_edges<true><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
+                                            (uint32_t *)m.entries.p); LAUNCHED();
+    } else if ((rc = m.entries.ensure(sizeof(uint32_t), st))) return rc;
+    // ---- (c)+(d) tiles ----
+    int occ = 1;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_tiles, TILE_THREADS, m.smem_bytes));
+    if (occ < 1) occ = 1;
+    uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(m.n_sms * occ));
+    ProfSpan span{};
+    const bool prof = g_profiling.load();
+    if (prof) {
+        CK(cudaEventCreate(&span.a));
+        CK(cudaEventCreate(&span.b));
+        CK(cudaEventRecord(span.a, st));
+    }
+    raster_tiles<<<grid, TILE_THREADS, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
+                                                           (const uint32_t *)m.entries.p); LAUNCHED();
+    if (prof) {
+        CK(cudaEventRecord(span.b, st));
+        g_spans.push_back(span);
+    }
+    CK(cudaGetLastError());
+    return FTL_OK;
+}
+
+int Engine::last_fill_info(FillInfo *info) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    *info = FillInfo();
+    if (!m.have_jobs) return FTL_OK;
+    JobState js;
+    Counters c;
+    CK(cudaStreamSynchronize(m.st));
+    CK(cudaMemcpy(&js, m.jstate.p, sizeof(js), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&c, m.counters.p, sizeof(c), cudaMemcpyDeviceToHost));
+    info->dir = js.dir;
+    info->top_row = js.top_row;
+    info->n_points = c.nv - c.n_popped;
+    return FTL_OK;
+}
+
+int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, std::vector<int32_t> *xy,
+                          std::vector<uint32_t> *subs) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    xy->clear();
+    subs->clear();
+    if (n_ops == 0) return FTL_OK;
+    int rc = validate_ops(ops, n_ops);
+    if (rc) return rc;
+    cudaStream_t st = m.st;
+    Params P{};
+    P.n_jobs = 1;
+    P.n_ops = (uint32_t)n_ops;
+    JobDesc jd{};
+    jd.op_begin = 0; jd.op_end = (uint32_t)n_ops;
+    memcpy(jd.e, e, sizeof(jd.e));
+    jd.tol_sq = tol_sq;
+    CK(cudaStreamSynchronize(st));
+    if ((rc = m.ops.ensure(n_ops * sizeof(ftl_path_op), st))) return rc;
+    if ((rc = m.jobs.ensure(sizeof(JobDesc), st))) return rc;
+    m.have_jobs = false;  // the resident job set is clobbered
+    CK(cudaMemcpy(m.ops.p, ops, n_ops * sizeof(ftl_path_op), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.jobs.p, &jd, sizeof(jd), cudaMemcpyHostToDevice));
+    if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
+    if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
+    uint32_t fb = div_up(P.n_ops, 128);
+    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
+    if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
+    SumHead tot;
+    CK(cudaStreamSynchronize(st));
+    CK(cudaMemcpy(&tot, &((SumHead *)m.off.p)[n_ops], sizeof(tot), cudaMemcpyDeviceToHost));
+    uint32_t nv = tot.sum;
+    if (nv == 0) return FTL_OK;
+    if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
+    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr); LAUNCHED();
+    CK(cudaStreamSynchronize(st));
+    std::vector<Vtx> v(nv);
+    CK(cudaMemcpy(v.data(), m.vtx.p, (size_t)nv * sizeof(Vtx), cudaMemcpyDeviceToHost));
+    // Apply the sub-figure closing rule (fig.rs:373-383) the way edge_build sees it.
+    for (uint32_t k = 0; k < nv;) {
+        uint32_t s = k, e2 = k;
+        while (e2 + 1 < nv && v[e2 + 1].sub == s) e2++;
+        uint32_t n = e2 - s + 1;
+        if (v[e2].x == v[s].x && v[e2].y == v[s].y) n--;
+        if (n > 0) {
+            subs->push_back((uint32_t)(xy->size() / 2));
+            subs->push_back(n);
+            for (uint32_t i = 0; i < n; i++) {
+                xy->push_back(v[s + i].x);
+                xy->push_back(v[s + i].y);
+            }
+        }
+        k = e2 + 1;
+    }
+    return FTL_OK;
+}
+
+int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, const float *opw, WideFlat *out) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    out->counts.assign(n_ops, 0);
+    out->xyw.clear();
+    if (n_ops == 0) return FTL_OK;
+    int rc = validate_ops(ops, n_ops);
+    if (rc) return rc;
+    cudaStream_t st = m.st;
+    Params P{};
+    P.n_jobs = 1;
+    P.n_ops = (uint32_t)n_ops;
+    JobDesc jd{};
+    jd.op_begin = 0; jd.op_end = (uint32_t)n_ops;
+    memcpy(jd.e, e, sizeof(jd.e));
+    jd.tol_sq = tol_sq;
+    CK(cudaStreamSynchronize(st));
+    if ((rc = m.ops.ensure(n_ops * sizeof(ftl_path_op), st))) return rc;
+    if ((rc = m.jobs.ensure(sizeof(JobDesc), st))) return rc;
+    if ((rc = m.opw.ensure(n_ops * 2 * sizeof(float), st))) return rc;
+    m.have_jobs = false;
+    CK(cudaMemcpy(m.ops.p, ops, n_ops * sizeof(ftl_path_op), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.jobs.p, &jd, sizeof(jd), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(m.opw.p, opw, n_ops * 2 * sizeof(float), cudaMemcpyHostToDevice));
+    if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
+    if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
+    uint32_t fb = div_up(P.n_ops, 128);
+    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
+    if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
+    CK(cudaStreamSynchronize(st));
+    std::vector<SumHead> off(n_ops + 1);
+    CK(cudaMemcpy(off.data(), m.off.p, (n_ops + 1) * sizeof(SumHead), cudaMemcpyDeviceToHost));
+    uint32_t np = off[n_ops].sum;
+    for (size_t i = 0; i < n_ops; i++) out->counts[i] = off[i + 1].sum - off[i].sum;
+    if (np == 0) return FTL_OK;
+    if ((rc = m.wide.ensure((size_t)np * 3 * sizeof(float), st))) return rc;
+    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p); LAUNCHED();
+    CK(cudaStreamSynchronize(st));
+    out->xyw.resize((size_t)np * 3);
+    CK(cudaMemcpy(out->xyw.data(), m.wide.p, (size_t)np * 3 * sizeof(float), cudaMemcpyDeviceToHost));
+    return FTL_OK;
+}
+
+int Engine::accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (n == 0 || rows == 0) return FTL_OK;
+    uint32_t WP = (((uint32_t)n + 127u) & ~127u) + 4u;
+    if ((size_t)WP * 4 > m.max_smem) {
+        set_error("row too long for the shared-memory row tile");
+        return FTL_ERR_TOO_WIDE;
+    }
+    int rc;
+    if ((rc = m.misc.ensure(n * rows * 3, m.st))) return rc;
+    int16_t *ds = (int16_t *)m.misc.p;
+    uint8_t *dd = (uint8_t *)m.misc.p + n * rows * 2;
+    CK(cudaMemcpyAsync(ds, src, n * rows * 2, cudaMemcpyHostToDevice, m.st));
+    accumulate_rows_kernel<<<(uint32_t)rows, 32, WP * 4, m.st>>>(ds, dd, (uint32_t)n, WP, rule == FTL_EVENODD); LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dst, dd, n * rows, cudaMemcpyDeviceToHost, m.st));
+    CK(cudaStreamSynchronize(m.st));
+    return FTL_OK;
+}
+
+int Engine::checksums(const void *rasters, size_t raster_bytes, uint32_t count, uint64_t *out) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (count == 0) return FTL_OK;
+    int rc;
+    if ((rc = m.misc.ensure((size_t)count * 8, m.st))) return rc;
+    fnv_rasters<<<count, 256, 0, m.st>>>((const uint8_t *)rasters, raster_bytes, (uint64_t *)m.misc.p); LAUNCHED();
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, m.misc.p, (size_t)count * 8, cudaMemcpyDeviceToHost, m.st));
+    CK(cudaStreamSynchronize(m.st));
+    return FTL_OK;
+}
+
+int Engine::sync() {
+    ENSURE_INIT();
+    CK(cudaStreamSynchronize(impl_->st));
+    return FTL_OK;
+}
+int Engine::alloc_raster(size_t bytes, void **dptr) {
+    ENSURE_INIT();
+    CK(cudaMalloc(dptr, bytes ? bytes : 1));
+    return FTL_OK;
+}
+int Engine::free_raster(void *dptr) {
+    if (!dptr) return FTL_OK;
+    ENSURE_INIT();
+    CK(cudaStreamSynchronize(impl_->st));
+    CK(cudaFree(dptr));
+    return FTL_OK;
+}
+int Engine::memset_async(void *dptr, int value, size_t bytes) {
+    ENSURE_INIT();
+    CK(cudaMemsetAsync(dptr, value, bytes, impl_->st));
+    return FTL_OK;
+}
+int Engine::copy_in(void *dptr, const void *src, size_t bytes) {
+    ENSURE_INIT();
+    CK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, impl_->st));
+    CK(cudaStreamSynchronize(impl_->st));
+    return FTL_OK;
+}
+int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
+    ENSURE_INIT();
+    CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, impl_->st));
+    CK(cudaStreamSynchronize(impl_->st));
+    return FTL_OK;
+}
+
+}  // namespace ftl

@@ -1,0 +1,112 @@
+// engine.h — host-side interface of the device pipeline (engine.cu).
+// One Engine per handle: it owns a CUDA stream, a pinned staging area and a
+// grow-only scratch arena in HBM, and runs the four stages of the hot path
+//   (a) flatten   (b) edge prep + band binning   (c)+(d) tile raster kernel
+// for a set of jobs that share one raster geometry.
+#pragma once
+#include <stddef.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/footile_b200.h"
+
+namespace ftl {
+
+struct Geometry {
+    uint32_t width = 0, height = 0;      // full raster size
+    uint32_t row_begin = 0, row_end = 0; // rows owned by this device
+    int format = FTL_MATTE8;
+    uint32_t bpp() const { return format == FTL_MATTE8 ? 1u : (format == FTL_GRAYA8P ? 2u : 4u); }
+    uint32_t rows() const { return row_end - row_begin; }
+    size_t pitch() const { return (size_t)width * bpp(); }
+    size_t bytes() const { return pitch() * rows(); }
+};
+
+// One fill: ops[op_begin, op_end) drawn into the raster whose owned rows start
+// at device address `raster`.
+struct HostJob {
+    uint32_t op_begin = 0, op_end = 0;
+    float e[6] = {1, 0, 0, 0, 1, 0};
+    float tol_sq = 0.09f;
+    int rule = 0;
+    uint8_t color[4] = {255, 255, 255, 255};
+    void *raster = nullptr;
+};
+
+struct FillInfo {
+    int32_t dir = 0, top_row = 0;
+    uint32_t n_points = 0;
+};
+
+struct WideFlat {                 // output of the stroke-side flatten
+    std::vector<uint32_t> counts; // points emitted per op
+    std::vector<float> xyw;       // (x, y, w) per point
+};
+
+class Engine {
+public:
+    explicit Engine(int device);
+    ~Engine();
+    Engine(const Engine &) = delete;
+    Engine &operator=(const Engine &) = delete;
+
+    int device() const { return device_; }
+    void *stream() const { return stream_; }
+
+    // Fill jobs.  If `ops` is null the ops uploaded by the previous call (or by
+    // upload()) are reused from HBM.
+    int fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    // Upload only (device-resident replay).
+    int upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    int replay();
+
+    // Stroke-side flatten: raw f32 points with widths, per op (blocking).
+    // opw: per op (pen_w, s_width) computed by the host from the PenWidth ops.
+    int flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, const float *opw,
+                     WideFlat *out);
+    // Parity probes (blocking).
+    int debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops,
+                      std::vector<int32_t> *xy, std::vector<uint32_t> *subs);
+    int last_fill_info(FillInfo *info);
+    int accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows);
+    int checksums(const void *rasters, size_t raster_bytes, uint32_t count, uint64_t *out);
+
+    int sync();
+    int alloc_raster(size_t bytes, void **dptr);
+    int free_raster(void *dptr);
+    int memset_async(void *dptr, int value, size_t bytes);
+    int copy_in(void *dptr, const void *src, size_t bytes);   // blocking
+    int copy_out(void *dst, const void *dptr, size_t bytes);  // blocking
+
+    static int device_count(int *count);
+    static uint64_t launch_count();
+    static void set_profiling(bool on);
+    static void tile_kernel_time(bool reset, double *ms, uint64_t *launches);
+
+    struct Impl;
+
+private:
+    Impl *impl_;
+    int device_;
+    void *stream_;
+};
+
+void set_error(const std::string &msg);
+const char *last_error();
+
+// Host-side stroker (stroker.cpp): outline ops of a flattened wide polyline.
+// Mirrors Stroke::add_point / close / path_ops (src/stroker.rs:204-262).
+struct StrokeParams {
+    int join = FTL_JOIN_MITER;
+    float miter_limit = 4.0f;
+    float tol_sq = 0.09f;
+};
+void stroke_outline(const StrokeParams &sp, const ftl_path_op *ops, size_t n_ops, const WideFlat &flat,
+                    std::vector<ftl_path_op> *out);
+// Per-op (pen_w, s_width) from the PenWidth ops; returns the final s_width
+// (plotter.rs:128-130,151-153,233-236,293-298).
+float stroke_widths(float s_width, const ftl_path_op *ops, size_t n_ops, std::vector<float> *opw);
+
+}  // namespace ftl

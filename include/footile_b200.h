@@ -1,0 +1,173 @@
+/* footile_b200.h — C ABI of the B200-native footile hot path.
+ *
+ * The reference (DougLau/footile, Rust) has no FFI: its seams are Rust method
+ * calls.  Every entry point below names the reference interface it replaces
+ * (file:line under the reference tree).  A Rust `extern "C"` shim binding
+ * these is shown in INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++ or torch types cross this ABI;
+ *   - every function returns an ftl_status (0 = OK) and never unwinds;
+ *     ftl_last_error() returns a thread-local message for the last failure;
+ *   - the raster lives in device memory (HBM) owned by the handle; host
+ *     pixels are copied in at creation / ftl_write_raster and out at
+ *     ftl_read_raster (the only blocking points besides ftl_sync);
+ *   - a handle is used from one thread at a time (the reference takes
+ *     `&mut self` on every drawing call); distinct handles are independent;
+ *   - there is NO CPU fallback: without a CUDA device every compute entry
+ *     point fails with FTL_ERR_NO_DEVICE.
+ */
+#ifndef FOOTILE_B200_H
+#define FOOTILE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FTL_ABI_VERSION 1
+
+/* ---- vocabulary -------------------------------------------------------- */
+
+/* PathOp (src/path.rs:18-31). v holds up to three points (x,y) or the pen width:
+ *   Close: -, Move/Line: v[0..1], Quad: v[0..3], Cubic: v[0..5], PenWidth: v[0]. */
+typedef struct ftl_path_op {
+    uint32_t tag;
+    float v[6];
+} ftl_path_op;
+
+enum ftl_op_tag { FTL_OP_CLOSE = 0, FTL_OP_MOVE = 1, FTL_OP_LINE = 2, FTL_OP_QUAD = 3, FTL_OP_CUBIC = 4, FTL_OP_PENWIDTH = 5 };
+
+/* FillRule (src/path.rs:9-14) */
+enum ftl_fill_rule { FTL_NONZERO = 0, FTL_EVENODD = 1 };
+
+/* JoinStyle (src/stroker.rs:13-20); the miter limit travels beside it. */
+enum ftl_join { FTL_JOIN_MITER = 0, FTL_JOIN_BEVEL = 1, FTL_JOIN_ROUND = 2 };
+
+/* Pixel formats of the generic bound P: Pixel<Chan=Ch8, Alpha=Premultiplied,
+ * Gamma=Linear> (src/plotter.rs:38-41) that the reference is used with:
+ * pix::matte::Matte8 (1 B), pix::gray::Graya8p (2 B: gray, alpha),
+ * pix::rgb::Rgba8p (4 B: r, g, b, a).  Row-major, pitch = width * bpp. */
+enum ftl_format { FTL_MATTE8 = 0, FTL_GRAYA8P = 1, FTL_RGBA8P = 2 };
+
+typedef enum ftl_status {
+    FTL_OK = 0,
+    FTL_ERR_INVALID = 1,     /* bad argument */
+    FTL_ERR_NO_DEVICE = 2,   /* no CUDA device / driver: there is no CPU fallback */
+    FTL_ERR_CUDA = 3,        /* CUDA runtime failure, see ftl_last_error() */
+    FTL_ERR_NOMEM = 4,
+    FTL_ERR_NONFINITE = 5,   /* NaN/Inf in a path op or transform (the reference recurses without bound: README.md:32-33) */
+    FTL_ERR_TOO_WIDE = 6     /* raster row does not fit the shared-memory row tile */
+} ftl_status;
+
+typedef struct ftl_plotter ftl_plotter; /* Plotter<P> (src/plotter.rs:38-56) */
+typedef struct ftl_batch ftl_batch;     /* N independent Plotter<P>s of one size, driven together */
+
+/* ---- library ----------------------------------------------------------- */
+int ftl_abi_version(void);
+const char *ftl_last_error(void);
+int ftl_device_count(int *count);
+
+/* ---- Plotter (src/plotter.rs:96-380) ------------------------------------ */
+
+/* Plotter::new(raster) (plotter.rs:96-115).  init_pixels: width*height*bpp host
+ * bytes (Raster::with_pixels / with_color), or NULL for Raster::with_clear. */
+int ftl_plotter_new(uint32_t width, uint32_t height, int format, const void *init_pixels, int device,
+                    ftl_plotter **out);
+/* Row-band variant for one raster split across GPUs: this handle owns rows
+ * [row_begin, row_end) of a width x height raster; init_pixels / read_raster
+ * cover only those rows.  Extension beyond the reference (which only loops
+ * rows: fig.rs:539); results equal the same rows of the unsplit fill. */
+int ftl_plotter_new_band(uint32_t width, uint32_t height, uint32_t row_begin, uint32_t row_end, int format,
+                         const void *init_pixels, int device, ftl_plotter **out);
+int ftl_plotter_free(ftl_plotter *p);                       /* drop(Plotter) */
+uint32_t ftl_width(const ftl_plotter *p);                   /* Plotter::width  (plotter.rs:118-120) */
+uint32_t ftl_height(const ftl_plotter *p);                  /* Plotter::height (plotter.rs:123-125) */
+int ftl_set_tolerance(ftl_plotter *p, float t);             /* Plotter::set_tolerance, clamped >= 0.01 (plotter.rs:133-137) */
+int ftl_set_transform(ftl_plotter *p, const float e[6]);    /* Plotter::set_transform (plotter.rs:140-143); e = pointy Transform rows [a b tx; c d ty] */
+int ftl_set_join(ftl_plotter *p, int join, float miter_limit); /* Plotter::set_join (plotter.rs:158-161) */
+float ftl_pen_width(const ftl_plotter *p);                  /* the persistent s_width (plotter.rs:53,151-153) */
+
+/* Plotter::fill(rule, ops, clr) (plotter.rs:339-350).  color: bpp bytes
+ * (premultiplied); ignored for FTL_MATTE8 exactly as the reference ignores it
+ * (fig.rs:632-636).  Asynchronous on the handle's stream. */
+int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
+/* Plotter::stroke(ops, clr) (plotter.rs:356-365). */
+int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
+
+/* Plotter::raster() / into_raster() (plotter.rs:368-380): synchronise and copy
+ * the owned rows to host memory.  nbytes must equal rows*width*bpp. */
+int ftl_read_raster(ftl_plotter *p, void *dst, size_t nbytes);
+/* Plotter::raster_mut() (plotter.rs:373-375): replace the owned rows. */
+int ftl_write_raster(ftl_plotter *p, const void *src, size_t nbytes);
+int ftl_sync(ftl_plotter *p);
+/* Zero-copy interop: device pointer of the owned rows (valid until free). */
+int ftl_raster_device_ptr(ftl_plotter *p, void **dptr, size_t *nbytes);
+
+/* ---- Batch: many fills per launch -------------------------------------- */
+/* The reference draws one path per Plotter::fill call on one core; callers
+ * that draw many independent paths (benches/fishyb.rs:18-20 allocates a raster
+ * and a plotter per iteration) loop.  A batch is `capacity` rasters of one
+ * size and format, resident in HBM, filled by ONE pass of the device pipeline.
+ * Job j = ops[op_offsets[j] .. op_offsets[j+1]) drawn into raster j with
+ * rules[j] (or rule 0 if NULL), transforms[6*j..] (or the identity if NULL),
+ * colors[4*j..] (or opaque white if NULL).  Equivalent to n_jobs independent
+ * `Plotter::new(raster_j).set_transform(..).fill(..)` calls. */
+int ftl_batch_new(uint32_t width, uint32_t height, int format, uint32_t capacity, int device, ftl_batch **out);
+int ftl_batch_free(ftl_batch *b);
+int ftl_batch_set_tolerance(ftl_batch *b, float t);
+/* Raster::with_clear for rasters [first, first+count) (zero them). */
+int ftl_batch_clear(ftl_batch *b, uint32_t first, uint32_t count);
+int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets,
+                   const uint8_t *rules, const float *transforms, const uint8_t *colors);
+/* Copy rasters [first, first+count) to host (blocking). */
+int ftl_batch_read(ftl_batch *b, uint32_t first, uint32_t count, void *dst, size_t nbytes);
+/* 64-bit FNV-1a of each raster's bytes, computed on the device (blocking). */
+int ftl_batch_checksums(ftl_batch *b, uint32_t first, uint32_t count, uint64_t *out);
+int ftl_batch_sync(ftl_batch *b);
+int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes);
+
+/* ---- Device-resident replay (bench `value` leg: inputs already in HBM) ---- */
+/* Upload the jobs of a batch once; ftl_batch_run() then repeats the device
+ * pipeline on the resident ops without touching host memory. */
+int ftl_batch_upload(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets,
+                     const uint8_t *rules, const float *transforms, const uint8_t *colors);
+int ftl_batch_run(ftl_batch *b);
+
+/* ---- Instrumentation ---------------------------------------------------- */
+/* Number of kernel launches issued by this library since load (all handles). */
+uint64_t ftl_launch_count(void);
+/* Device time (ms) and launch count of the raster-tile kernel (scatter + row
+ * scan + fill rule + store/blend) accumulated since the last call with
+ * reset != 0.  Measured with CUDA events on the handle's stream when
+ * profiling is enabled via ftl_set_profiling(1) (adds two event records per
+ * launch; off by default). */
+int ftl_set_profiling(int enabled);
+int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches);
+
+/* ---- Parity probes (used by tests only) --------------------------------- */
+/* Flattened Fixed points of a fill after point intake (fig.rs:428-461):
+ * returns the count via *n_points and writes up to cap (x,y) i32 pairs; subs
+ * receives up to sub_cap (start,len) pairs.  Blocking. */
+int ftl_debug_flatten(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, int32_t *xy, size_t cap,
+                      size_t *n_points, uint32_t *subs, size_t sub_cap, size_t *n_subs);
+/* (dir, top_row, n_points) of the last fill (fig.rs:495-496); dir 0 = Forward. */
+int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]);
+/* The outline ops Plotter::stroke hands to fill (stroker.rs:239-247). */
+int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
+                         size_t *n_out);
+/* The host stroker alone (stroker.rs:204-416) on an already flattened wide
+ * polyline: counts[i] points of op i, xyw = (x, y, width) per point.  Pure
+ * host code; needs no device. */
+int ftl_debug_stroke_outline(int join, float miter_limit, float tol_sq, const ftl_path_op *ops, size_t n_ops,
+                             const uint32_t *counts, const float *xyw, ftl_path_op *out, size_t cap, size_t *n_out);
+/* Row accumulate alone (imgbuf.rs:38-51,141-154): dst[i] = rule(prefix sum of
+ * src[0..i]) over n i16 cells per row, rows independent.  Host buffers. */
+int ftl_debug_accumulate(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows, int device);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FOOTILE_B200_H */

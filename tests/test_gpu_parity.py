@@ -1,0 +1,430 @@
+"""GPU parity: the CUDA path (through the C ABI) against the CPU oracle.
+
+Bit-exact everywhere: Fixed vertices, (dir, top_row), Matte8 bytes, and also
+Graya8p / Rgba8p pixels (the north_star tolerance for composited pixels is
++-1 LSB; both sides implement the same recalled pix arithmetic, so the tests
+assert equality and would report the max deviation if it ever appeared).
+"""
+import numpy as np
+import pytest
+
+import oracle
+from footile_b200 import Batch, FillRule, Format, JoinStyle, Path2D, PathOp, Plotter, Raster, debug_accumulate, scenes
+from footile_b200.path import OP_DTYPE, OpTag
+
+pytestmark = pytest.mark.gpu
+
+FMT = {Format.Matte8: oracle.MATTE8, Format.Graya8p: oracle.GRAYA8P, Format.Rgba8p: oracle.RGBA8P}
+
+
+def both(w, h, fmt, init=None, transform=None, tol=None, join=None, **okw):
+    ras = Raster(w, h, fmt, init)
+    g = Plotter(ras)
+    o = oracle.Plotter(w, h, FMT[fmt], init=None if init is None else ras.pixels, **okw)
+    if transform is not None:
+        g.set_transform(transform)
+        o.set_transform(transform)
+    if tol is not None:
+        g.set_tolerance(tol)
+        o.set_tolerance(tol)
+    if join is not None:
+        g.set_join(join)
+        o.set_join(join.kind, join.limit)
+    return g, o
+
+
+def assert_same(g, o, what=""):
+    a, b = g.raster().pixels, o.raster()
+    if not np.array_equal(a, b):
+        d = np.abs(a.astype(int) - b.astype(int))
+        ys, xs = np.nonzero(d)
+        raise AssertionError("%s: %d bytes differ, max |d|=%d, first at row %d byte %d (gpu %d, oracle %d)" % (
+            what, len(ys), d.max(), ys[0], xs[0], a[ys[0], xs[0]], b[ys[0], xs[0]]))
+
+
+def poly(points, close=True):
+    p = Path2D().absolute().move_to(*points[0])
+    for q in points[1:]:
+        p = p.line_to(*q)
+    if close:
+        p = p.close()
+    return p.finish()
+
+
+# ---- kernel (d) alone: imgbuf.rs KATs --------------------------------------
+def test_accumulate_kats():  # imgbuf.rs:205-232
+    b = np.zeros(3000, dtype=np.int16); b[0] = 200
+    assert (debug_accumulate(FillRule.NonZero, b) == 200).all()
+    d = np.zeros(5000, dtype=np.int16); d[0] = 300
+    assert (debug_accumulate(FillRule.NonZero, d) == 255).all()
+    e = np.zeros(3000, dtype=np.int16); e[0] = 300
+    assert (debug_accumulate(FillRule.EvenOdd, e) == 212).all()
+
+
+def test_accumulate_random_rows_vs_oracle():
+    rng = np.random.default_rng(5)
+    for n in (1, 3, 8, 100, 127, 128, 129, 1000, 4096, 5001):
+        src = rng.integers(-600, 600, (7, n)).astype(np.int16)
+        src[rng.random((7, n)) < 0.7] = 0
+        src[0, 0] = 32767  # forces i16 wrap-around in the running sum
+        src[0, n // 2] = 32767
+        for rule in (FillRule.NonZero, FillRule.EvenOdd):
+            got = debug_accumulate(rule, src)
+            for r in range(7):
+                exp, _ = oracle.accumulate(int(rule), src[r], simd=True)
+                assert np.array_equal(got[r], exp), (n, rule, r)
+
+
+# ---- fig.rs raster KATs through the full device pipeline -------------------
+KATS = [  # (w, h, points, expected) — src/fig.rs:723-794
+    (9, 1, [(0, 0), (9, 1), (0, 1)], [242, 213, 185, 156, 128, 100, 71, 43, 14]),
+    (3, 3, [(-1, 0), (-1, 3), (3, 1.5)], [112, 16, 0, 255, 224, 32, 112, 16, 0]),
+    (1, 3, [(0.5, 0), (0.5, 1.5), (1, 3), (1, 0)], [128, 117, 43]),
+    (3, 3, [(1.5, 0), (1.5, 1.5), (2, 3), (3, 3), (3, 0)], [0, 128, 255, 0, 117, 255, 0, 43, 255]),
+    (9, 1, [(0, 0), (0, 0.3), (9, 0)], [73, 64, 56, 47, 39, 30, 22, 13, 4]),
+]
+
+
+@pytest.mark.parametrize("w,h,pts,exp", KATS)
+def test_fig_kats(w, h, pts, exp):
+    g = Plotter(Raster(w, h, Format.Matte8))
+    g.fill(FillRule.NonZero, poly(pts, close=False), (255,))
+    assert g.raster().as_u8_slice().tolist() == exp
+
+
+def test_fig_3x3_rgba():  # fig.rs:702-721
+    g = Plotter(Raster(3, 3, Format.Rgba8p))
+    g.fill(FillRule.NonZero, poly([(1, 2), (1, 3), (2, 3), (2, 2)], close=False), (99, 99, 99, 255))
+    exp = np.zeros((3, 12), dtype=np.uint8)
+    exp[2, 4:8] = (99, 99, 99, 255)
+    assert np.array_equal(g.raster().pixels, exp)
+
+
+def test_plotter_overlapping():  # plotter.rs:389-403 (smoke in the reference; compared with the oracle here)
+    path = (Path2D().absolute().move_to(8.0, 4.0).line_to(8.0, 3.0).cubic_to(8.0, 3.0, 8.0, 3.0, 9.0, 3.75)
+            .line_to(8.0, 3.75).line_to(8.5, 3.75).line_to(8.5, 3.5).finish())
+    g, o = both(16, 16, Format.Matte8)
+    g.fill(FillRule.NonZero, path, (255,))
+    o.fill(oracle.NONZERO, path, (255,))
+    assert_same(g, o)
+
+
+# ---- (a) flattening: Fixed vertices bit-exact -------------------------------
+def random_path(rng, size, n_seg, closed_prob=0.5):
+    p = Path2D().absolute()
+    p = p.move_to(*rng.uniform(0, size, 2))
+    for _ in range(n_seg):
+        k = rng.integers(0, 6)
+        if k == 0:
+            p = p.line_to(*rng.uniform(-0.2 * size, 1.2 * size, 2))
+        elif k in (1, 2):
+            p = p.quad_to(*rng.uniform(-0.2 * size, 1.2 * size, 4))
+        elif k in (3, 4):
+            p = p.cubic_to(*rng.uniform(-0.2 * size, 1.2 * size, 6))
+        else:
+            if rng.random() < closed_prob:
+                p = p.close()
+            if rng.random() < 0.7:
+                p = p.move_to(*rng.uniform(0, size, 2))
+    return p.finish()
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_flatten_vertices_bit_exact(seed):
+    rng = np.random.default_rng(100 + seed)
+    size = [16, 64, 256, 1024, 4096, 20000][seed]
+    tr = [None, [2, 0, 0, 0, 2, 0], [0.7, -0.3, 5.5, 0.2, 1.3, -3.25]][seed % 3]
+    tol = [None, 0.01, 1.0][seed % 3]
+    g, o = both(32, 32, Format.Matte8, transform=tr, tol=tol, vid_cap=1 << 30)
+    for _ in range(8):
+        ops = random_path(rng, size, int(rng.integers(1, 40)))
+        gx, gs = g.debug_flatten(ops)
+        ox, os_ = o.debug_flatten(ops)
+        assert np.array_equal(gs, os_)
+        assert np.array_equal(gx, ox)
+
+
+def test_flatten_degenerate_sequences():
+    # de-dup, closing-point pop, Move/Move, Line right after Close, leading Close
+    cases = [
+        [PathOp.Move(1, 1), PathOp.Move(2, 2), PathOp.Line(5, 2), PathOp.Line(5, 2), PathOp.Line(2, 9), PathOp.Line(2, 2)],
+        [PathOp.Close(), PathOp.Line(3, 3), PathOp.Line(9, 3), PathOp.Line(9, 9), PathOp.Close(), PathOp.Line(4, 1), PathOp.Line(7, 5)],
+        [PathOp.Move(1, 1), PathOp.Close(), PathOp.Close(), PathOp.Quad(5, 0, 9, 9), PathOp.PenWidth(3), PathOp.Cubic(1, 9, 0, 5, 0, 0)],
+        [PathOp.Line(4, 4)],
+        [PathOp.Move(4, 4)],
+        [PathOp.PenWidth(2.0)],
+        [PathOp.Move(0, 0), PathOp.Cubic(0, 0, 0, 0, 0, 0), PathOp.Line(0, 0), PathOp.Close()],
+        [PathOp.Move(2, 2), PathOp.Line(6, 2), PathOp.Line(6, 6), PathOp.Line(2, 2), PathOp.Line(2, 2), PathOp.Move(1, 1), PathOp.Line(1, 7), PathOp.Line(3, 7)],
+    ]
+    for ops in cases:
+        g, o = both(12, 12, Format.Matte8)
+        gx, gs = g.debug_flatten(ops)
+        ox, os_ = o.debug_flatten(ops)
+        assert np.array_equal(gs, os_) and np.array_equal(gx, ox), ops
+        g.fill(FillRule.NonZero, ops, (255,))
+        o.fill(oracle.NONZERO, ops, (255,))
+        assert_same(g, o, str(ops))
+        assert g.debug_last_fill() == o.last_info() or o.last_info()["n_points"] == 0
+
+
+def test_empty_and_noop_paths():
+    init = np.full((5, 7), 9, dtype=np.uint8)
+    g = Plotter(Raster(7, 5, Format.Matte8, init))
+    g.fill(FillRule.NonZero, [], (255,))
+    g.fill(FillRule.EvenOdd, [PathOp.Move(3, 3)], (255,))  # single point: popped, nothing drawn (fig.rs:491)
+    assert np.array_equal(g.raster().pixels, init)
+
+
+# ---- (b)+(c)+(d): random figures, all formats, both rules -------------------
+@pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p, Format.Graya8p])
+def test_random_polygons_vs_oracle(fmt):
+    rng = np.random.default_rng(7 + int(fmt))
+    for it in range(60):
+        w = int(rng.choice([1, 3, 8, 17, 40, 130, 257]))
+        h = int(rng.choice([1, 3, 8, 17, 40, 97]))
+        bpp = {Format.Matte8: 1, Format.Graya8p: 2, Format.Rgba8p: 4}[fmt]
+        init = rng.integers(0, 256, (h, w * bpp)).astype(np.uint8)
+        g, o = both(w, h, fmt, init=init)
+        for layer in range(2):
+            ops = []
+            for _ in range(int(rng.integers(1, 4))):
+                n = int(rng.integers(1, 9))
+                snap = rng.random() < 0.4
+                pts = np.stack([rng.uniform(-w, 2 * w, n), rng.uniform(-h / 2, 1.5 * h, n)], axis=1)
+                if snap:
+                    pts = np.round(pts * 2) / 2
+                ops += list(poly([tuple(p) for p in pts], close=rng.random() < 0.7))
+            rule = int(rng.integers(0, 2))
+            clr = rng.integers(0, 256, 4).astype(np.uint8)
+            clr[:3] = np.minimum(clr[:3], clr[3])
+            if fmt == Format.Graya8p:
+                clr[0] = min(clr[0], clr[1])
+            g.fill(rule, ops, clr)
+            o.fill(rule, ops, clr)
+            assert g.debug_last_fill() == o.last_info()
+            assert_same(g, o, "it %d layer %d" % (it, layer))
+
+
+def test_negative_top_row_shift():
+    ops = poly([(1.0, -2.5), (6.0, 3.0), (0.5, 5.0)])
+    g, o = both(8, 8, Format.Matte8)
+    g.fill(FillRule.NonZero, ops, (255,))
+    o.fill(oracle.NONZERO, ops, (255,))
+    assert g.debug_last_fill()["top_row"] == -3
+    assert_same(g, o)
+
+
+def test_rows_above_top_untouched_and_below_overwritten():
+    init = np.full((16, 16), 77, dtype=np.uint8)
+    g, o = both(16, 16, Format.Matte8, init=init)
+    ops = poly([(4, 5.5), (12, 6), (8, 9)])
+    g.fill(FillRule.NonZero, ops, (255,))
+    o.fill(oracle.NONZERO, ops, (255,))
+    r = g.raster().pixels
+    assert (r[:5] == 77).all() and (r[10:] == 0).all()
+    assert_same(g, o)
+
+
+@pytest.mark.parametrize("rule", [FillRule.NonZero, FillRule.EvenOdd])
+def test_curved_paths_vs_oracle(rule):
+    rng = np.random.default_rng(31 + int(rule))
+    for size in (64, 200, 512):
+        for _ in range(6):
+            ops = random_path(rng, size, int(rng.integers(3, 30)))
+            g, o = both(size, size, Format.Matte8)
+            g.fill(rule, ops, (255,))
+            o.fill(int(rule), ops, (255,))
+            assert g.debug_last_fill() == o.last_info()
+            assert_same(g, o)
+
+
+# ---- config 1: fishy --------------------------------------------------------
+def test_config1_fishy_example_rgba():  # examples/fishy.rs:9-31
+    fish, eye = scenes.fishy_example()
+    g, o = both(128, 128, Format.Rgba8p)
+    for p in (g, o):
+        p.fill(0, fish, (127, 96, 96, 255))
+        p.stroke(fish, (255, 208, 208, 255))
+        p.stroke(eye, (0, 0, 0, 255))
+    assert_same(g, o)
+    assert g.raster().pixels.any()
+    assert g.pen_width() == o.pen_width() == 2.0  # PenWidth persists (plotter.rs:151-153)
+
+
+@pytest.mark.parametrize("size", [16, 256])
+def test_config1_fishy_bench(size):  # benches/fishyb.rs:10-39 (scale 2; stroke exercises the double transform)
+    path = scenes.fishy_bench()
+    g, o = both(size, size, Format.Matte8, transform=[2, 0, 0, 0, 2, 0])
+    g.fill(FillRule.NonZero, path, (255,))
+    o.fill(oracle.NONZERO, path, (255,))
+    assert_same(g, o, "fill")
+    g, o = both(size, size, Format.Matte8, transform=[2, 0, 0, 0, 2, 0])
+    g.stroke(path, (255,))
+    o.stroke(path, (255,))
+    assert_same(g, o, "stroke")
+
+
+# ---- config 2: heptagram -----------------------------------------------------
+@pytest.mark.parametrize("rule", [FillRule.NonZero, FillRule.EvenOdd])
+@pytest.mark.parametrize("size", [100, 4096])
+def test_config2_heptagram(rule, size):
+    path = scenes.heptagram_abs()
+    tr = scenes.heptagram_transform(size)
+    g, o = both(size, size, Format.Matte8, transform=tr)
+    g.fill(rule, path, (255,))
+    o.fill(int(rule), path, (255,))
+    assert g.debug_last_fill() == o.last_info()
+    assert_same(g, o)
+    r = g.raster().pixels
+    assert r.max() == 255 and (r[: g.debug_last_fill()["top_row"]] == 0).all()
+
+
+def test_config2_heptagram_example_relative():  # examples/heptagram.rs:12-24 (relative builder, EvenOdd, 100x100)
+    path = scenes.heptagram()
+    g, o = both(100, 100, Format.Matte8, transform=[50, 0, 25, 0, 50, 25])
+    g.fill(FillRule.EvenOdd, path, (255,))
+    o.fill(oracle.EVENODD, path, (255,))
+    assert_same(g, o)
+
+
+# ---- config 3: strokes --------------------------------------------------------
+@pytest.mark.parametrize("join", [JoinStyle.Miter(4.0), JoinStyle.Bevel, JoinStyle.Round])
+def test_config3_stroke_scenes_small(join):  # examples/*.rs at their own size
+    for name, path in scenes.stroke_scenes(1.0).items():
+        g, o = both(128, 128, Format.Matte8, join=join)
+        go = g.debug_stroke_ops(path)
+        oo = o.debug_stroke_ops(path)
+        assert len(go) == len(oo) and go.tobytes() == oo.tobytes(), name
+        g.stroke(path, (255,))
+        o.stroke(path, (255,))
+        assert_same(g, o, name)
+        assert g.raster().pixels.any(), name
+
+
+@pytest.mark.parametrize("join", [JoinStyle.Round, JoinStyle.Miter(4.0)])
+def test_config3_strokes_4k_rgba(join):  # 3840x2160 Rgba8p over (64,128,64,255), scenes x30
+    w, h = 3840, 2160
+    base = Raster.with_color(w, h, Format.Rgba8p, (64, 128, 64, 255)).pixels
+    g, o = both(w, h, Format.Rgba8p, init=base, join=join)
+    for name, path in scenes.stroke_scenes(30.0).items():
+        g.stroke(path, (255, 255, 0, 255))
+        o.stroke(path, (255, 255, 0, 255))
+    assert_same(g, o)
+
+
+# ---- config 4: batch of random curve paths -------------------------------------
+def fnv_expected(img):
+    """Host replica of ftl_batch_checksums: 256 interleaved FNV-1a lanes folded in order."""
+    b = np.ascontiguousarray(img).ravel()
+    assert b.size % 256 == 0
+    lanes = b.reshape(-1, 256).astype(np.uint64)
+    h = np.full(256, 0xcbf29ce484222325, dtype=np.uint64)
+    prime = np.uint64(0x100000001b3)
+    with np.errstate(over="ignore"):
+        for row in lanes:
+            h = (h ^ row) * prime
+        g = np.uint64(0xcbf29ce484222325)
+        for v in h:
+            for k in range(8):
+                g = (g ^ ((v >> np.uint64(8 * k)) & np.uint64(0xFF))) * prime
+    return int(g)
+
+
+def test_config4_batch_matches_oracle():
+    n, size = 48, 512
+    ops, offs, rules = scenes.random_curve_paths(1000, n)
+    b = Batch(size, size, Format.Matte8, n)
+    b.fill(ops, offs, rules=rules)
+    got = b.read()
+    sums = b.checksums()
+    for j in range(n):
+        o = oracle.Plotter(size, size, oracle.MATTE8)
+        o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
+        exp = o.raster()
+        assert np.array_equal(got[j], exp), "path %d" % j
+        if j % 8 == 0:
+            assert int(sums[j]) == fnv_expected(exp)
+    assert got.any()
+
+
+def test_config4_batch_transforms_colors_rgba():
+    n, size = 12, 64
+    rng = np.random.default_rng(3)
+    paths = [random_path(rng, size, 12) for _ in range(n)]
+    ops, offs = Batch.pack(paths)
+    rules = rng.integers(0, 2, n).astype(np.uint8)
+    tr = np.tile(np.array([1, 0, 0, 0, 1, 0], dtype=np.float32), (n, 1))
+    tr[:, 2] = rng.uniform(-5, 5, n)
+    tr[:, 0] = rng.uniform(0.5, 1.5, n)
+    colors = rng.integers(0, 256, (n, 4)).astype(np.uint8)
+    colors[:, :3] = np.minimum(colors[:, :3], colors[:, 3:4])
+    b = Batch(size, size, Format.Rgba8p, n)
+    b.fill(ops, offs, rules=rules, transforms=tr, colors=colors)
+    got = b.read()
+    for j in range(n):
+        o = oracle.Plotter(size, size, oracle.RGBA8P)
+        o.set_transform(tr[j])
+        o.fill(int(rules[j]), paths[j], colors[j])
+        assert np.array_equal(got[j], o.raster()), j
+
+
+def test_batch_replay_is_idempotent_for_matte():
+    ops, offs, rules = scenes.random_curve_paths(5, 4, segments=8, size=128)
+    b = Batch(128, 128, Format.Matte8, 4)
+    b.upload(ops, offs, rules=rules)
+    b.run()
+    first = b.read().copy()
+    b.run().run()
+    assert np.array_equal(first, b.read())
+
+
+# ---- config 5: many sub-figures in one fill, row bands ---------------------------
+def test_config5_many_subfigures_and_bands():
+    size, n_poly = 2048, 600
+    ops = scenes.random_polygons(0, n_poly, vertices=64, size=size, extent=256)
+    for rule in (FillRule.NonZero, FillRule.EvenOdd):
+        o = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True)
+        o.fill(int(rule), ops, (255,))
+        exp = o.raster()
+        g = Plotter(Raster(size, size, Format.Matte8))
+        g.fill(rule, ops, (255,))
+        assert g.debug_last_fill() == o.last_info()
+        assert np.array_equal(g.raster().pixels, exp)
+        # the same fill split into 4 row bands, each on its own handle (the multi-GPU layout)
+        for k in range(4):
+            r0, r1 = k * size // 4, (k + 1) * size // 4
+            gb = Plotter(Raster(size, size, Format.Matte8), rows=(r0, r1))
+            gb.fill(rule, ops, (255,))
+            assert np.array_equal(gb.raster().pixels, exp[r0:r1]), (rule, k)
+
+
+def test_sequential_oracle_agrees_on_many_subfigures():
+    size = 512
+    ops = scenes.random_polygons(7, 40, vertices=16, size=size, extent=128)
+    a = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True).fill(0, ops, (255,)).raster()
+    b = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=False).fill(0, ops, (255,)).raster()
+    assert np.array_equal(a, b)
+
+
+# ---- wide raster (single row tile per CTA) ---------------------------------------
+def test_wide_raster_32768():
+    w, h = 32768, 24
+    ops = poly([(100.5, 1.25), (32000.0, 3.0), (16000.0, 22.5), (5.0, 20.0)])
+    g, o = both(w, h, Format.Matte8)
+    g.fill(FillRule.NonZero, ops, (255,))
+    o.fill(oracle.NONZERO, ops, (255,))
+    assert_same(g, o)
+
+
+def test_error_paths():
+    from footile_b200 import FootileError
+    g = Plotter(Raster(8, 8, Format.Matte8))
+    with pytest.raises(FootileError):
+        g.fill(FillRule.NonZero, [PathOp.Move(float("nan"), 0), PathOp.Line(1, 1)], (255,))
+    with pytest.raises(FootileError):
+        g.set_transform([float("inf"), 0, 0, 0, 1, 0])
+    with pytest.raises(FootileError):
+        g.fill(7, [PathOp.Move(0, 0)], (255,))
+    g.set_tolerance(-5.0)  # clamps to 0.01 like the reference (plotter.rs:133-137)
+    g.fill(FillRule.NonZero, poly([(1, 1), (6, 1), (3, 6)]), (255,))
+    assert g.raster().pixels.any()

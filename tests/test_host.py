@@ -1,0 +1,136 @@
+"""CPU-side tests: the C-ABI library loads and exports every declared symbol, the host-side path
+vocabulary and stroker behave like the reference's, and compute entry points fail loudly without a GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+import oracle
+import footile_b200 as fb
+from footile_b200 import _lib, scenes
+from footile_b200.path import OP_DTYPE, OpTag, Path2D, PathOp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    try:
+        import torch
+        return torch.cuda.is_available()
+    except Exception:
+        return False
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "footile_b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(ftl_[a-z0-9_]+)\s*\(", hdr))
+    assert declared, "no declarations found"
+    L = C.CDLL(_lib.LIB_PATH)
+    for name in sorted(declared):
+        assert hasattr(L, name), "libfootile_b200.so does not export %s" % name
+    assert declared == set(_lib.SYMBOLS)
+    assert _lib.lib().ftl_abi_version() == 1
+
+
+def test_no_cpu_fallback():
+    if _has_gpu():
+        pytest.skip("GPU present")
+    with pytest.raises(fb.FootileError) as e:
+        fb.Plotter(fb.Raster(8, 8))
+    assert e.value.status == 2  # FTL_ERR_NO_DEVICE
+    with pytest.raises(fb.FootileError):
+        fb.device_count()
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "footile_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(import|from)\s+oracle\b", src, flags=re.M), "%s imports the oracle" % f
+                assert not re.search(r"#include[^\n]*oracle|libfootile_oracle|orc_[a-z_]+\s*\(", src), "%s links the oracle" % f
+
+
+def test_op_layout_matches_header():
+    assert OP_DTYPE.itemsize == 28
+    assert OP_DTYPE.fields["tag"][1] == 0 and OP_DTYPE.fields["v"][1] == 4
+    assert [int(t) for t in OpTag] == [0, 1, 2, 3, 4, 5]
+
+
+def test_path2d_relative_absolute_close():  # path.rs:64-171
+    p = (Path2D().move_to(10, 10).line_to(5, 0).quad_to(1, 1, 2, 0).close().line_to(3, 4)
+         .absolute().cubic_to(1, 2, 3, 4, 5, 6).pen_width(2.5).finish())
+    assert [int(t) for t in p["tag"]] == [1, 2, 3, 0, 2, 4, 5]
+    assert p["v"][1][:2].tolist() == [15, 10]          # relative to the pen
+    assert p["v"][2][:4].tolist() == [16, 11, 17, 10]  # both points relative to the same pen
+    assert p["v"][4][:2].tolist() == [3, 4]            # close() moved the builder pen to the origin
+    assert p["v"][5][:6].tolist() == [1, 2, 3, 4, 5, 6]
+    assert p["v"][6][0] == 2.5
+
+
+def test_path2d_doc_example():  # lib.rs:10-27 / plotter.rs:23-37: builds without error
+    fish, eye = scenes.fishy_example()
+    assert len(fish) == 7 and len(eye) == 5
+    assert fish["v"][3][:6].tolist() == [-16.0, 0.0, -16.0, 128.0, 80.0, 80.0]
+
+
+def test_scene_generators_are_counter_based():
+    a, offs, rules = scenes.random_curve_paths(10, 6)
+    b, _, _ = scenes.random_curve_paths(12, 2)
+    per = int(offs[1])
+    assert a[2 * per: 4 * per].tobytes() == b.tobytes()      # sharding never changes a path
+    assert rules.tolist() == [0, 1, 0, 1, 0, 1]
+    v = a["v"][a["tag"] >= 1]
+    assert v.min() >= 0 and v.max() < 512
+    c = scenes.random_polygons(5, 3)
+    d = scenes.random_polygons(6, 1)
+    assert c[65:130].tobytes() == d.tobytes()
+    assert c["v"][:, :2].min() >= 0 and c["v"][:, :2].max() < 32768
+
+
+def _outline(join, limit, tol_sq, ops, counts, xyw):
+    ops = fb.as_ops(ops)
+    cap = 1 << 16
+    out = np.zeros(cap, dtype=OP_DTYPE)
+    n = C.c_size_t()
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    xyw = np.ascontiguousarray(xyw, dtype=np.float32)
+    _lib.check(_lib.lib().ftl_debug_stroke_outline(join, limit, tol_sq, ops.ctypes.data, len(ops), counts.ctypes.data,
+                                                   xyw.ctypes.data if xyw.size else None, out.ctypes.data, cap, C.byref(n)))
+    assert n.value <= cap
+    return out[: n.value]
+
+
+@pytest.mark.parametrize("join,limit", [(0, 4.0), (0, 1.5), (0, 0.0), (1, 0.0), (2, 0.0)])
+def test_host_stroker_matches_oracle(join, limit):
+    """The product's host stroker (stroker.cpp) against the oracle's (stroker.rs restatement) on
+    line-only paths, where flattening is the identity so no device is needed."""
+    rng = np.random.default_rng(17 + join)
+    paths = list(scenes.stroke_scenes(1.0).values())[:5]  # all but the curve scene
+    for _ in range(40):
+        p = Path2D().absolute().pen_width(float(rng.uniform(0.5, 12)))
+        p = p.move_to(*rng.uniform(0, 100, 2))
+        for _ in range(int(rng.integers(1, 9))):
+            k = rng.random()
+            if k < 0.7:
+                p = p.line_to(*rng.uniform(0, 100, 2))
+            elif k < 0.8:
+                p = p.pen_width(float(rng.uniform(0.5, 12)))
+            elif k < 0.9:
+                p = p.close()
+            else:
+                p = p.move_to(*rng.uniform(0, 100, 2))
+        paths.append(p.finish())
+    for ops in paths:
+        o = oracle.Plotter(8, 8, oracle.MATTE8)
+        o.set_join(join, limit)
+        exp = o.debug_stroke_ops(ops)
+        wide = oracle.Plotter(8, 8, oracle.MATTE8).debug_flatten_wide(ops)
+        counts = [1 if int(t) in (1, 2) else 0 for t in ops["tag"]]
+        got = _outline(join, limit, np.float32(0.3) * np.float32(0.3), ops, counts, wide)
+        assert len(got) == len(exp)
+        assert got.tobytes() == exp.tobytes()
