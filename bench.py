@@ -1,0 +1,323 @@
+#!/usr/bin/env python
+"""bench.py — throughput of the footile hot path on B200 (and the CPU baseline beside it).
+
+Contract (see DESIGN.md "Measurement"):
+  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload heptagram|batch512]
+A step is one pass of the hot path over one batch of synthetic paths.  Default workload =
+BASELINE.json configs[1]: heptagram fills (NonZero / EvenOdd alternating) into 4096x4096 Matte8
+rasters, `--batch` rasters per step (default 64 = 1 GiB of output, far beyond the 126 MB L2).
+  value : Gpx/s with the path ops already resident in HBM (ftl_batch_run), CUDA events on the
+          library's stream, max over ranks.
+  e2e   : the same metric through the C ABI with HOST buffers: ftl_batch_fill(host ops) then
+          ftl_batch_read of every raster into pinned host memory, inside the timed region.
+  roofline : raster_tiles kernel, algorithmic bytes / CUDA-event duration vs MEASURED_PEAKS.json.
+  cpu_baseline : the oracle (CPU restatement of footile, 1 thread) on a bounded sample, rank 0, N=1.
+--impl reference times the oracle on all host threads (one plotter per thread).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+PIXELS_NOTE = "px = W * (H - max(top_row,0)) per fill: the reference resolves every pixel of those rows (fig.rs:497,539)"
+
+
+def peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- workloads -----------------------------------------------------------------
+def make_workload(name, batch, rank):
+    from footile_b200 import scenes
+    if name == "heptagram":
+        size = 4096
+        path = scenes.heptagram_abs()
+        ops = np.tile(path, batch)
+        offs = np.arange(batch + 1, dtype=np.uint64) * np.uint64(len(path))
+        rules = (np.arange(batch) & 1).astype(np.uint8)
+        tr = np.tile(scenes.heptagram_transform(size), (batch, 1))
+        return dict(size=size, ops=ops, offs=offs, rules=rules, tr=tr, desc="heptagram {7/2} fill, NonZero/EvenOdd alternating, 4096x4096 Matte8")
+    if name == "batch512":
+        size = 512
+        ops, offs, rules = scenes.random_curve_paths(rank * batch, batch)
+        return dict(size=size, ops=ops, offs=offs, rules=rules, tr=None, desc="random quad/cubic paths (64 segments), 512x512 Matte8 per path")
+    raise SystemExit("unknown workload " + name)
+
+
+def oracle_pixels(wl, sample):
+    """Pixels per fill by the reference's dense-row convention, from the oracle's top_row."""
+    import oracle
+    px = []
+    for j in sample:
+        o = oracle.Plotter(8, 8, oracle.MATTE8)  # tiny raster: only (dir, top_row) are needed
+        if wl["tr"] is not None:
+            o.set_transform(wl["tr"][j])
+        o.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], (255,))
+        top = o.last_info()["top_row"]
+        px.append(wl["size"] * max(0, wl["size"] - max(top, 0)))
+    return px
+
+
+def cpu_run(wl, jobs, threads):
+    """Time the oracle over `jobs` (indices) using `threads` host threads; returns seconds (rasters pre-allocated)."""
+    import oracle
+    size = wl["size"]
+    chunks = [jobs[t::threads] for t in range(threads)]
+    plotters = [[oracle.Plotter(size, size, oracle.MATTE8) for _ in c] for c in chunks]
+    for ps, c in zip(plotters, chunks):
+        for p, j in zip(ps, c):
+            if wl["tr"] is not None:
+                p.set_transform(wl["tr"][j])
+
+    def work(t):
+        for p, j in zip(plotters[t], chunks[t]):
+            p.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], (255,))
+
+    t0 = time.perf_counter()
+    if threads == 1:
+        work(0)
+    else:
+        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
+        for th in ths:
+            th.start()
+        for th in ths:
+            th.join()
+    return time.perf_counter() - t0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512"])
+    ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 64 heptagram / 4096 batch512)")
+    ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    batch = args.batch or (64 if args.workload == "heptagram" else 4096)
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    unit = "Gpx/s"
+    metric = "Gpx/s composited (%s)" % ("heptagram fill 4096^2 Matte8" if args.workload == "heptagram" else "100k-path batch 512^2 Matte8")
+    config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": "Matte8", "pixels": PIXELS_NOTE,
+              "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
+
+    # ---------------- reference arm: the oracle on all host cores ----------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wl = make_workload(args.workload, batch, 0)
+        config["workload"] = wl["desc"]
+        config["raster"] = "%dx%d" % (wl["size"], wl["size"])
+        cores = os.cpu_count() or 1
+        per_step = max(cores, min(batch, cores * (2 if args.workload == "heptagram" else 64)))
+        jobs = list(range(per_step))
+        px = sum(oracle_pixels(wl, jobs))
+        for _ in range(min(args.warmup, 2)):
+            cpu_run(wl, jobs, cores)
+        t = 0.0
+        for _ in range(args.steps):
+            t += cpu_run(wl, jobs, cores)
+        v = px * args.steps / t / 1e9
+        sample = "%d fills per step on %d threads (one plotter per thread), rasters pre-allocated" % (per_step, cores)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
+                          "vs_baseline": None, "dtype": "i32 fixed-point 16.16 / u8", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                          "paths_per_s": per_step * args.steps / t,
+                          "note": "CPU restatement of footile (the Rust reference cannot be built in this image)"}))
+        return
+
+    # ---------------- our arm ----------------
+    import torch
+    import torch.distributed as dist
+    import footile_b200 as fb
+    from footile_b200 import Batch, Format
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    wl = make_workload(args.workload, batch, rank)
+    size = wl["size"]
+    config["workload"] = wl["desc"]
+    config["raster"] = "%dx%d" % (size, size)
+    b = Batch(size, size, Format.Matte8, batch, device=local_rank)
+    stream = torch.cuda.ExternalStream(b.stream(), device=local_rank)
+    px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" and batch <= 512 else range(min(batch, 2)))
+    if len(px_fill) == batch:
+        px_step = float(sum(px_fill))
+    else:  # heptagram: every fill has the same top row
+        px_step = float(px_fill[0]) * batch
+    raster_bytes = size * size
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        b.sync()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- value: ops resident in HBM ----
+    b.upload(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+    for _ in range(args.warmup):
+        b.run()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    fb.set_profiling(True)
+    fb.tile_kernel_time(reset=True)
+    l0 = fb.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for _ in range(args.steps):
+        b.run()
+    ev1.record(stream)
+    barrier()
+    launches = fb.launch_count() - l0
+    ms = max_over_ranks(ev0.elapsed_time(ev1))
+    tile_ms, tile_n = fb.tile_kernel_time(reset=True)
+    fb.set_profiling(False)
+    clocks = sampler.stop()
+    value = px_step * world * args.steps / (ms * 1e-3) / 1e9
+    paths_per_s = batch * world * args.steps / (ms * 1e-3)
+
+    # ---- e2e: host ops in, rasters out to pinned host memory, every step ----
+    if args.kernel_only:
+        if rank == 0:
+            print(json.dumps({"metric": metric, "value": value, "unit": unit, "ms_per_step": ms / args.steps, "kernel_only": True,
+                              "tile_ms_per_launch": tile_ms / max(tile_n, 1), "gpu_launches": int(launches)}))
+        return
+    pinned = torch.empty(batch * raster_bytes, dtype=torch.uint8, pin_memory=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+        b.read_into(0, batch, pinned.data_ptr(), pinned.numel())
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(e2e_steps):
+        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+        b.read_into(0, batch, pinned.data_ptr(), pinned.numel())
+    e1.record(stream)
+    barrier()
+    e2e_ms = max_over_ranks(e0.elapsed_time(e1))
+    e2e_val = px_step * world * e2e_steps / (e2e_ms * 1e-3) / 1e9
+    h2d = int(wl["ops"].nbytes + batch * 64)
+    d2h = int(batch * raster_bytes)
+
+    # ---- roofline of the tile kernel (pixel term: 1 B/px store for Matte8) ----
+    peak, peak_kind = peaks()
+    roof = None
+    if tile_n:
+        per_launch_ms = tile_ms / tile_n
+        achieved = px_step / (per_launch_ms * 1e-3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+                traffic = json.load(f).get(args.workload)
+        except Exception:
+            pass
+        roof = {"kernel": "raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step, "avg_launch_ms": per_launch_ms,
+                "launches_timed": tile_n, "share_of_step": tile_ms / ms if ms else None}
+
+    # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----
+    cpu = None
+    if rank == 0 and world == 1:
+        n_cpu = args.cpu_fills or (8 if args.workload == "heptagram" else 256)
+        n_cpu = min(n_cpu, batch)
+        jobs = list(range(n_cpu))
+        cpu_run(wl, jobs[: max(1, n_cpu // 4)], 1)
+        reps, t = 0, 0.0
+        while t < 8.0 and reps < 50:
+            t += cpu_run(wl, jobs, 1)
+            reps += 1
+        cpx = sum(oracle_pixels(wl, jobs)) if args.workload == "batch512" else px_step / batch * n_cpu
+        cpu = {"value": cpx * reps / t / 1e9, "unit": unit, "cores": 1, "kind": "port",
+               "sample": "%d fills x %d repeats of this workload, single thread, SSSE3 accumulate, rasters pre-allocated" % (n_cpu, reps),
+               "paths_per_s": n_cpu * reps / t}
+
+    if rank == 0:
+        print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                          "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                          "dtype": "i32 fixed-point 16.16 / u8", "data": "synthetic", "config": config, "paths_per_s": paths_per_s,
+                          "clocks": clocks, "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                                                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
+                          "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -328,6 +328,25 @@ int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes) {
     return FTL_OK;
 }
 
+int ftl_batch_stream(ftl_batch *b, void **stream) {
+    GUARD_BEGIN
+    if (!b || !stream) return bad("null argument");
+    int rc = b->eng.sync();  // forces lazy stream creation
+    if (rc) return rc;
+    *stream = b->eng.stream();
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_stream(ftl_plotter *p, void **stream) {
+    GUARD_BEGIN
+    if (!p || !stream) return bad("null argument");
+    int rc = p->eng.sync();
+    if (rc) return rc;
+    *stream = p->eng.stream();
+    return FTL_OK;
+    GUARD_END
+}
+
 // ---- instrumentation ----
 uint64_t ftl_launch_count(void) { return Engine::launch_count(); }
 int ftl_set_profiling(int enabled) {

@@ -264,3 +264,13 @@ class Batch:
         p, n = C.c_void_p(), C.c_size_t()
         _lib.check(_lib.lib().ftl_batch_device_ptr(self._handle, C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def stream(self):
+        """cudaStream_t (as int) the batch issues its work on."""
+        s = C.c_void_p()
+        _lib.check(_lib.lib().ftl_batch_stream(self._handle, C.byref(s)))
+        return s.value
+
+    def read_into(self, first, count, ptr, nbytes):
+        """Copy rasters to a caller-provided host address (e.g. pinned memory)."""
+        _lib.check(_lib.lib().ftl_batch_read(self._handle, first, count, C.c_void_p(ptr), nbytes))

@@ -128,6 +128,10 @@ int ftl_batch_read(ftl_batch *b, uint32_t first, uint32_t count, void *dst, size
 int ftl_batch_checksums(ftl_batch *b, uint32_t first, uint32_t count, uint64_t *out);
 int ftl_batch_sync(ftl_batch *b);
 int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes);
+/* The cudaStream_t every call on this handle is issued on (for event timing
+ * and for ordering a caller's own kernels after a fill). */
+int ftl_batch_stream(ftl_batch *b, void **stream);
+int ftl_stream(ftl_plotter *p, void **stream);
 
 /* ---- Device-resident replay (bench `value` leg: inputs already in HBM) ---- */
 /* Upload the jobs of a batch once; ftl_batch_run() then repeats the device
