@@ -75,15 +75,17 @@ struct __align__(16) JobDesc {  // 64 B, host-filled
 };
 static_assert(sizeof(JobDesc) == 64, "JobDesc layout");
 
-struct __align__(16) JobState {  // 32 B, device-written
+struct __align__(16) JobState {  // 48 B, device-written
     unsigned long long top_key;  // min over vertices of (y,x), sign-biased
     uint32_t top_vid;
     int32_t dir;        // 0 Forward, 1 Reverse (fig.rs:402-411)
     int32_t top_row;    // row_of(y of top-left vertex) (fig.rs:496)
     int32_t first_row;  // max(top_row, 0): first raster row the fill touches (fig.rs:497)
     int32_t shift;      // min(top_row, 0): geometry row r lands on raster row r - shift
-    uint32_t pad;
+    uint32_t vtx_begin, vtx_end;  // this job's vertex (= edge slot) range
+    uint32_t pad[3];
 };
+static_assert(sizeof(JobState) == 48, "JobState layout");
 
 struct __align__(16) Vtx {  // 16 B
     int32_t x, y;   // Fixed 16.16
@@ -95,11 +97,12 @@ struct __align__(16) EdgeRec {  // 32 B: one per ring segment whose end points d
     int32_t x_bot0;     // X at the bottom of the edge's first row
     int32_t inv_slope;  // dx/dy
     int32_t step_pix;   // min(|dy/dx|, 1), 0 when vertical
-    int32_t y0, y1;     // upper / lower Y
+    int32_t ry0, ry1;   // raster rows of the upper / lower vertex (geometry row - shift)
+    uint32_t fr;        // fract(y_upper) | fract(y_lower) << 16
     uint32_t job;
-    uint32_t flags;     // bit0 valid, bit1 direction upper->lower (0 Forward, 1 Reverse)
-    uint32_t pad;
+    uint32_t flags;     // bit0 valid, bit1 set when the edge runs against the figure direction (sign -1, fig.rs:286)
 };
+constexpr uint32_t DIRECT_MAX = 64;  // jobs with at most this many edge slots skip binning: their tiles scan the job's edges
 
 struct __align__(8) SumHead {  // scan element over ops: vertex count + position of the last sub-figure head
     uint32_t sum, head;
@@ -115,7 +118,7 @@ struct Counters {
 struct Params {  // per-call constants, passed by value
     uint32_t W, H, row_begin, row_end;
     uint32_t fmt, bpp, pitch;
-    uint32_t log2R, R, n_bands, WP;  // rows per tile, bands per job, padded smem row (cells)
+    uint32_t log2R, R, n_bands, WP, chunks;  // rows per tile, bands per job, smem row stride (cells), 512-cell chunks per row
     uint32_t n_jobs, n_ops, n_tiles;
 };
 
@@ -414,11 +417,18 @@ __device__ __forceinline__ uint32_t vtx_next_fwd(const Vtx *V, uint32_t nv, uint
     return k + 1;
 }
 
-__global__ void init_job_state(JobState *JS, uint32_t n_jobs) {
+__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < n_jobs) JS[j] = {~0ull, NONE32, 0, 0, 0x7FFFFFFF, 0, 0};
+    if (j >= n_jobs) return;
+    JobState s;
+    s.top_key = ~0ull; s.top_vid = NONE32; s.dir = 0; s.top_row = 0; s.first_row = 0x7FFFFFFF; s.shift = 0;
+    s.vtx_begin = off ? off[jobs[j].op_begin].sum : 0u;
+    s.vtx_end = off ? off[jobs[j].op_end].sum : 0u;
+    s.pad[0] = s.pad[1] = s.pad[2] = 0;
+    JS[j] = s;
 }
 
+// Top-left vertex, pass 1: minimum (y,x) over the live vertices of each job (fig.rs:493-494).
 __global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS) {
     const uint32_t nv = C->nv;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
@@ -427,29 +437,10 @@ __global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, con
         atomicMin(&JS[v.job].top_key, vtx_key(v));
     }
 }
-
-// Edge::new (fig.rs:179-210)
-__device__ __forceinline__ EdgeRec make_edge(const Vtx &p0, const Vtx &p1, uint32_t job, uint32_t dd) {
-    EdgeRec e;
-    fx_t dx = fx_sub(p1.x, p0.x), dy = fx_sub(p1.y, p0.y);
-    e.step_pix = dx != 0 ? fx_min(fx_abs(fx_div(dy, dx)), FX_ONE) : 0;
-    e.inv_slope = fx_div(dx, dy);
-    fx_t y_bot = fx_sub(fx_floor(fx_add(p0.y, FX_ONE)), p0.y);
-    e.x_bot0 = fx_add(p0.x, fx_mul(e.inv_slope, y_bot));
-    e.y0 = p0.y;
-    e.y1 = p1.y;
-    e.job = job;
-    e.flags = 1u | (dd << 1);
-    e.pad = 0;
-    return e;
-}
-
-// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most
-// one edge, directed from its upper to its lower vertex.  This is the same
-// set of edges the reference creates in update_edges/add_edge (fig.rs:576-600)
-// when it visits both neighbours of every vertex.
-__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, Counters *__restrict__ C, JobState *JS,
-                                                  EdgeRec *__restrict__ E, uint32_t *__restrict__ sub_last) {
+// Pass 2: the stable sort keeps the lowest vertex id among equal keys; also
+// records each sub-figure's last live vertex for the Reverse ring neighbour.
+__global__ void __launch_bounds__(256) vtx_topvid(const Vtx *__restrict__ V, Counters *__restrict__ C, JobState *JS,
+                                                  uint32_t *__restrict__ sub_last) {
     const uint32_t nv = C->nv;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
         Vtx v = V[k];
@@ -457,19 +448,7 @@ __global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, Cou
         bool pop = last && vtx_same(v, V[v.sub]);
         if (last) sub_last[v.sub] = pop ? (k > v.sub ? k - 1 : NONE32) : k;
         if (pop) atomicAdd(&C->n_popped, 1u);
-        EdgeRec e;
-        e.flags = 0;
-        if (!pop) {
-            if (vtx_key(v) == JS[v.job].top_key) atomicMin(&JS[v.job].top_vid, k);
-            uint32_t w = vtx_next_fwd(V, nv, k, v, last);
-            if (w != k) {
-                Vtx q = V[w];
-                if (q.y > v.y) e = make_edge(v, q, v.job, 0u);        // v is upper; w is v's Forward neighbour
-                else if (q.y < v.y) e = make_edge(q, v, v.job, 1u);   // w is upper; v is w's Reverse neighbour
-            }
-        }
-        if (e.flags) E[k] = e;
-        else E[k].flags = 0;
+        else if (vtx_key(v) == JS[v.job].top_key) atomicMin(&JS[v.job].top_vid, k);
     }
 }
 
@@ -495,22 +474,64 @@ __global__ void job_finalize(const Vtx *__restrict__ V, const Counters *__restri
     JS[j].shift = top < 0 ? top : 0;
 }
 
+// Edge::new (fig.rs:179-210), with rows already mapped to raster rows and the
+// sign against the figure direction resolved.
+__device__ __forceinline__ EdgeRec make_edge(const Vtx &p0, const Vtx &p1, uint32_t job, uint32_t dd, const JobState &js) {
+    EdgeRec e;
+    fx_t dx = fx_sub(p1.x, p0.x), dy = fx_sub(p1.y, p0.y);
+    e.step_pix = dx != 0 ? fx_min(fx_abs(fx_div(dy, dx)), FX_ONE) : 0;
+    e.inv_slope = fx_div(dx, dy);
+    fx_t y_bot = fx_sub(fx_floor(fx_add(p0.y, FX_ONE)), p0.y);
+    e.x_bot0 = fx_add(p0.x, fx_mul(e.inv_slope, y_bot));
+    e.ry0 = fx_to_i32(p0.y) - js.shift;
+    e.ry1 = fx_to_i32(p1.y) - js.shift;
+    e.fr = (uint32_t)fx_fract(p0.y) | ((uint32_t)fx_fract(p1.y) << 16);
+    e.job = job;
+    e.flags = 1u | ((dd != (uint32_t)js.dir ? 1u : 0u) << 1);
+    return e;
+}
+
+// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most
+// one edge, directed from its upper to its lower vertex.  This is the same
+// set of edges the reference creates in update_edges/add_edge (fig.rs:576-600)
+// when it visits both neighbours of every vertex.
+__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, const Counters *__restrict__ C, const JobState *__restrict__ JS,
+                                                  EdgeRec *__restrict__ E) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        bool last = vtx_is_last(V, nv, k);
+        bool pop = last && vtx_same(v, V[v.sub]);
+        EdgeRec e;
+        e.flags = 0;
+        if (!pop) {
+            uint32_t w = vtx_next_fwd(V, nv, k, v, last);
+            if (w != k) {
+                Vtx q = V[w];
+                if (q.y > v.y) e = make_edge(v, q, v.job, 0u, JS[v.job]);        // v is upper; w is v's Forward neighbour
+                else if (q.y < v.y) e = make_edge(q, v, v.job, 1u, JS[v.job]);   // w is upper; v is w's Reverse neighbour
+            }
+        }
+        if (e.flags) E[k] = e;
+        else E[k].flags = 0;
+    }
+}
+
 // Band range of an edge inside this device's rows; returns false if none.
-__device__ __forceinline__ bool edge_bands(const EdgeRec &e, const JobState &js, const Params &P, uint32_t *b0, uint32_t *b1) {
-    int64_t ry0 = (int64_t)fx_to_i32(e.y0) - js.shift, ry1 = (int64_t)fx_to_i32(e.y1) - js.shift;
-    int64_t lo = ry0, hi = ry1;
-    if (lo < js.first_row) lo = js.first_row;
-    if (lo < (int64_t)P.row_begin) lo = P.row_begin;
-    if (hi > (int64_t)P.row_end - 1) hi = (int64_t)P.row_end - 1;
+__device__ __forceinline__ bool edge_bands(const EdgeRec &e, const Params &P, uint32_t *b0, uint32_t *b1) {
+    int32_t lo = e.ry0, hi = e.ry1;  // ry0 >= first_row >= 0 by construction
+    if (lo < (int32_t)P.row_begin) lo = (int32_t)P.row_begin;
+    if (hi > (int32_t)P.row_end - 1) hi = (int32_t)P.row_end - 1;
     if (lo > hi) return false;
-    *b0 = (uint32_t)(lo - P.row_begin) >> P.log2R;
-    *b1 = (uint32_t)(hi - P.row_begin) >> P.log2R;
+    *b0 = (uint32_t)(lo - (int32_t)P.row_begin) >> P.log2R;
+    *b1 = (uint32_t)(hi - (int32_t)P.row_begin) >> P.log2R;
     return true;
 }
 
 // Counting sort of edges by (job,row band): pass FILL=false counts, pass
 // FILL=true writes edge ids at the scanned offsets.  Short edges are handled
 // by their own thread; an edge crossing many bands is spread over the warp.
+// Jobs with at most DIRECT_MAX edge slots are not binned at all.
 template <bool FILL>
 __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
                                                  const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
@@ -524,9 +545,12 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
         if (k < nv) {
             EdgeRec e = E[k];
             uint32_t b1;
-            if ((e.flags & 1u) && edge_bands(e, JS[e.job], P, &b0, &b1)) {
-                nb = b1 - b0 + 1;
-                tbase = e.job * P.n_bands;
+            if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
+                const JobState &js = JS[e.job];
+                if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
+                    nb = b1 - b0 + 1;
+                    tbase = e.job * P.n_bands;
+                }
             }
         }
         if (nb > 0 && nb <= 4) {
@@ -553,20 +577,35 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
 // ---------------------------------------------------------------------------
 // (c)+(d) tile raster kernel
 // ---------------------------------------------------------------------------
-// Signed coverage of one edge on one geometry row, scattered into the row's
+// Shared-memory row tile: R rows; a row is `chunks` chunks of 512 i32 cells
+// plus a 4-cell pad, followed (after all rows) by R*chunks touched-group masks
+// (bit g of mask word c = some cell of the 16-cell group g of chunk c is
+// non-zero).  i32 sums truncated to i16 at resolve are the reference's
+// wrapping i16 sums: truncation is a ring homomorphism.
+//
+// Cells are XOR-swizzled at 16-byte granularity so that a lane can own 16
+// CONSECUTIVE cells (4 LDS.128) without bank conflicts: quad q lives at
+// q ^ ((q >> 3) & 3).
+constexpr uint32_t CHUNK = 512;
+__device__ __forceinline__ uint32_t cell_phys(uint32_t c) {
+    uint32_t q = c >> 2;
+    return ((q ^ ((q >> 3) & 3u)) << 2) | (c & 3u);
+}
+
+// Signed coverage of one edge on one raster row, scattered into the row's
 // shared-memory cells.  Closed form of Scanner::scan_continuing_edges /
 // add_edge + Edge::scan_area (fig.rs:238-321,557-600); SURVEY Appendix A.4.
-__device__ __forceinline__ void scatter_edge_row(const EdgeRec &e, int32_t ed, int32_t r, int32_t *row, int32_t W) {
-    const int32_t r0 = fx_to_i32(e.y0), r1 = fx_to_i32(e.y1);
-    const bool starting = r == r0, ending = r == r1;
+__device__ __forceinline__ void scatter_edge_row(const EdgeRec &e, int32_t ry, int32_t *row, uint32_t *mask, int32_t W) {
+    const bool starting = ry == e.ry0, ending = ry == e.ry1;
+    const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
     // continuing_cov / starting_cov (fig.rs:238-241,252-259)
-    int32_t cov = (ending ? pixel_cov(fx_fract(e.y1)) : 256) - (starting ? pixel_cov(fx_fract(e.y0)) : 0);
+    int32_t cov = (ending ? pixel_cov(fr1) : 256) - (starting ? pixel_cov(fr0) : 0);
     if (cov <= 0) return;
     // advance_edges in closed form (fig.rs:569-573)
-    fx_t x_bot = (fx_t)((uint32_t)e.x_bot0 + (uint32_t)(r - r0) * (uint32_t)e.inv_slope);
-    // calculate_x_limits_* / set_x_limits (fig.rs:244-249,262-278)
-    fx_t x0 = starting ? fx_sub(x_bot, fx_mul(e.inv_slope, fx_sub(FX_ONE, fx_fract(e.y0)))) : fx_sub(x_bot, e.inv_slope);
-    fx_t x1 = ending ? fx_sub(x_bot, fx_mul(e.inv_slope, fx_sub(fx_ceil(e.y1), e.y1))) : x_bot;
+    fx_t x_bot = (fx_t)((uint32_t)e.x_bot0 + (uint32_t)(ry - e.ry0) * (uint32_t)e.inv_slope);
+    // calculate_x_limits_* / set_x_limits (fig.rs:244-249,262-278); ceil(y)-y = (ONE - fract) & MASK
+    fx_t x0 = starting ? fx_sub(x_bot, fx_mul(e.inv_slope, FX_ONE - fr0)) : fx_sub(x_bot, e.inv_slope);
+    fx_t x1 = ending ? fx_sub(x_bot, fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK)) : x_bot;
     fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
     int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
     if (min_pix >= W) return;
@@ -575,150 +614,213 @@ __device__ __forceinline__ void scatter_edge_row(const EdgeRec &e, int32_t ed, i
                                  : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
     fx_t first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
     fx_t step = e.step_pix > 0 ? e.step_pix : FX_ONE;
+    const int32_t ed = (e.flags & 2u) ? -1 : 1;  // fig.rs:286
     // scan_area (fig.rs:285-302): X(k) = min(pixel_cov(min(first + k*step, 1)), cov);
     // cell min_pix+k receives X(k)-X(k-1); cells left of 0 fold into cell 0.
     int32_t c = min_pix > 0 ? min_pix : 0;
     int64_t xc = (int64_t)first + (int64_t)(c - min_pix) * (int64_t)step;
-    int32_t prev = 0;
+    int32_t prev = 0, last_g = -1;
     for (; c < W; c++) {
         int32_t xk = pixel_cov((fx_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE));
         if (xk > cov) xk = cov;
         int32_t d = xk - prev;
-        if (d != 0) atomicAdd(&row[c], ed * d);
+        if (d != 0) {
+            atomicAdd(&row[cell_phys((uint32_t)c)], ed * d);
+            int32_t g = c >> 4;
+            if (g != last_g) {
+                atomicOr(&mask[g >> 5], 1u << (g & 31));
+                last_g = g;
+            }
+        }
         prev = xk;
         if (xk >= cov) break;
         xc += step;
     }
 }
 
-// alpha of one pixel from the wrapped i16 sum (fig.rs:637-664; imgbuf.rs:54-66,157-167)
-__device__ __forceinline__ uint32_t rule_alpha(int32_t sum, bool even_odd) {
-    int32_t s = (int32_t)(int16_t)sum;
-    if (even_odd) {
-        int32_t c = (s & 0xFF) - (s & 0x100);
-        s = c < 0 ? -c : c;
+// Four consecutive pixels: wrapped-i16 sums (p_i + base) -> alpha bytes
+// (fig.rs:637-664; imgbuf.rs:54-66,157-167), two pixels per 16x2 SIMD op.
+template <bool EVEN_ODD>
+__device__ __forceinline__ uint32_t quad_alpha(int32_t p0, int32_t p1, int32_t p2, int32_t p3, int32_t base) {
+    if (!EVEN_ODD) {
+        const uint32_t bp = __byte_perm((uint32_t)base, (uint32_t)base, 0x1010);
+        uint32_t lo = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x5410), hi = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x5410);
+        lo = __viaddmin_s16x2_relu(lo, bp, 0x00FF00FFu);  // clamp(i16(p + base), 0, 255) per halfword
+        hi = __viaddmin_s16x2_relu(hi, bp, 0x00FF00FFu);
+        return __byte_perm(lo, hi, 0x6420);
+    } else {
+        uint32_t lo = __byte_perm((uint32_t)(p0 + base), (uint32_t)(p1 + base), 0x5410);
+        uint32_t hi = __byte_perm((uint32_t)(p2 + base), (uint32_t)(p3 + base), 0x5410);
+        // |(s & 0xFF) - (s & 0x100)| = odd ? 256 - v : v, then 256 saturates to 255
+        uint32_t bl = (lo >> 8) & 0x00010001u, bh = (hi >> 8) & 0x00010001u;
+        lo = ((lo & 0x00FF00FFu) ^ (bl * 0xFFu)) + bl;
+        hi = ((hi & 0x00FF00FFu) ^ (bh * 0xFFu)) + bh;
+        lo -= (lo >> 8) & 0x00010001u;
+        hi -= (hi >> 8) & 0x00010001u;
+        return __byte_perm(lo, hi, 0x6420);
     }
-    return (uint32_t)(s < 0 ? 0 : (s > 255 ? 255 : s));
 }
 
-// Resolve one row held in shared memory by one warp: inclusive prefix sum of
-// the cells (zeroing them), fill rule, then store (Matte8) or SrcOver blend
-// (Graya8p / Rgba8p) into the raster row.  Each lane owns 4 consecutive
-// cells per 128-cell chunk: LDS.128, 3 adds, a 5-step shuffle scan.
-__device__ __forceinline__ void resolve_row(int32_t *row, uint8_t *dst, uint32_t W, uint32_t fmt, bool even_odd, uint32_t color) {
+__device__ __forceinline__ uint32_t blend_rgba(uint32_t px, uint32_t color, uint32_t alpha, uint32_t clr_a) {
+    uint32_t sa1 = 255u - pix::ch8_mul(alpha, clr_a);
+    uint32_t o = 0;
+#pragma unroll
+    for (int ch = 0; ch < 4; ch++) o |= pix::src_over_ch((px >> (8 * ch)) & 0xFF, (color >> (8 * ch)) & 0xFF, alpha, sa1) << (8 * ch);
+    return o;
+}
+
+// Resolve one row held in shared memory by one warp.  Per 512-cell chunk each
+// lane owns 16 consecutive cells: it reads them (4 LDS.128), zeroes them, scans
+// them serially, one 5-step shuffle scan carries the lane totals across the
+// warp, then the fill rule turns the 16 sums into 16 alpha bytes which are
+// stored (Matte8, one STG.128 per lane: imgbuf.rs:59,93) or blended SrcOver
+// into the raster row (Graya8p/Rgba8p: fig.rs:641-642,662-663).  Chunks whose
+// mask word is zero hold no edge: their pixels take the constant alpha of the
+// running sum without touching shared memory.
+template <int FMT, bool EVEN_ODD, bool ALIGNED>
+__device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t chunks, uint32_t color) {
     const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sw = (lane >> 1) & 3u;
+    const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
     int32_t carry = 0;
-    const uint32_t clr_a = fmt == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
-    for (uint32_t x0 = 0; x0 < W; x0 += 128) {
-        const uint32_t x = x0 + lane * 4;
-        int4 v = *reinterpret_cast<int4 *>(row + x);
-        *reinterpret_cast<int4 *>(row + x) = make_int4(0, 0, 0, 0);
-        v.y += v.x; v.z += v.y; v.w += v.z;
-        int32_t inc = v.w;
+    for (uint32_t ch = 0; ch < chunks; ch++) {
+        const uint32_t m = mask[ch];
+        const uint32_t x = ch * CHUNK + lane * 16;
+        uint32_t a[4];
+        if (m == 0) {
+            uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
+            a[0] = a[1] = a[2] = a[3] = q;
+        } else {
+            __syncwarp();
+            if (lane == 0) mask[ch] = 0;
+            int4 v[4];
+            if ((m >> lane) & 1u) {
+                int32_t *base = row + ch * CHUNK + lane * 16;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += o;
-        }
-        int32_t base = carry + inc - v.w;
-        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
-        uint32_t a0 = rule_alpha(base + v.x, even_odd), a1 = rule_alpha(base + v.y, even_odd);
-        uint32_t a2 = rule_alpha(base + v.z, even_odd), a3 = rule_alpha(base + v.w, even_odd);
-        if (x >= W) continue;
-        if (fmt == FTL_MATTE8) {  // store, colour ignored (fig.rs:632-636; imgbuf.rs:59,93)
-            uint32_t packed = a0 | (a1 << 8) | (a2 << 16) | (a3 << 24);
-            uint8_t *d = dst + x;
-            if (x + 4 <= W && ((uintptr_t)d & 3) == 0) *reinterpret_cast<uint32_t *>(d) = packed;
-            else
-                for (uint32_t i = 0; i < 4 && x + i < W; i++) d[i] = (uint8_t)(packed >> (8 * i));
-        } else if (fmt == FTL_RGBA8P) {  // fig.rs:641-642,662-663 via pix (pix_compat.cuh)
-            uint32_t al[4] = {a0, a1, a2, a3};
-            uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
-            uint32_t px[4];
-            const bool vec = x + 4 <= W && ((uintptr_t)d & 15) == 0;
-            if (vec) {
-                uint4 t = *reinterpret_cast<uint4 *>(d);
-                px[0] = t.x; px[1] = t.y; px[2] = t.z; px[3] = t.w;
-            } else
-                for (uint32_t i = 0; i < 4; i++) px[i] = x + i < W ? d[i] : 0;
+                for (int j = 0; j < 4; j++) {
+                    int4 *p = reinterpret_cast<int4 *>(base + ((j ^ sw) << 2));
+                    v[j] = *p;
+                    *p = make_int4(0, 0, 0, 0);
+                }
+            } else {
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                uint32_t sa1 = 255u - pix::ch8_mul(al[i], clr_a);
-                uint32_t o = 0;
-#pragma unroll
-                for (int ch = 0; ch < 4; ch++)
-                    o |= pix::src_over_ch((px[i] >> (8 * ch)) & 0xFF, (color >> (8 * ch)) & 0xFF, al[i], sa1) << (8 * ch);
-                px[i] = o;
+                for (int j = 0; j < 4; j++) v[j] = make_int4(0, 0, 0, 0);
             }
-            if (vec) *reinterpret_cast<uint4 *>(d) = make_uint4(px[0], px[1], px[2], px[3]);
+            // lane-local inclusive prefix: 4 independent quad scans, then quad offsets
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                v[j].y += v[j].x; v[j].z += v[j].y; v[j].w += v[j].z;
+            }
+            int32_t o1 = v[0].w, o2 = o1 + v[1].w, o3 = o2 + v[2].w, tot = o3 + v[3].w;
+            int32_t inc = tot;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if (lane >= d) inc += o;
+            }
+            const int32_t b0 = carry + inc - tot;
+            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+            a[0] = quad_alpha<EVEN_ODD>(v[0].x, v[0].y, v[0].z, v[0].w, b0);
+            a[1] = quad_alpha<EVEN_ODD>(v[1].x, v[1].y, v[1].z, v[1].w, b0 + o1);
+            a[2] = quad_alpha<EVEN_ODD>(v[2].x, v[2].y, v[2].z, v[2].w, b0 + o2);
+            a[3] = quad_alpha<EVEN_ODD>(v[3].x, v[3].y, v[3].z, v[3].w, b0 + o3);
+        }
+        if (x >= W) continue;
+        if (FMT == FTL_MATTE8) {
+            uint8_t *d = dst + x;
+            if (ALIGNED && x + 16 <= W) *reinterpret_cast<uint4 *>(d) = make_uint4(a[0], a[1], a[2], a[3]);
             else
-                for (uint32_t i = 0; i < 4 && x + i < W; i++) d[i] = px[i];
+                for (uint32_t i = 0; i < 16 && x + i < W; i++) d[i] = (uint8_t)(a[i >> 2] >> (8 * (i & 3)));
+        } else if (FMT == FTL_RGBA8P) {
+            uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
+            if (ALIGNED && x + 16 <= W) {
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    uint4 t = reinterpret_cast<uint4 *>(d)[j];
+                    t.x = blend_rgba(t.x, color, a[j] & 0xFF, clr_a);
+                    t.y = blend_rgba(t.y, color, (a[j] >> 8) & 0xFF, clr_a);
+                    t.z = blend_rgba(t.z, color, (a[j] >> 16) & 0xFF, clr_a);
+                    t.w = blend_rgba(t.w, color, a[j] >> 24, clr_a);
+                    reinterpret_cast<uint4 *>(d)[j] = t;
+                }
+            } else
+                for (uint32_t i = 0; i < 16 && x + i < W; i++) d[i] = blend_rgba(d[i], color, (a[i >> 2] >> (8 * (i & 3))) & 0xFF, clr_a);
         } else {  // Graya8p
-            uint32_t al[4] = {a0, a1, a2, a3};
             uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
-            for (uint32_t i = 0; i < 4 && x + i < W; i++) {
-                uint32_t p = d[i];
-                uint32_t sa1 = 255u - pix::ch8_mul(al[i], clr_a);
-                uint32_t o = pix::src_over_ch(p & 0xFF, color & 0xFF, al[i], sa1) |
-                             (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, al[i], sa1) << 8);
-                d[i] = (uint16_t)o;
+            for (uint32_t i = 0; i < 16 && x + i < W; i++) {
+                uint32_t al = (a[i >> 2] >> (8 * (i & 3))) & 0xFF, p = d[i];
+                uint32_t sa1 = 255u - pix::ch8_mul(al, clr_a);
+                d[i] = (uint16_t)(pix::src_over_ch(p & 0xFF, color & 0xFF, al, sa1) | (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, al, sa1) << 8));
             }
         }
     }
 }
 
-// Persistent CTAs over (job, band) tiles.  Shared memory: R rows x WP i32
-// cells (i32 sums truncated to i16 at resolve are the reference's wrapping
-// i16 sums: truncation is a ring homomorphism).
+template <int FMT, bool ALIGNED>
+__device__ __forceinline__ void resolve_row_rule(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t chunks, uint32_t color,
+                                                 bool even_odd) {
+    if (even_odd) resolve_row<FMT, true, ALIGNED>(row, mask, dst, W, chunks, color);
+    else resolve_row<FMT, false, ALIGNED>(row, mask, dst, W, chunks, color);
+}
+
+// Persistent CTAs over (job, band) tiles.
+template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(TILE_THREADS) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                              const JobState *__restrict__ JS, Params P,
                                                              const uint32_t *__restrict__ tile_off,
                                                              const uint32_t *__restrict__ entries) {
     extern __shared__ __align__(16) int32_t area[];
-    const uint32_t cells = P.R * P.WP;
-    for (uint32_t i = threadIdx.x * 4; i < cells; i += TILE_THREADS * 4) *reinterpret_cast<int4 *>(area + i) = make_int4(0, 0, 0, 0);
+    uint32_t *masks = reinterpret_cast<uint32_t *>(area + P.R * P.WP);
+    const uint32_t words = P.R * P.WP + P.R * P.chunks;
+    for (uint32_t i = threadIdx.x; i < words; i += TILE_THREADS) area[i] = 0;
     __syncthreads();
     const uint32_t warp = threadIdx.x >> 5;
     for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
         const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
         const JobState js = JS[j];
-        const int64_t row0 = (int64_t)P.row_begin + ((int64_t)band << P.log2R);
-        int64_t row_hi = row0 + P.R;
-        if (row_hi > (int64_t)P.row_end) row_hi = P.row_end;
-        if (row_hi <= (int64_t)js.first_row) continue;  // rows above the figure are untouched (fig.rs:497)
+        const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
+        int32_t row_hi = row0 + (int32_t)P.R;
+        if (row_hi > (int32_t)P.row_end) row_hi = (int32_t)P.row_end;
+        if (row_hi <= js.first_row) continue;  // rows above the figure are untouched (fig.rs:497)
         const JobDesc &jd = jobs[j];
-        const uint32_t e0 = tile_off[tile], ne = tile_off[tile + 1] - e0;
         // ---- (c) scatter: one thread per (edge, row of the band) ----
+        const uint32_t n_slots = js.vtx_end - js.vtx_begin;
+        const bool direct = n_slots <= DIRECT_MAX;
+        const uint32_t e0 = direct ? js.vtx_begin : tile_off[tile];
+        const uint32_t ne = direct ? n_slots : tile_off[tile + 1] - e0;
         for (uint32_t i = threadIdx.x; i < (ne << P.log2R); i += TILE_THREADS) {
             const uint32_t rr = i & (P.R - 1);
-            const int64_t ry = row0 + rr;
-            if (ry < (int64_t)js.first_row || ry >= row_hi) continue;
-            const EdgeRec e = E[entries[e0 + (i >> P.log2R)]];
-            const int64_t r = ry + js.shift;
-            if (r < (int64_t)fx_to_i32(e.y0) || r > (int64_t)fx_to_i32(e.y1)) continue;
-            const int32_t ed = ((e.flags >> 1) & 1u) == (uint32_t)js.dir ? 1 : -1;  // fig.rs:286
-            scatter_edge_row(e, ed, (int32_t)r, area + rr * P.WP, (int32_t)P.W);
+            const int32_t ry = row0 + (int32_t)rr;
+            if (ry >= row_hi) continue;
+            const uint32_t k = direct ? e0 + (i >> P.log2R) : entries[e0 + (i >> P.log2R)];
+            const EdgeRec e = E[k];
+            if (!(e.flags & 1u) || ry < e.ry0 || ry > e.ry1) continue;
+            scatter_edge_row(e, ry, area + rr * P.WP, masks + rr * P.chunks, (int32_t)P.W);
         }
         __syncthreads();
         // ---- (d) resolve: one warp per row ----
         for (uint32_t rr = warp; rr < P.R; rr += TILE_THREADS / 32) {
-            const int64_t ry = row0 + rr;
-            if (ry < (int64_t)js.first_row || ry >= row_hi) continue;
-            uint8_t *dst = reinterpret_cast<uint8_t *>(jd.raster) + (size_t)(ry - P.row_begin) * P.pitch;
-            resolve_row(area + rr * P.WP, dst, P.W, P.fmt, jd.rule == FTL_EVENODD, jd.color);
+            const int32_t ry = row0 + (int32_t)rr;
+            if (ry < js.first_row || ry >= row_hi) continue;
+            uint8_t *dst = reinterpret_cast<uint8_t *>(jd.raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
+            resolve_row_rule<FMT, ALIGNED>(area + rr * P.WP, masks + rr * P.chunks, dst, P.W, P.chunks, jd.color, jd.rule == FTL_EVENODD);
         }
         __syncthreads();
     }
 }
 
-// Kernel (d) alone, for the imgbuf.rs KATs: one CTA per row of i16 cells.
+// Kernel (d) alone, for the imgbuf.rs KATs: one warp per row of i16 cells.
 __global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__restrict__ src, uint8_t *__restrict__ dst, uint32_t n,
-                                                             uint32_t WP, int even_odd) {
+                                                             uint32_t chunks, int even_odd) {
     extern __shared__ __align__(16) int32_t area[];
+    uint32_t *mask = reinterpret_cast<uint32_t *>(area + chunks * CHUNK);
     const int16_t *s = src + (size_t)blockIdx.x * n;
-    for (uint32_t i = threadIdx.x; i < WP; i += 32) area[i] = i < n ? (int32_t)s[i] : 0;
+    for (uint32_t i = threadIdx.x; i < chunks * CHUNK; i += 32) area[cell_phys(i)] = i < n ? (int32_t)s[i] : 0;
+    for (uint32_t i = threadIdx.x; i < chunks; i += 32) mask[i] = 0xFFFFFFFFu;
     __syncwarp();
-    resolve_row(area, dst + (size_t)blockIdx.x * n, n, FTL_MATTE8, even_odd != 0, 0);
+    uint8_t *d = dst + (size_t)blockIdx.x * n;
+    if ((n & 15u) == 0) resolve_row_rule<FTL_MATTE8, true>(area, mask, d, n, chunks, 0, even_odd != 0);
+    else resolve_row_rule<FTL_MATTE8, false>(area, mask, d, n, chunks, 0, even_odd != 0);
 }
 
 // 64-bit FNV-1a per raster (parity checks of large batches): one CTA per
@@ -853,6 +955,15 @@ Engine::~Engine() {
 
 static int engine_init(Engine::Impl *m, int device, void **stream_out);
 
+typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *);
+static TileKernel tile_kernel(int fmt, bool aligned) {
+    switch (fmt) {
+    case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true> : raster_tiles<FTL_MATTE8, false>;
+    case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true> : raster_tiles<FTL_GRAYA8P, false>;
+    default: return aligned ? raster_tiles<FTL_RGBA8P, true> : raster_tiles<FTL_RGBA8P, false>;
+    }
+}
+
 #define ENSURE_INIT()                                                        \
     do {                                                                     \
         CK(cudaSetDevice(device_));                                          \
@@ -879,7 +990,8 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
     m->n_sms = prop.multiProcessorCount;
     m->max_smem = prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
-    CK(cudaFuncSetAttribute(raster_tiles, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+    for (int f = 0; f < 3; f++)
+        for (int a = 0; a < 2; a++) CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
     CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
     *stream_out = m->st;
     return FTL_OK;
@@ -903,8 +1015,9 @@ static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typen
 static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
-    P->WP = ((g.width + 127u) & ~127u) + 4u;  // +4 cells staggers the banks of consecutive rows
-    size_t row_bytes = (size_t)P->WP * 4;
+    P->chunks = (g.width + CHUNK - 1) / CHUNK;
+    P->WP = P->chunks * CHUNK + 4u;  // +4 cells staggers the banks of consecutive rows
+    size_t row_bytes = (size_t)P->WP * 4 + (size_t)P->chunks * 4;
     if (row_bytes > max_smem) {
         set_error("raster width exceeds the shared-memory row tile");
         return FTL_ERR_TOO_WIDE;
@@ -989,7 +1102,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     if (ops_bytes) CK(cudaMemcpyAsync(m.ops.p, m.pin_ops.p, ops_bytes, cudaMemcpyHostToDevice, m.st));
     CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
     m.P = P;
-    m.smem_bytes = (int)((size_t)P.R * P.WP * 4);
+    m.smem_bytes = (int)((size_t)P.R * ((size_t)P.WP * 4 + (size_t)P.chunks * 4));
     m.have_jobs = true;
     return FTL_OK;
 }
@@ -1014,7 +1127,6 @@ int Engine::replay() {
     if ((rc = m.jstate.ensure((size_t)P.n_jobs * sizeof(JobState), st))) return rc;
     Counters *d_cnt = (Counters *)m.counters.p;
     JobState *d_js = (JobState *)m.jstate.p;
-    init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, P.n_jobs); LAUNCHED();
     CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
     uint32_t nv = 0;
     if (P.n_ops > 0) {
@@ -1033,6 +1145,7 @@ int Engine::replay() {
             flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr); LAUNCHED();
         }
     }
+    init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
     // ---- (b) edge prep + binning ----
     if ((rc = m.tcount.ensure((size_t)P.n_tiles * sizeof(uint32_t), st))) return rc;
     if ((rc = m.toff.ensure(((size_t)P.n_tiles + 1) * sizeof(uint32_t), st))) return rc;
@@ -1043,8 +1156,9 @@ int Engine::replay() {
         if ((rc = m.sub_last.ensure((size_t)nv * sizeof(uint32_t), st))) return rc;
         uint32_t vb = std::min<uint32_t>(div_up(nv, 256), (uint32_t)m.n_sms * 8);
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
-        edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p, (uint32_t *)m.sub_last.p); LAUNCHED();
+        vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
         job_finalize<<<div_up(P.n_jobs, 128), 128, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (const uint32_t *)m.sub_last.p, P.n_jobs); LAUNCHED();
+        edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p); LAUNCHED();
         bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
     }
     if ((rc = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_tiles, (uint32_t *)m.toff.p, m.tpart))) return rc;
@@ -1060,7 +1174,9 @@ int Engine::replay() {
     } else if ((rc = m.entries.ensure(sizeof(uint32_t), st))) return rc;
     // ---- (c)+(d) tiles ----
     int occ = 1;
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, raster_tiles, TILE_THREADS, m.smem_bytes));
+    const bool aligned = P.fmt == FTL_MATTE8 ? (P.W % 16 == 0) : (P.fmt == FTL_RGBA8P ? (P.W % 4 == 0) : true);
+    TileKernel tk = tile_kernel((int)P.fmt, aligned);
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, TILE_THREADS, m.smem_bytes));
     if (occ < 1) occ = 1;
     uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(m.n_sms * occ));
     ProfSpan span{};
@@ -1070,7 +1186,7 @@ int Engine::replay() {
         CK(cudaEventCreate(&span.b));
         CK(cudaEventRecord(span.a, st));
     }
-    raster_tiles<<<grid, TILE_THREADS, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
+    tk<<<grid, TILE_THREADS, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
                                                            (const uint32_t *)m.entries.p); LAUNCHED();
     if (prof) {
         CK(cudaEventRecord(span.b, st));
@@ -1200,8 +1316,9 @@ int Engine::accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n
     ENSURE_INIT();
     Impl &m = *impl_;
     if (n == 0 || rows == 0) return FTL_OK;
-    uint32_t WP = (((uint32_t)n + 127u) & ~127u) + 4u;
-    if ((size_t)WP * 4 > m.max_smem) {
+    uint32_t chunks = ((uint32_t)n + CHUNK - 1) / CHUNK;
+    size_t smem = (size_t)chunks * CHUNK * 4 + (size_t)chunks * 4;
+    if (smem > m.max_smem) {
         set_error("row too long for the shared-memory row tile");
         return FTL_ERR_TOO_WIDE;
     }
@@ -1210,7 +1327,7 @@ int Engine::accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n
     int16_t *ds = (int16_t *)m.misc.p;
     uint8_t *dd = (uint8_t *)m.misc.p + n * rows * 2;
     CK(cudaMemcpyAsync(ds, src, n * rows * 2, cudaMemcpyHostToDevice, m.st));
-    accumulate_rows_kernel<<<(uint32_t)rows, 32, WP * 4, m.st>>>(ds, dd, (uint32_t)n, WP, rule == FTL_EVENODD); LAUNCHED();
+    accumulate_rows_kernel<<<(uint32_t)rows, 32, smem, m.st>>>(ds, dd, (uint32_t)n, chunks, rule == FTL_EVENODD); LAUNCHED();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(dst, dd, n * rows, cudaMemcpyDeviceToHost, m.st));
     CK(cudaStreamSynchronize(m.st));
