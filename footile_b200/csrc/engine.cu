@@ -61,7 +61,6 @@ static std::atomic<bool> g_profiling{false};
 // ---------------------------------------------------------------------------
 constexpr uint32_t NONE32 = 0xFFFFFFFFu;
 constexpr int MAX_DEPTH = 24;  // subdivision depth cap (the reference recurses without bound)
-constexpr int TILE_THREADS = 256;
 
 struct __align__(16) JobDesc {  // 64 B, host-filled
     uint32_t op_begin, op_end;
@@ -120,6 +119,7 @@ struct Params {  // per-call constants, passed by value
     uint32_t fmt, bpp, pitch;
     uint32_t log2R, R, n_bands, WP, chunks;  // rows per tile, bands per job, smem row stride (cells), 512-cell chunks per row
     uint32_t n_jobs, n_ops, n_tiles;
+    uint32_t team_warps, team_words, cta_warps;  // warps per row team, smem words per team, warps per CTA
 };
 
 // ---------------------------------------------------------------------------
@@ -669,86 +669,47 @@ __device__ __forceinline__ uint32_t blend_rgba(uint32_t px, uint32_t color, uint
     return o;
 }
 
-// Resolve one row held in shared memory by one warp.  Per 512-cell chunk each
-// lane owns 16 consecutive cells: it reads them (4 LDS.128), zeroes them, scans
-// them serially, one 5-step shuffle scan carries the lane totals across the
-// warp, then the fill rule turns the 16 sums into 16 alpha bytes which are
-// stored (Matte8, one STG.128 per lane: imgbuf.rs:59,93) or blended SrcOver
-// into the raster row (Graya8p/Rgba8p: fig.rs:641-642,662-663).  Chunks whose
-// mask word is zero hold no edge: their pixels take the constant alpha of the
-// running sum without touching shared memory.
-template <int FMT, bool EVEN_ODD, bool ALIGNED>
-__device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t chunks, uint32_t color) {
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t sw = (lane >> 1) & 3u;
-    const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
-    int32_t carry = 0;
-    for (uint32_t ch = 0; ch < chunks; ch++) {
-        const uint32_t m = mask[ch];
-        const uint32_t x = ch * CHUNK + lane * 16;
-        uint32_t a[4];
-        if (m == 0) {
-            uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
-            a[0] = a[1] = a[2] = a[3] = q;
+// Output of one lane's 16 pixels: alpha words a[0..3] (4 pixels each).
+template <int FMT, bool ALIGNED>
+__device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                       uint32_t color, uint32_t clr_a) {
+    if (x >= W) return;
+    if (FMT == FTL_MATTE8) {  // store, colour ignored (fig.rs:632-636; imgbuf.rs:59,93)
+        uint8_t *d = dst + x;
+        if (ALIGNED && x + 16 <= W) {
+            *reinterpret_cast<uint4 *>(d) = make_uint4(a0, a1, a2, a3);
         } else {
-            __syncwarp();
-            if (lane == 0) mask[ch] = 0;
-            int4 v[4];
-            if ((m >> lane) & 1u) {
-                int32_t *base = row + ch * CHUNK + lane * 16;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    int4 *p = reinterpret_cast<int4 *>(base + ((j ^ sw) << 2));
-                    v[j] = *p;
-                    *p = make_int4(0, 0, 0, 0);
-                }
+            for (uint32_t i = 0; i < 16; i++) {
+                uint32_t w = i < 4 ? a0 : (i < 8 ? a1 : (i < 12 ? a2 : a3));
+                if (x + i < W) d[i] = (uint8_t)(w >> (8 * (i & 3)));
+            }
+        }
+    } else if (FMT == FTL_RGBA8P) {  // fig.rs:641-642,662-663 via pix (pix_compat.cuh)
+        uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t w = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
+            if (ALIGNED && x + 4 * j + 4 <= W) {
+                uint4 t = reinterpret_cast<uint4 *>(d)[j];
+                t.x = blend_rgba(t.x, color, w & 0xFF, clr_a);
+                t.y = blend_rgba(t.y, color, (w >> 8) & 0xFF, clr_a);
+                t.z = blend_rgba(t.z, color, (w >> 16) & 0xFF, clr_a);
+                t.w = blend_rgba(t.w, color, w >> 24, clr_a);
+                reinterpret_cast<uint4 *>(d)[j] = t;
             } else {
 #pragma unroll
-                for (int j = 0; j < 4; j++) v[j] = make_int4(0, 0, 0, 0);
+                for (uint32_t i = 0; i < 4; i++)
+                    if (x + 4 * j + i < W) d[4 * j + i] = blend_rgba(d[4 * j + i], color, (w >> (8 * i)) & 0xFF, clr_a);
             }
-            // lane-local inclusive prefix: 4 independent quad scans, then quad offsets
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                v[j].y += v[j].x; v[j].z += v[j].y; v[j].w += v[j].z;
-            }
-            int32_t o1 = v[0].w, o2 = o1 + v[1].w, o3 = o2 + v[2].w, tot = o3 + v[3].w;
-            int32_t inc = tot;
-#pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-                if (lane >= d) inc += o;
-            }
-            const int32_t b0 = carry + inc - tot;
-            carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
-            a[0] = quad_alpha<EVEN_ODD>(v[0].x, v[0].y, v[0].z, v[0].w, b0);
-            a[1] = quad_alpha<EVEN_ODD>(v[1].x, v[1].y, v[1].z, v[1].w, b0 + o1);
-            a[2] = quad_alpha<EVEN_ODD>(v[2].x, v[2].y, v[2].z, v[2].w, b0 + o2);
-            a[3] = quad_alpha<EVEN_ODD>(v[3].x, v[3].y, v[3].z, v[3].w, b0 + o3);
         }
-        if (x >= W) continue;
-        if (FMT == FTL_MATTE8) {
-            uint8_t *d = dst + x;
-            if (ALIGNED && x + 16 <= W) *reinterpret_cast<uint4 *>(d) = make_uint4(a[0], a[1], a[2], a[3]);
-            else
-                for (uint32_t i = 0; i < 16 && x + i < W; i++) d[i] = (uint8_t)(a[i >> 2] >> (8 * (i & 3)));
-        } else if (FMT == FTL_RGBA8P) {
-            uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
-            if (ALIGNED && x + 16 <= W) {
+    } else {  // Graya8p
+        uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    uint4 t = reinterpret_cast<uint4 *>(d)[j];
-                    t.x = blend_rgba(t.x, color, a[j] & 0xFF, clr_a);
-                    t.y = blend_rgba(t.y, color, (a[j] >> 8) & 0xFF, clr_a);
-                    t.z = blend_rgba(t.z, color, (a[j] >> 16) & 0xFF, clr_a);
-                    t.w = blend_rgba(t.w, color, a[j] >> 24, clr_a);
-                    reinterpret_cast<uint4 *>(d)[j] = t;
-                }
-            } else
-                for (uint32_t i = 0; i < 16 && x + i < W; i++) d[i] = blend_rgba(d[i], color, (a[i >> 2] >> (8 * (i & 3))) & 0xFF, clr_a);
-        } else {  // Graya8p
-            uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
-            for (uint32_t i = 0; i < 16 && x + i < W; i++) {
-                uint32_t al = (a[i >> 2] >> (8 * (i & 3))) & 0xFF, p = d[i];
+        for (uint32_t i = 0; i < 16; i++) {
+            uint32_t w = i < 4 ? a0 : (i < 8 ? a1 : (i < 12 ? a2 : a3));
+            if (x + i < W) {
+                uint32_t al = (w >> (8 * (i & 3))) & 0xFF, p = d[i];
                 uint32_t sa1 = 255u - pix::ch8_mul(al, clr_a);
                 d[i] = (uint16_t)(pix::src_over_ch(p & 0xFF, color & 0xFF, al, sa1) | (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, al, sa1) << 8));
             }
@@ -756,56 +717,146 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     }
 }
 
-template <int FMT, bool ALIGNED>
-__device__ __forceinline__ void resolve_row_rule(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t chunks, uint32_t color,
-                                                 bool even_odd) {
-    if (even_odd) resolve_row<FMT, true, ALIGNED>(row, mask, dst, W, chunks, color);
-    else resolve_row<FMT, false, ALIGNED>(row, mask, dst, W, chunks, color);
+// Resolve chunks [c_begin, c_end) of one row held in shared memory, by one
+// warp.  Per 512-cell chunk each lane owns 16 consecutive cells: it reads them
+// (4 LDS.128), zeroes them, scans them serially, one 5-step shuffle scan
+// carries the lane totals across the warp, then the fill rule turns the 16
+// sums into 16 alpha bytes which are stored (Matte8: one STG.128 per lane) or
+// blended SrcOver into the raster row (Graya8p/Rgba8p).  A chunk whose mask
+// word is zero holds no edge: its pixels take the constant alpha of the
+// running sum without touching shared memory.
+template <int FMT, bool EVEN_ODD, bool ALIGNED>
+__device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t c_begin, uint32_t c_end,
+                                            int32_t carry, uint32_t color) {
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t sw = (lane >> 1) & 3u;
+    const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    for (uint32_t ch = c_begin; ch < c_end; ch++) {
+        const uint32_t m = mask[ch];
+        const uint32_t x = ch * CHUNK + lane * 16;
+        if (m == 0) {
+            const uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
+            emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
+            continue;
+        }
+        __syncwarp();
+        if (lane == 0) mask[ch] = 0;
+        int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
+        if ((m >> lane) & 1u) {
+            int32_t *base = row + ch * CHUNK + lane * 16;
+            int4 *p0 = reinterpret_cast<int4 *>(base + ((0 ^ sw) << 2)), *p1 = reinterpret_cast<int4 *>(base + ((1 ^ sw) << 2));
+            int4 *p2 = reinterpret_cast<int4 *>(base + ((2 ^ sw) << 2)), *p3 = reinterpret_cast<int4 *>(base + ((3 ^ sw) << 2));
+            v0 = *p0; v1 = *p1; v2 = *p2; v3 = *p3;
+            const int4 z = make_int4(0, 0, 0, 0);
+            *p0 = z; *p1 = z; *p2 = z; *p3 = z;
+        }
+        // lane-local inclusive prefix: 4 independent quad scans, then quad offsets
+        v0.y += v0.x; v0.z += v0.y; v0.w += v0.z;
+        v1.y += v1.x; v1.z += v1.y; v1.w += v1.z;
+        v2.y += v2.x; v2.z += v2.y; v2.w += v2.z;
+        v3.y += v3.x; v3.z += v3.y; v3.w += v3.z;
+        const int32_t o1 = v0.w, o2 = o1 + v1.w, o3 = o2 + v2.w, tot = o3 + v3.w;
+        int32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        const int32_t b0 = carry + inc - tot;
+        carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const uint32_t a0 = quad_alpha<EVEN_ODD>(v0.x, v0.y, v0.z, v0.w, b0);
+        const uint32_t a1 = quad_alpha<EVEN_ODD>(v1.x, v1.y, v1.z, v1.w, b0 + o1);
+        const uint32_t a2 = quad_alpha<EVEN_ODD>(v2.x, v2.y, v2.z, v2.w, b0 + o2);
+        const uint32_t a3 = quad_alpha<EVEN_ODD>(v3.x, v3.y, v3.z, v3.w, b0 + o3);
+        emit16<FMT, ALIGNED>(dst, x, W, a0, a1, a2, a3, color, clr_a);
+    }
 }
 
-// Persistent CTAs over (job, band) tiles.
+// Sum of the cells of chunks [c_begin, c_end) (no zeroing): the carry a later
+// warp of the same row team starts from.
+__device__ __forceinline__ int32_t segment_total(const int32_t *row, const uint32_t *mask, uint32_t c_begin, uint32_t c_end) {
+    const uint32_t lane = threadIdx.x & 31;
+    int32_t s = 0;
+    for (uint32_t ch = c_begin; ch < c_end; ch++) {
+        const uint32_t m = mask[ch];
+        if ((m >> lane) & 1u) {
+            const int4 *p = reinterpret_cast<const int4 *>(row + ch * CHUNK + lane * 16);
+#pragma unroll
+            for (int j = 0; j < 4; j++) s += p[j].x + p[j].y + p[j].z + p[j].w;  // swizzle permutes quads inside the group only
+        }
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
+    return s;
+}
+
+__device__ __forceinline__ void team_sync(uint32_t T, uint32_t team) {
+    if (T == 1) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T * 32) : "memory");
+}
+
+// The tile kernel.  A row TEAM of T warps (T = 1 for rows up to 4096 px) owns
+// one shared-memory row buffer and walks the rows of a (job, band) tile: the
+// team's lanes scatter the coverage of every edge crossing the row, then the
+// row is resolved and written.  Teams never wait for each other, so the
+// scatter latency of one team hides behind the resolve of the others.
 template <int FMT, bool ALIGNED>
-__global__ void __launch_bounds__(TILE_THREADS) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
-                                                             const JobState *__restrict__ JS, Params P,
-                                                             const uint32_t *__restrict__ tile_off,
-                                                             const uint32_t *__restrict__ entries) {
-    extern __shared__ __align__(16) int32_t area[];
-    uint32_t *masks = reinterpret_cast<uint32_t *>(area + P.R * P.WP);
-    const uint32_t words = P.R * P.WP + P.R * P.chunks;
-    for (uint32_t i = threadIdx.x; i < words; i += TILE_THREADS) area[i] = 0;
-    __syncthreads();
-    const uint32_t warp = threadIdx.x >> 5;
-    for (uint32_t tile = blockIdx.x; tile < P.n_tiles; tile += gridDim.x) {
+__global__ void __launch_bounds__(256) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+                                                    const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
+                                                    const uint32_t *__restrict__ entries) {
+    extern __shared__ __align__(16) int32_t smem[];
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t T = P.team_warps;
+    const uint32_t team = warp / T, wt = warp - team * T;
+    const uint32_t teams_per_cta = (blockDim.x >> 5) / T;
+    int32_t *cells = smem + team * P.team_words;
+    uint32_t *mask = reinterpret_cast<uint32_t *>(cells + P.chunks * CHUNK);
+    int32_t *seg_tot = reinterpret_cast<int32_t *>(mask + P.chunks);
+    const uint32_t tl = wt * 32 + lane, team_lanes = T * 32;
+    for (uint32_t i = tl; i < P.team_words; i += team_lanes) cells[i] = 0;
+    team_sync(T, team);
+    const uint32_t cpw = (P.chunks + T - 1) / T;  // chunks per warp of the team
+    const uint32_t c_begin = min(wt * cpw, P.chunks), c_end = min(c_begin + cpw, P.chunks);
+    const uint32_t n_teams = gridDim.x * teams_per_cta;
+    for (uint32_t tile = blockIdx.x * teams_per_cta + team; tile < P.n_tiles; tile += n_teams) {
         const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
         const JobState js = JS[j];
-        const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
+        int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
         int32_t row_hi = row0 + (int32_t)P.R;
         if (row_hi > (int32_t)P.row_end) row_hi = (int32_t)P.row_end;
-        if (row_hi <= js.first_row) continue;  // rows above the figure are untouched (fig.rs:497)
-        const JobDesc &jd = jobs[j];
-        // ---- (c) scatter: one thread per (edge, row of the band) ----
+        if (row0 < js.first_row) row0 = js.first_row;  // rows above the figure are untouched (fig.rs:497)
+        if (row0 >= row_hi) continue;
+        const unsigned long long raster = jobs[j].raster;
+        const uint32_t rule = jobs[j].rule, color = jobs[j].color;
         const uint32_t n_slots = js.vtx_end - js.vtx_begin;
         const bool direct = n_slots <= DIRECT_MAX;
         const uint32_t e0 = direct ? js.vtx_begin : tile_off[tile];
         const uint32_t ne = direct ? n_slots : tile_off[tile + 1] - e0;
-        for (uint32_t i = threadIdx.x; i < (ne << P.log2R); i += TILE_THREADS) {
-            const uint32_t rr = i & (P.R - 1);
-            const int32_t ry = row0 + (int32_t)rr;
-            if (ry >= row_hi) continue;
-            const uint32_t k = direct ? e0 + (i >> P.log2R) : entries[e0 + (i >> P.log2R)];
-            const EdgeRec e = E[k];
-            if (!(e.flags & 1u) || ry < e.ry0 || ry > e.ry1) continue;
-            scatter_edge_row(e, ry, area + rr * P.WP, masks + rr * P.chunks, (int32_t)P.W);
+        // the first team_lanes edges of the tile stay in registers for all its rows
+        EdgeRec mine;
+        mine.flags = 0;
+        if (tl < ne) mine = E[direct ? e0 + tl : entries[e0 + tl]];
+        for (int32_t ry = row0; ry < row_hi; ry++) {
+            // ---- (c) scatter: one lane per edge crossing this row ----
+            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) scatter_edge_row(mine, ry, cells, mask, (int32_t)P.W);
+            for (uint32_t i = tl + team_lanes; i < ne; i += team_lanes) {
+                const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
+                if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) scatter_edge_row(e, ry, cells, mask, (int32_t)P.W);
+            }
+            team_sync(T, team);
+            // ---- (d) resolve ----
+            int32_t carry = 0;
+            if (T > 1) {
+                int32_t s = segment_total(cells, mask, c_begin, c_end);
+                if (lane == 0) seg_tot[wt] = s;
+                team_sync(T, team);
+                for (uint32_t u = 0; u < wt; u++) carry += seg_tot[u];
+            }
+            uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
+            if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dst, P.W, c_begin, c_end, carry, color);
+            else resolve_row<FMT, false, ALIGNED>(cells, mask, dst, P.W, c_begin, c_end, carry, color);
+            team_sync(T, team);
         }
-        __syncthreads();
-        // ---- (d) resolve: one warp per row ----
-        for (uint32_t rr = warp; rr < P.R; rr += TILE_THREADS / 32) {
-            const int32_t ry = row0 + (int32_t)rr;
-            if (ry < js.first_row || ry >= row_hi) continue;
-            uint8_t *dst = reinterpret_cast<uint8_t *>(jd.raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
-            resolve_row_rule<FMT, ALIGNED>(area + rr * P.WP, masks + rr * P.chunks, dst, P.W, P.chunks, jd.color, jd.rule == FTL_EVENODD);
-        }
-        __syncthreads();
     }
 }
 
@@ -819,8 +870,14 @@ __global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__re
     for (uint32_t i = threadIdx.x; i < chunks; i += 32) mask[i] = 0xFFFFFFFFu;
     __syncwarp();
     uint8_t *d = dst + (size_t)blockIdx.x * n;
-    if ((n & 15u) == 0) resolve_row_rule<FTL_MATTE8, true>(area, mask, d, n, chunks, 0, even_odd != 0);
-    else resolve_row_rule<FTL_MATTE8, false>(area, mask, d, n, chunks, 0, even_odd != 0);
+    const bool al = (n & 15u) == 0;
+    if (even_odd) {
+        if (al) resolve_row<FTL_MATTE8, true, true>(area, mask, d, n, 0, chunks, 0, 0);
+        else resolve_row<FTL_MATTE8, true, false>(area, mask, d, n, 0, chunks, 0, 0);
+    } else {
+        if (al) resolve_row<FTL_MATTE8, false, true>(area, mask, d, n, 0, chunks, 0, 0);
+        else resolve_row<FTL_MATTE8, false, false>(area, mask, d, n, 0, chunks, 0, 0);
+    }
 }
 
 // 64-bit FNV-1a per raster (parity checks of large batches): one CTA per
@@ -1016,14 +1073,19 @@ static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
-    P->WP = P->chunks * CHUNK + 4u;  // +4 cells staggers the banks of consecutive rows
-    size_t row_bytes = (size_t)P->WP * 4 + (size_t)P->chunks * 4;
-    if (row_bytes > max_smem) {
+    P->WP = P->chunks * CHUNK;
+    // one row team per 8 chunks (4096 px) of width: T = 1, 2, 4 or 8 warps share a row buffer
+    uint32_t T = 1;
+    while (T < 8 && P->chunks > 8 * T) T <<= 1;
+    P->team_warps = T;
+    P->team_words = (P->chunks * CHUNK + P->chunks + 8 + 3u) & ~3u;  // cells + masks + segment totals, 16-byte multiple
+    P->cta_warps = T > 4 ? 8 : 4;
+    size_t cta_bytes = (size_t)P->team_words * 4 * (P->cta_warps / T);
+    if (cta_bytes > max_smem) {
         set_error("raster width exceeds the shared-memory row tile");
         return FTL_ERR_TOO_WIDE;
     }
-    uint32_t log2R = 0;
-    while (log2R < 5 && (row_bytes << (log2R + 1)) <= 72 * 1024) log2R++;
+    uint32_t log2R = 3;  // band height: binning granularity only (a team keeps one row in shared memory)
     while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
     P->log2R = log2R; P->R = 1u << log2R;
     P->n_bands = div_up(g.rows(), P->R);
@@ -1102,7 +1164,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     if (ops_bytes) CK(cudaMemcpyAsync(m.ops.p, m.pin_ops.p, ops_bytes, cudaMemcpyHostToDevice, m.st));
     CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
     m.P = P;
-    m.smem_bytes = (int)((size_t)P.R * ((size_t)P.WP * 4 + (size_t)P.chunks * 4));
+    m.smem_bytes = (int)((size_t)P.team_words * 4 * (P.cta_warps / P.team_warps));
     m.have_jobs = true;
     return FTL_OK;
 }
@@ -1176,9 +1238,10 @@ int Engine::replay() {
     int occ = 1;
     const bool aligned = P.fmt == FTL_MATTE8 ? (P.W % 16 == 0) : (P.fmt == FTL_RGBA8P ? (P.W % 4 == 0) : true);
     TileKernel tk = tile_kernel((int)P.fmt, aligned);
-    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, TILE_THREADS, m.smem_bytes));
+    const int tile_threads = (int)P.cta_warps * 32;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
-    uint32_t grid = std::min<uint32_t>(P.n_tiles, (uint32_t)(m.n_sms * occ));
+    uint32_t grid = std::min<uint32_t>(div_up(P.n_tiles, P.cta_warps / P.team_warps), (uint32_t)(m.n_sms * occ));
     ProfSpan span{};
     const bool prof = g_profiling.load();
     if (prof) {
@@ -1186,7 +1249,7 @@ int Engine::replay() {
         CK(cudaEventCreate(&span.b));
         CK(cudaEventRecord(span.a, st));
     }
-    tk<<<grid, TILE_THREADS, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
+    tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
                                                            (const uint32_t *)m.entries.p); LAUNCHED();
     if (prof) {
         CK(cudaEventRecord(span.b, st));
