@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -649,14 +650,16 @@ __device__ __forceinline__ uint32_t quad_alpha(int32_t p0, int32_t p1, int32_t p
         hi = __viaddmin_s16x2_relu(hi, bp, 0x00FF00FFu);
         return __byte_perm(lo, hi, 0x6420);
     } else {
-        uint32_t lo = __byte_perm((uint32_t)(p0 + base), (uint32_t)(p1 + base), 0x5410);
-        uint32_t hi = __byte_perm((uint32_t)(p2 + base), (uint32_t)(p3 + base), 0x5410);
+        const uint32_t bp = __byte_perm((uint32_t)base, (uint32_t)base, 0x1010);
+        uint32_t lo = __byte_perm((uint32_t)p0, (uint32_t)p1, 0x5410), hi = __byte_perm((uint32_t)p2, (uint32_t)p3, 0x5410);
+        lo = __viaddmin_s16x2(lo, bp, 0x7FFF7FFFu);  // wrapping i16 add of the base, per halfword
+        hi = __viaddmin_s16x2(hi, bp, 0x7FFF7FFFu);
         // |(s & 0xFF) - (s & 0x100)| = odd ? 256 - v : v, then 256 saturates to 255
         uint32_t bl = (lo >> 8) & 0x00010001u, bh = (hi >> 8) & 0x00010001u;
         lo = ((lo & 0x00FF00FFu) ^ (bl * 0xFFu)) + bl;
         hi = ((hi & 0x00FF00FFu) ^ (bh * 0xFFu)) + bh;
-        lo -= (lo >> 8) & 0x00010001u;
-        hi -= (hi >> 8) & 0x00010001u;
+        lo = __vimin_s16x2_relu(lo, 0x00FF00FFu);
+        hi = __vimin_s16x2_relu(hi, 0x00FF00FFu);
         return __byte_perm(lo, hi, 0x6420);
     }
 }
@@ -731,11 +734,11 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sw = (lane >> 1) & 3u;
     const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);  // alpha of an edge-free span at the current sum
     for (uint32_t ch = c_begin; ch < c_end; ch++) {
         const uint32_t m = mask[ch];
         const uint32_t x = ch * CHUNK + lane * 16;
         if (m == 0) {
-            const uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
             emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
             continue;
         }
@@ -769,6 +772,7 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         const uint32_t a2 = quad_alpha<EVEN_ODD>(v2.x, v2.y, v2.z, v2.w, b0 + o2);
         const uint32_t a3 = quad_alpha<EVEN_ODD>(v3.x, v3.y, v3.z, v3.w, b0 + o3);
         emit16<FMT, ALIGNED>(dst, x, W, a0, a1, a2, a3, color, clr_a);
+        q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
     }
 }
 
@@ -1048,7 +1052,10 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
     m->max_smem = prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
     for (int f = 0; f < 3; f++)
-        for (int a = 0; a < 2; a++) CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+        for (int a = 0; a < 2; a++) {
+            CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+            CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
     CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
     *stream_out = m->st;
     return FTL_OK;
@@ -1075,8 +1082,9 @@ static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
     P->WP = P->chunks * CHUNK;
     // one row team per 8 chunks (4096 px) of width: T = 1, 2, 4 or 8 warps share a row buffer
-    uint32_t T = 1;
-    while (T < 8 && P->chunks > 8 * T) T <<= 1;
+    uint32_t T = 1, cpw_max = 8;
+    if (const char *ev = getenv("FTL_CHUNKS_PER_WARP")) cpw_max = (uint32_t)std::max(1, atoi(ev));  // tuning knob
+    while (T < 8 && P->chunks > cpw_max * T) T <<= 1;
     P->team_warps = T;
     P->team_words = (P->chunks * CHUNK + P->chunks + 8 + 3u) & ~3u;  // cells + masks + segment totals, 16-byte multiple
     P->cta_warps = T > 4 ? 8 : 4;
