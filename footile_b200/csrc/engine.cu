@@ -112,7 +112,10 @@ struct Counters {
     uint32_t nv;         // vertices after intake
     uint32_t n_entries;  // (edge,band) pairs after binning
     uint32_t n_popped;   // closing vertices dropped by the sub-figure close rule (fig.rs:376-380)
-    uint32_t pad;
+    uint32_t overflow;   // a speculatively sized scratch buffer was too small: nothing was drawn, the host re-runs
+    uint32_t need_v;     // vertices the call needed when it overflowed
+    uint32_t need_e;     // bin entries the call needed when it overflowed
+    uint32_t pad[2];
 };
 
 struct Params {  // per-call constants, passed by value
@@ -229,6 +232,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const typename Op::T 
         if (base + i < n) out[base + i] = run;
         run = Op::combine(run, v[i]);
         if (base + i + 1 == n) out[n] = run;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// capacity guards: scratch buffers are sized from the previous call, so the
+// pipeline runs without a host round trip; if a count exceeds its buffer the
+// call draws nothing and the host repeats it with exact sizes.
+// ---------------------------------------------------------------------------
+__global__ void set_vertex_count(Counters *C, const SumHead *__restrict__ off, uint32_t n_ops, uint32_t cap_v) {
+    uint32_t nv = off[n_ops].sum;
+    if (nv > cap_v) {
+        C->overflow = 1;
+        C->need_v = nv;
+        nv = 0;
+    }
+    C->nv = nv;
+}
+__global__ void set_entry_count(Counters *C, const uint32_t *__restrict__ toff, uint32_t n_tiles, uint32_t cap_e) {
+    uint32_t n = toff[n_tiles];
+    C->n_entries = n;
+    if (n > cap_e) {
+        C->overflow = 1;
+        C->need_e = n;
     }
 }
 
@@ -352,7 +378,8 @@ template <bool WIDE, bool EMIT>
 __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                    const float *__restrict__ opw, SumHead *__restrict__ cnt,
                                                    const SumHead *__restrict__ off, Vtx *__restrict__ vout,
-                                                   float *__restrict__ wout) {
+                                                   float *__restrict__ wout, const Counters *__restrict__ C) {
+    if (EMIT && C && C->overflow) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
         const ftl_path_op op = ops[i];
         OpSink<WIDE, EMIT> sink;
@@ -537,6 +564,7 @@ template <bool FILL>
 __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
                                                  const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
                                                  const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ entries) {
+    if (FILL && C->overflow) return;
     const uint32_t nv = C->nv;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t span = gridDim.x * blockDim.x;
@@ -807,7 +835,8 @@ __device__ __forceinline__ void team_sync(uint32_t T, uint32_t team) {
 template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(256) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                     const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
-                                                    const uint32_t *__restrict__ entries) {
+                                                    const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
+    if (C->overflow) return;
     extern __shared__ __align__(16) int32_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const uint32_t T = P.team_warps;
@@ -958,11 +987,24 @@ struct Engine::Impl {
     size_t max_smem = 0;
     DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc;
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
+    PinBuf pin_ring;
     // resident job set
     Params P{};
     bool have_jobs = false;
     int smem_bytes = 0;
+    // replays issued without a host round trip whose counters have not been checked yet
+    uint32_t pending = 0;
+    bool use_graph = true;
+    cudaGraphExec_t graph = nullptr;
+    uint64_t graph_kernels = 0;  // kernel launches one replay of the graph stands for
+    std::vector<uint64_t> graph_key;
+    void drop_graph() {
+        if (graph) cudaGraphExecDestroy(graph);
+        graph = nullptr;
+        graph_key.clear();
+    }
 };
+constexpr uint32_t RING = 64;
 
 int Engine::device_count(int *count) {
     int n = 0;
@@ -1007,7 +1049,8 @@ Engine::~Engine() {
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
                               &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc})
                 b->release();
-            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc}) b->release();
+            m.drop_graph();
+            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring}) b->release();
             cudaStreamDestroy(impl_->st);
         }
         delete impl_;
@@ -1015,8 +1058,10 @@ Engine::~Engine() {
 }
 
 static int engine_init(Engine::Impl *m, int device, void **stream_out);
+static int run_pipeline(Engine::Impl &m, bool exact);
+static int resolve_pending(Engine::Impl &m);
 
-typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *);
+typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *, const Counters *);
 static TileKernel tile_kernel(int fmt, bool aligned) {
     switch (fmt) {
     case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true> : raster_tiles<FTL_MATTE8, false>;
@@ -1057,6 +1102,7 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
             CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+    if (const char *ev = getenv("FTL_NO_GRAPH")) m->use_graph = atoi(ev) == 0;
     *stream_out = m->st;
     return FTL_OK;
 }
@@ -1121,6 +1167,10 @@ static int validate_ops(const ftl_path_op *ops, size_t n) {
 int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
     ENSURE_INIT();
     Impl &m = *impl_;
+    {
+        int rc0 = resolve_pending(m);  // earlier replays refer to the job set that is about to be replaced
+        if (rc0) return rc0;
+    }
     if (jobs.empty() || g.rows() == 0 || g.width == 0) {
         m.have_jobs = false;
         return FTL_OK;
@@ -1183,10 +1233,13 @@ int Engine::fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_
     return replay();
 }
 
-int Engine::replay() {
-    ENSURE_INIT();
-    Impl &m = *impl_;
-    if (!m.have_jobs) return FTL_OK;
+// One pass of the device pipeline over the resident job set.
+//   exact = true : sizes are read back after each scan (two host round trips) and the scratch
+//                  buffers are grown to fit; used for the first call and after an overflow.
+//   exact = false: buffers keep the capacity of earlier calls, every kernel takes its counts
+//                  from device memory and nothing waits for the host; the stages before the tile
+//                  kernel are replayed from a CUDA graph.
+static int run_pipeline(Engine::Impl &m, bool exact) {
     const Params P = m.P;
     cudaStream_t st = m.st;
     int rc;
@@ -1194,54 +1247,108 @@ int Engine::replay() {
     const JobDesc *d_jobs = (const JobDesc *)m.jobs.p;
     if ((rc = m.counters.ensure(sizeof(Counters), st))) return rc;
     if ((rc = m.pin_small.ensure(64))) return rc;
+    if ((rc = m.pin_ring.ensure(RING * sizeof(Counters)))) return rc;
     if ((rc = m.jstate.ensure((size_t)P.n_jobs * sizeof(JobState), st))) return rc;
-    Counters *d_cnt = (Counters *)m.counters.p;
-    JobState *d_js = (JobState *)m.jstate.p;
-    CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
-    uint32_t nv = 0;
-    if (P.n_ops > 0) {
-        // ---- (a) flatten: count, scan, emit ----
-        if ((rc = m.cnt.ensure((size_t)P.n_ops * sizeof(SumHead), st))) return rc;
-        if ((rc = m.off.ensure(((size_t)P.n_ops + 1) * sizeof(SumHead), st))) return rc;
-        uint32_t fb = std::min<uint32_t>(div_up(P.n_ops, 128), (uint32_t)m.n_sms * 16);
-        flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
-        if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
-        CK(cudaMemcpyAsync(&d_cnt->nv, &((SumHead *)m.off.p)[P.n_ops].sum, sizeof(uint32_t), cudaMemcpyDeviceToDevice, st));
-        CK(cudaMemcpyAsync(m.pin_small.p, &d_cnt->nv, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        nv = *(uint32_t *)m.pin_small.p;
-        if (nv > 0) {
-            if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
-            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr); LAUNCHED();
-        }
-    }
-    init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
-    // ---- (b) edge prep + binning ----
+    if ((rc = m.cnt.ensure((size_t)(P.n_ops + 1) * sizeof(SumHead), st))) return rc;
+    if ((rc = m.off.ensure(((size_t)P.n_ops + 1) * sizeof(SumHead), st))) return rc;
     if ((rc = m.tcount.ensure((size_t)P.n_tiles * sizeof(uint32_t), st))) return rc;
     if ((rc = m.toff.ensure(((size_t)P.n_tiles + 1) * sizeof(uint32_t), st))) return rc;
-    CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
-    uint32_t n_entries = 0;
-    if (nv > 0) {
-        if ((rc = m.edges.ensure((size_t)nv * sizeof(EdgeRec), st))) return rc;
-        if ((rc = m.sub_last.ensure((size_t)nv * sizeof(uint32_t), st))) return rc;
-        uint32_t vb = std::min<uint32_t>(div_up(nv, 256), (uint32_t)m.n_sms * 8);
+    if ((rc = m.partials.ensure((size_t)div_up(P.n_ops + 1, SCAN_BLOCK) * sizeof(SumHead), st))) return rc;
+    if ((rc = m.tpart.ensure((size_t)div_up(P.n_tiles + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return rc;
+    if (!exact) {
+        if ((rc = m.vtx.ensure(sizeof(Vtx), st))) return rc;
+        if ((rc = m.edges.ensure(sizeof(EdgeRec), st))) return rc;
+        if ((rc = m.sub_last.ensure(sizeof(uint32_t), st))) return rc;
+        if ((rc = m.entries.ensure(sizeof(uint32_t), st))) return rc;
+    }
+    Counters *d_cnt = (Counters *)m.counters.p;
+    JobState *d_js = (JobState *)m.jstate.p;
+    uint32_t cap_v = (uint32_t)std::min<size_t>({m.vtx.cap / sizeof(Vtx), m.edges.cap / sizeof(EdgeRec), m.sub_last.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF});
+    uint32_t cap_e = (uint32_t)std::min<size_t>(m.entries.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF);
+    const uint32_t fb = std::min<uint32_t>(div_up(P.n_ops ? P.n_ops : 1, 128), (uint32_t)m.n_sms * 16);
+
+    // ---- stages (a) and (b), as a replayable sequence ----
+    auto front = [&](bool sync_sizes) -> int {
+        CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
+        uint32_t nv_hint = cap_v;
+        if (P.n_ops > 0) {
+            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
+            int r2 = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials);
+            if (r2) return r2;
+            if (sync_sizes) {
+                CK(cudaMemcpyAsync(m.pin_small.p, &((SumHead *)m.off.p)[P.n_ops].sum, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+                uint32_t nv = *(uint32_t *)m.pin_small.p;
+                size_t want = nv ? nv : 1;
+                if ((r2 = m.vtx.ensure(want * sizeof(Vtx), st))) return r2;
+                if ((r2 = m.edges.ensure(want * sizeof(EdgeRec), st))) return r2;
+                if ((r2 = m.sub_last.ensure(want * sizeof(uint32_t), st))) return r2;
+                cap_v = (uint32_t)std::min<size_t>({m.vtx.cap / sizeof(Vtx), m.edges.cap / sizeof(EdgeRec), m.sub_last.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF});
+                nv_hint = nv;
+            }
+            set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED();
+            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt); LAUNCHED();
+        }
+        init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
+        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
+        const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
         vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
         job_finalize<<<div_up(P.n_jobs, 128), 128, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (const uint32_t *)m.sub_last.p, P.n_jobs); LAUNCHED();
         edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p); LAUNCHED();
         bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
-    }
-    if ((rc = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_tiles, (uint32_t *)m.toff.p, m.tpart))) return rc;
-    if (nv > 0) {
-        CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_tiles], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
-        CK(cudaStreamSynchronize(st));
-        n_entries = *(uint32_t *)m.pin_small.p;
-        if ((rc = m.entries.ensure((size_t)(n_entries ? n_entries : 1) * sizeof(uint32_t), st))) return rc;
+        int r3 = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_tiles, (uint32_t *)m.toff.p, m.tpart);
+        if (r3) return r3;
+        if (sync_sizes) {
+            CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_tiles], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            uint32_t n_entries = *(uint32_t *)m.pin_small.p;
+            if ((r3 = m.entries.ensure((size_t)(n_entries ? n_entries : 1) * sizeof(uint32_t), st))) return r3;
+            cap_e = (uint32_t)std::min<size_t>(m.entries.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF);
+        }
+        set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_tiles, cap_e); LAUNCHED();
         CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
-        uint32_t vb = std::min<uint32_t>(div_up(nv, 256), (uint32_t)m.n_sms * 8);
         bin_edges<true><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
                                             (uint32_t *)m.entries.p); LAUNCHED();
-    } else if ((rc = m.entries.ensure(sizeof(uint32_t), st))) return rc;
+        CK(cudaGetLastError());
+        return FTL_OK;
+    };
+
+    if (exact) {
+        m.drop_graph();
+        if ((rc = front(true))) return rc;
+    } else if (!m.use_graph) {
+        if ((rc = front(false))) return rc;
+    } else {
+        // the sequence depends only on these values: replay the captured graph while they are unchanged
+        std::vector<uint64_t> key = {(uint64_t)(uintptr_t)m.ops.p, (uint64_t)(uintptr_t)m.jobs.p, (uint64_t)(uintptr_t)m.cnt.p, (uint64_t)(uintptr_t)m.off.p,
+                                     (uint64_t)(uintptr_t)m.partials.p, (uint64_t)(uintptr_t)m.vtx.p, (uint64_t)(uintptr_t)m.edges.p,
+                                     (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
+                                     (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
+                                     (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
+                                     P.n_tiles, P.team_warps};
+        if (!m.graph || key != m.graph_key) {
+            m.drop_graph();
+            cudaGraph_t g = nullptr;
+            const uint64_t l0 = g_launches.load();
+            CK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            rc = front(false);
+            cudaError_t ce = cudaStreamEndCapture(st, &g);
+            m.graph_kernels = g_launches.load() - l0;
+            g_launches.fetch_sub(m.graph_kernels);  // captured, not launched
+            if (rc) {
+                if (g) cudaGraphDestroy(g);
+                return rc;
+            }
+            CK(ce);
+            CK(cudaGraphInstantiate(&m.graph, g, 0));
+            CK(cudaGraphDestroy(g));
+            m.graph_key = key;
+        }
+        CK(cudaGraphLaunch(m.graph, st));
+        g_launches.fetch_add(m.graph_kernels, std::memory_order_relaxed);
+    }
+
     // ---- (c)+(d) tiles ----
     int occ = 1;
     const bool aligned = P.fmt == FTL_MATTE8 ? (P.W % 16 == 0) : (P.fmt == FTL_RGBA8P ? (P.W % 4 == 0) : true);
@@ -1258,13 +1365,46 @@ int Engine::replay() {
         CK(cudaEventRecord(span.a, st));
     }
     tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
-                                                           (const uint32_t *)m.entries.p); LAUNCHED();
+                                                 (const uint32_t *)m.entries.p, d_cnt); LAUNCHED();
     if (prof) {
         CK(cudaEventRecord(span.b, st));
         g_spans.push_back(span);
     }
     CK(cudaGetLastError());
+    if (!exact) {
+        CK(cudaMemcpyAsync((Counters *)m.pin_ring.p + m.pending, d_cnt, sizeof(Counters), cudaMemcpyDeviceToHost, st));
+        m.pending++;
+    }
     return FTL_OK;
+}
+
+// Check the counters of the replays issued since the last check; repeat, with exact sizes, those
+// that found a scratch buffer too small (they drew nothing).
+static int resolve_pending(Engine::Impl &m) {
+    if (m.pending == 0) return FTL_OK;
+    CK(cudaStreamSynchronize(m.st));
+    uint32_t redo = 0;
+    const Counters *ring = (const Counters *)m.pin_ring.p;
+    for (uint32_t i = 0; i < m.pending; i++) redo += ring[i].overflow ? 1u : 0u;
+    m.pending = 0;
+    for (uint32_t i = 0; i < redo; i++) {
+        int rc = run_pipeline(m, true);
+        if (rc) return rc;
+    }
+    return FTL_OK;
+}
+
+int Engine::replay() {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (!m.have_jobs) return FTL_OK;
+    if (m.pending >= RING) {
+        int rc = resolve_pending(m);
+        if (rc) return rc;
+    }
+    // speculate once every scratch buffer has a capacity from an earlier call
+    const bool exact = m.vtx.cap == 0 || m.edges.cap == 0 || m.entries.cap == 0;
+    return run_pipeline(m, exact);
 }
 
 int Engine::last_fill_info(FillInfo *info) {
@@ -1272,6 +1412,10 @@ int Engine::last_fill_info(FillInfo *info) {
     Impl &m = *impl_;
     *info = FillInfo();
     if (!m.have_jobs) return FTL_OK;
+    {
+        int rc = resolve_pending(m);
+        if (rc) return rc;
+    }
     JobState js;
     Counters c;
     CK(cudaStreamSynchronize(m.st));
@@ -1290,8 +1434,9 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     xy->clear();
     subs->clear();
     if (n_ops == 0) return FTL_OK;
-    int rc = validate_ops(ops, n_ops);
+    int rc = resolve_pending(m);
     if (rc) return rc;
+    if ((rc = validate_ops(ops, n_ops))) return rc;
     cudaStream_t st = m.st;
     Params P{};
     P.n_jobs = 1;
@@ -1309,7 +1454,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
+    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     SumHead tot;
     CK(cudaStreamSynchronize(st));
@@ -1317,7 +1462,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     uint32_t nv = tot.sum;
     if (nv == 0) return FTL_OK;
     if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
-    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr); LAUNCHED();
+    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, nullptr); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     std::vector<Vtx> v(nv);
     CK(cudaMemcpy(v.data(), m.vtx.p, (size_t)nv * sizeof(Vtx), cudaMemcpyDeviceToHost));
@@ -1346,8 +1491,9 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     out->counts.assign(n_ops, 0);
     out->xyw.clear();
     if (n_ops == 0) return FTL_OK;
-    int rc = validate_ops(ops, n_ops);
+    int rc = resolve_pending(m);
     if (rc) return rc;
+    if ((rc = validate_ops(ops, n_ops))) return rc;
     cudaStream_t st = m.st;
     Params P{};
     P.n_jobs = 1;
@@ -1367,7 +1513,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr); LAUNCHED();
+    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     CK(cudaStreamSynchronize(st));
     std::vector<SumHead> off(n_ops + 1);
@@ -1376,7 +1522,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     for (size_t i = 0; i < n_ops; i++) out->counts[i] = off[i + 1].sum - off[i].sum;
     if (np == 0) return FTL_OK;
     if ((rc = m.wide.ensure((size_t)np * 3 * sizeof(float), st))) return rc;
-    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p); LAUNCHED();
+    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, nullptr); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     out->xyw.resize((size_t)np * 3);
     CK(cudaMemcpy(out->xyw.data(), m.wide.p, (size_t)np * 3 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -1410,6 +1556,7 @@ int Engine::checksums(const void *rasters, size_t raster_bytes, uint32_t count, 
     Impl &m = *impl_;
     if (count == 0) return FTL_OK;
     int rc;
+    if ((rc = resolve_pending(m))) return rc;
     if ((rc = m.misc.ensure((size_t)count * 8, m.st))) return rc;
     fnv_rasters<<<count, 256, 0, m.st>>>((const uint8_t *)rasters, raster_bytes, (uint64_t *)m.misc.p); LAUNCHED();
     CK(cudaGetLastError());
@@ -1420,6 +1567,8 @@ int Engine::checksums(const void *rasters, size_t raster_bytes, uint32_t count, 
 
 int Engine::sync() {
     ENSURE_INIT();
+    int rc = resolve_pending(*impl_);
+    if (rc) return rc;
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;
 }
@@ -1431,6 +1580,7 @@ int Engine::alloc_raster(size_t bytes, void **dptr) {
 int Engine::free_raster(void *dptr) {
     if (!dptr) return FTL_OK;
     ENSURE_INIT();
+    resolve_pending(*impl_);
     CK(cudaStreamSynchronize(impl_->st));
     CK(cudaFree(dptr));
     return FTL_OK;
@@ -1442,12 +1592,20 @@ int Engine::memset_async(void *dptr, int value, size_t bytes) {
 }
 int Engine::copy_in(void *dptr, const void *src, size_t bytes) {
     ENSURE_INIT();
+    {
+        int rc = resolve_pending(*impl_);
+        if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, impl_->st));
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;
 }
 int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
     ENSURE_INIT();
+    {
+        int rc = resolve_pending(*impl_);
+        if (rc) return rc;
+    }
     CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, impl_->st));
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;

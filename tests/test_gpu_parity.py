@@ -428,3 +428,28 @@ def test_error_paths():
     g.set_tolerance(-5.0)  # clamps to 0.01 like the reference (plotter.rs:133-137)
     g.fill(FillRule.NonZero, poly([(1, 1), (6, 1), (3, 6)]), (255,))
     assert g.raster().pixels.any()
+
+
+# ---- speculative (sync-free) replay: scratch overflow is detected and the call repeated -------------
+def test_speculative_capacity_overflow_is_recovered():
+    rng = np.random.default_rng(11)
+    g, o = both(256, 256, Format.Rgba8p, init=np.full((256, 1024), 40, dtype=np.uint8))
+    small = poly([(10, 10), (50, 12), (30, 60)])
+    big = random_path(rng, 256, 60)  # needs far more vertices / bin entries than `small` sized the buffers for
+    for ops, clr in ((small, (200, 10, 10, 255)), (big, (10, 90, 10, 128)), (small, (0, 0, 50, 60)), (big, (9, 9, 9, 9))):
+        g.fill(FillRule.NonZero, ops, clr)  # non-idempotent blend: a repeated or dropped pass would show
+        o.fill(oracle.NONZERO, ops, clr)
+    assert_same(g, o)
+
+
+def test_many_async_replays_then_read():
+    ops, offs, rules = scenes.random_curve_paths(77, 6, segments=16, size=128)
+    b = Batch(128, 128, Format.Matte8, 6)
+    b.upload(ops, offs, rules=rules)
+    for _ in range(150):  # more than the pending-check ring holds
+        b.run()
+    got = b.read()
+    for j in range(6):
+        o = oracle.Plotter(128, 128, oracle.MATTE8)
+        o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
+        assert np.array_equal(got[j], o.raster())
