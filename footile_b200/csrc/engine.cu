@@ -123,7 +123,7 @@ struct Params {  // per-call constants, passed by value
     uint32_t fmt, bpp, pitch;
     uint32_t log2R, R, n_bands, WP, chunks;  // rows per tile, bands per job, smem row stride (cells), 512-cell chunks per row
     uint32_t n_jobs, n_ops, n_tiles;
-    uint32_t team_warps, team_words, cta_warps;  // warps per row team, smem words per team, warps per CTA
+    uint32_t win_chunks, warp_words, cta_warps;  // chunks per row window, smem words per warp, warps per CTA
 };
 
 // ---------------------------------------------------------------------------
@@ -621,50 +621,83 @@ __device__ __forceinline__ uint32_t cell_phys(uint32_t c) {
     return ((q ^ ((q >> 3) & 3u)) << 2) | (c & 3u);
 }
 
-// Signed coverage of one edge on one raster row, scattered into the row's
-// shared-memory cells.  Closed form of Scanner::scan_continuing_edges /
-// add_edge + Edge::scan_area (fig.rs:238-321,557-600); SURVEY Appendix A.4.
-__device__ __forceinline__ void scatter_edge_row(const EdgeRec &e, int32_t ry, int32_t *row, uint32_t *mask, int32_t W) {
+// Signed coverage of one edge on one raster row.  Closed form of
+// Scanner::scan_continuing_edges / add_edge + Edge::scan_area
+// (fig.rs:238-321,557-600); SURVEY Appendix A.4.  `edge_row_setup` evaluates
+// everything that does not depend on the pixel; `edge_row_scatter` then adds
+// the per-cell deltas of the cells inside one column window into the shared
+// row buffer and can be resumed window after window.
+struct EdgeRowState {
+    int32_t cov;      // coverage of the row by this edge, 1..256; 0 = nothing to do
+    int32_t first;    // x_cov at cell min_pix
+    int32_t step;     // x_cov increment per cell
+    int32_t min_pix;  // leftmost cell (may be negative: folded into cell 0)
+    int32_t c0;       // max(min_pix, 0)
+    int32_t ed;       // +1 / -1 (fig.rs:286)
+    int32_t c;        // next cell of this lane
+};
+__device__ __forceinline__ int32_t edge_row_x(const EdgeRowState &st, int32_t k) {  // X(k) = min(pixel_cov(min(first + k*step, 1)), cov)
+    int64_t xc = (int64_t)st.first + (int64_t)k * (int64_t)st.step;
+    int32_t xk = pixel_cov((fx_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE));
+    return xk < st.cov ? xk : st.cov;
+}
+__device__ __forceinline__ EdgeRowState edge_row_setup(const EdgeRec &e, int32_t ry, int32_t W, uint32_t sub) {
+    EdgeRowState st;
     const bool starting = ry == e.ry0, ending = ry == e.ry1;
     const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
     // continuing_cov / starting_cov (fig.rs:238-241,252-259)
-    int32_t cov = (ending ? pixel_cov(fr1) : 256) - (starting ? pixel_cov(fr0) : 0);
-    if (cov <= 0) return;
+    st.cov = (ending ? pixel_cov(fr1) : 256) - (starting ? pixel_cov(fr0) : 0);
     // advance_edges in closed form (fig.rs:569-573)
     fx_t x_bot = (fx_t)((uint32_t)e.x_bot0 + (uint32_t)(ry - e.ry0) * (uint32_t)e.inv_slope);
     // calculate_x_limits_* / set_x_limits (fig.rs:244-249,262-278); ceil(y)-y = (ONE - fract) & MASK
     fx_t x0 = starting ? fx_sub(x_bot, fx_mul(e.inv_slope, FX_ONE - fr0)) : fx_sub(x_bot, e.inv_slope);
     fx_t x1 = ending ? fx_sub(x_bot, fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK)) : x_bot;
     fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
-    int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
-    if (min_pix >= W) return;
+    st.min_pix = fx_to_i32(min_x);
+    const int32_t max_pix = fx_to_i32(max_x);
+    if (st.cov < 0 || st.min_pix >= W) st.cov = 0;
     // first_cov / step_cov (fig.rs:305-321); full_cov = cov/256 in Fixed = cov << 8
-    fx_t rr = min_pix == max_pix ? fx_mul(fx_sub(FX_ONE, fx_fract(fx_avg(max_x, min_x))), (fx_t)(cov << 8))
-                                 : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
-    fx_t first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
-    fx_t step = e.step_pix > 0 ? e.step_pix : FX_ONE;
-    const int32_t ed = (e.flags & 2u) ? -1 : 1;  // fig.rs:286
-    // scan_area (fig.rs:285-302): X(k) = min(pixel_cov(min(first + k*step, 1)), cov);
-    // cell min_pix+k receives X(k)-X(k-1); cells left of 0 fold into cell 0.
-    int32_t c = min_pix > 0 ? min_pix : 0;
-    int64_t xc = (int64_t)first + (int64_t)(c - min_pix) * (int64_t)step;
-    int32_t prev = 0, last_g = -1;
-    for (; c < W; c++) {
-        int32_t xk = pixel_cov((fx_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE));
-        if (xk > cov) xk = cov;
-        int32_t d = xk - prev;
-        if (d != 0) {
-            atomicAdd(&row[cell_phys((uint32_t)c)], ed * d);
-            int32_t g = c >> 4;
-            if (g != last_g) {
-                atomicOr(&mask[g >> 5], 1u << (g & 31));
-                last_g = g;
-            }
+    fx_t rr = st.min_pix == max_pix ? fx_mul(fx_sub(FX_ONE, fx_fract(fx_avg(max_x, min_x))), (fx_t)(st.cov << 8))
+                                    : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
+    st.first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
+    st.step = e.step_pix > 0 ? e.step_pix : FX_ONE;
+    st.ed = (e.flags & 2u) ? -1 : 1;
+    st.c0 = st.min_pix > 0 ? st.min_pix : 0;
+    st.c = st.c0 + (int32_t)sub;
+    return st;
+}
+// scan_area (fig.rs:285-302) for the cells of this lane inside [win_lo, win_hi): cell min_pix+k
+// receives X(k)-X(k-1); cells left of 0 fold into cell 0, which receives X(-min_pix).  `lpe` lanes
+// share the edge, each taking every lpe-th cell.
+__device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_lo, int32_t win_hi, int32_t *cells, uint32_t *mask, uint32_t lpe) {
+    if (st.cov <= 0) return;
+    if (st.c < win_lo) st.c += (int32_t)(((uint32_t)(win_lo - st.c) + lpe - 1) / lpe * lpe);
+    if (st.c >= win_hi) return;
+    int32_t xp = st.c > st.c0 ? edge_row_x(st, st.c - 1 - st.min_pix) : 0;
+    int32_t lo = 0x7FFFFFFF, hi = -1;
+    while (st.c < win_hi) {
+        if (xp >= st.cov) {  // every later cell receives 0
+            st.cov = 0;
+            break;
         }
-        prev = xk;
-        if (xk >= cov) break;
-        xc += step;
+        const int32_t xk = edge_row_x(st, st.c - st.min_pix);
+        const int32_t d = xk - xp;
+        if (d != 0) {
+            const int32_t rel = st.c - win_lo;
+            atomicAdd(&cells[cell_phys((uint32_t)rel)], st.ed * d);
+            lo = min(lo, rel);
+            hi = rel;
+        }
+        st.c += (int32_t)lpe;
+        xp = lpe == 1 ? xk : edge_row_x(st, st.c - 1 - st.min_pix);
     }
+    // mark the 16-cell groups [lo >> 4, hi >> 4] of the window as touched
+    if (hi >= 0)
+        for (uint32_t g = (uint32_t)lo >> 4, g1 = (uint32_t)hi >> 4; g <= g1;) {
+            const uint32_t top = min(g1, g | 31u);
+            atomicOr(&mask[g >> 5], ((2u << (top - g)) - 1u) << (g & 31u));
+            g = top + 1;
+        }
 }
 
 // Four consecutive pixels: wrapped-i16 sums (p_i + base) -> alpha bytes
@@ -698,6 +731,32 @@ __device__ __forceinline__ uint32_t blend_rgba(uint32_t px, uint32_t color, uint
 #pragma unroll
     for (int ch = 0; ch < 4; ch++) o |= pix::src_over_ch((px >> (8 * ch)) & 0xFF, (color >> (8 * ch)) & 0xFF, alpha, sa1) << (8 * ch);
     return o;
+}
+
+// alpha of one pixel from the wrapped i16 sum (fig.rs:637-664; imgbuf.rs:54-66,157-167)
+template <bool EVEN_ODD>
+__device__ __forceinline__ uint32_t rule_alpha(int32_t sum) {
+    int32_t s = (int32_t)(int16_t)sum;
+    if (EVEN_ODD) {
+        int32_t c = (s & 0xFF) - (s & 0x100);
+        s = c < 0 ? -c : c;
+    }
+    return (uint32_t)__vimin_s32_relu(s, 255);
+}
+
+// Output of one pixel.
+template <int FMT>
+__device__ __forceinline__ void emit1(uint8_t *dst, uint32_t x, uint32_t W, uint32_t alpha, uint32_t color, uint32_t clr_a) {
+    if (x >= W) return;
+    if (FMT == FTL_MATTE8) dst[x] = (uint8_t)alpha;
+    else if (FMT == FTL_RGBA8P) {
+        uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
+        *d = blend_rgba(*d, color, alpha, clr_a);
+    } else {
+        uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
+        uint32_t p = *d, sa1 = 255u - pix::ch8_mul(alpha, clr_a);
+        *d = (uint16_t)(pix::src_over_ch(p & 0xFF, color & 0xFF, alpha, sa1) | (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, alpha, sa1) << 8));
+    }
 }
 
 // Output of one lane's 16 pixels: alpha words a[0..3] (4 pixels each).
@@ -758,20 +817,67 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
 // running sum without touching shared memory.
 template <int FMT, bool EVEN_ODD, bool ALIGNED>
 __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t c_begin, uint32_t c_end,
-                                            int32_t carry, uint32_t color) {
+                                            int32_t &carry_io, uint32_t color) {
+    int32_t carry = carry_io;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t sw = (lane >> 1) & 3u;
     const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    const uint32_t n = c_end - c_begin;  // <= 32 chunks per warp
+    // the warp's chunk masks: lane i holds (and clears) the mask of chunk c_begin + i
+    uint32_t mym = 0;
+    if (lane < n) {
+        mym = mask[c_begin + lane];
+        if (mym) mask[c_begin + lane] = 0;
+    }
+    const uint32_t dense = __ballot_sync(0xFFFFFFFFu, mym != 0);
     uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);  // alpha of an edge-free span at the current sum
-    for (uint32_t ch = c_begin; ch < c_end; ch++) {
-        const uint32_t m = mask[ch];
+    uint4 *out4 = reinterpret_cast<uint4 *>(dst) + lane;
+    for (uint32_t i = 0; i < n; i++) {
+        const uint32_t ch = c_begin + i;
         const uint32_t x = ch * CHUNK + lane * 16;
-        if (m == 0) {
-            emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
+        const bool full = (ch + 1) * CHUNK <= W;
+        if (!((dense >> i) & 1u)) {
+            if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(q, q, q, q);
+            else emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
             continue;
         }
-        __syncwarp();
-        if (lane == 0) mask[ch] = 0;
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, i);
+        if (__popc(m) <= 4) {
+            // Sparse chunk: each touched 16-cell group is scanned by a half-warp (one cell per lane,
+            // two groups per step); the other groups take the constant alpha of the sum reaching them.
+            int32_t mybase = carry;  // sum reaching group `lane` of this chunk
+            const uint32_t half = lane >> 4, l16 = lane & 15u;
+            for (uint32_t mm = m; mm;) {
+                const int32_t g = __ffs(mm) - 1;
+                mm &= mm - 1;
+                const int32_t g2 = mm ? __ffs(mm) - 1 : -1;
+                if (g2 >= 0) mm &= mm - 1;
+                const int32_t gg = half ? g2 : g;
+                int32_t inc = 0;
+                if (gg >= 0) {
+                    int32_t *p = row + ch * CHUNK + (((uint32_t)gg * 4 + ((l16 >> 2) ^ (((uint32_t)gg >> 1) & 3u))) << 2) + (l16 & 3u);
+                    inc = *p;
+                    *p = 0;
+                }
+#pragma unroll
+                for (int d = 1; d < 16; d <<= 1) {
+                    int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d, 16);
+                    if (l16 >= (uint32_t)d) inc += o;
+                }
+                const int32_t t_lo = __shfl_sync(0xFFFFFFFFu, inc, 15), t_hi = __shfl_sync(0xFFFFFFFFu, inc, 31);
+                if (gg >= 0) emit1<FMT>(dst, ch * CHUNK + (uint32_t)gg * 16 + l16, W, rule_alpha<EVEN_ODD>(carry + inc + (half ? t_lo : 0)), color, clr_a);
+                if ((int32_t)lane > g) mybase += t_lo;
+                if (g2 >= 0 && (int32_t)lane > g2) mybase += t_hi;
+                carry += t_lo + t_hi;
+            }
+            if (!((m >> lane) & 1u)) {
+                const uint32_t qq = quad_alpha<EVEN_ODD>(0, 0, 0, 0, mybase);
+                if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(qq, qq, qq, qq);
+                else emit16<FMT, ALIGNED>(dst, x, W, qq, qq, qq, qq, color, clr_a);
+            }
+            q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
+            continue;
+        }
         int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
         if ((m >> lane) & 1u) {
             int32_t *base = row + ch * CHUNK + lane * 16;
@@ -799,59 +905,35 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         const uint32_t a1 = quad_alpha<EVEN_ODD>(v1.x, v1.y, v1.z, v1.w, b0 + o1);
         const uint32_t a2 = quad_alpha<EVEN_ODD>(v2.x, v2.y, v2.z, v2.w, b0 + o2);
         const uint32_t a3 = quad_alpha<EVEN_ODD>(v3.x, v3.y, v3.z, v3.w, b0 + o3);
-        emit16<FMT, ALIGNED>(dst, x, W, a0, a1, a2, a3, color, clr_a);
+        if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(a0, a1, a2, a3);
+        else emit16<FMT, ALIGNED>(dst, x, W, a0, a1, a2, a3, color, clr_a);
         q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
     }
+    carry_io = carry;
 }
 
-// Sum of the cells of chunks [c_begin, c_end) (no zeroing): the carry a later
-// warp of the same row team starts from.
-__device__ __forceinline__ int32_t segment_total(const int32_t *row, const uint32_t *mask, uint32_t c_begin, uint32_t c_end) {
-    const uint32_t lane = threadIdx.x & 31;
-    int32_t s = 0;
-    for (uint32_t ch = c_begin; ch < c_end; ch++) {
-        const uint32_t m = mask[ch];
-        if ((m >> lane) & 1u) {
-            const int4 *p = reinterpret_cast<const int4 *>(row + ch * CHUNK + lane * 16);
-#pragma unroll
-            for (int j = 0; j < 4; j++) s += p[j].x + p[j].y + p[j].z + p[j].w;  // swizzle permutes quads inside the group only
-        }
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xFFFFFFFFu, s, d);
-    return s;
-}
-
-__device__ __forceinline__ void team_sync(uint32_t T, uint32_t team) {
-    if (T == 1) __syncwarp();
-    else asm volatile("bar.sync %0, %1;" ::"r"(team + 1), "r"(T * 32) : "memory");
-}
-
-// The tile kernel.  A row TEAM of T warps (T = 1 for rows up to 4096 px) owns
-// one shared-memory row buffer and walks the rows of a (job, band) tile: the
-// team's lanes scatter the coverage of every edge crossing the row, then the
-// row is resolved and written.  Teams never wait for each other, so the
-// scatter latency of one team hides behind the resolve of the others.
+// The tile kernel.  Every WARP owns a private shared-memory row window
+// (`win_chunks` chunks of 512 cells + their masks) and walks the rows of a
+// (job, band) tile on its own: its lanes scatter the coverage of the edges
+// crossing the row, then the row is resolved and written, window after
+// window, with the running sum carried across windows.  Warps never wait for
+// each other, and the small window keeps many warps resident per SM, which is
+// what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED>
-__global__ void __launch_bounds__(256) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
-                                                    const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
-                                                    const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
+__global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+                                                       const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
+                                                       const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
     extern __shared__ __align__(16) int32_t smem[];
-    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t T = P.team_warps;
-    const uint32_t team = warp / T, wt = warp - team * T;
-    const uint32_t teams_per_cta = (blockDim.x >> 5) / T;
-    int32_t *cells = smem + team * P.team_words;
-    uint32_t *mask = reinterpret_cast<uint32_t *>(cells + P.chunks * CHUNK);
-    int32_t *seg_tot = reinterpret_cast<int32_t *>(mask + P.chunks);
-    const uint32_t tl = wt * 32 + lane, team_lanes = T * 32;
-    for (uint32_t i = tl; i < P.team_words; i += team_lanes) cells[i] = 0;
-    team_sync(T, team);
-    const uint32_t cpw = (P.chunks + T - 1) / T;  // chunks per warp of the team
-    const uint32_t c_begin = min(wt * cpw, P.chunks), c_end = min(c_begin + cpw, P.chunks);
-    const uint32_t n_teams = gridDim.x * teams_per_cta;
-    for (uint32_t tile = blockIdx.x * teams_per_cta + team; tile < P.n_tiles; tile += n_teams) {
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
+    int32_t *cells = smem + warp * P.warp_words;
+    uint32_t *mask = reinterpret_cast<uint32_t *>(cells + P.win_chunks * CHUNK);
+    for (uint32_t i = lane; i < P.warp_words; i += 32) cells[i] = 0;
+    __syncwarp();
+    const int32_t W = (int32_t)P.W, win_cells = (int32_t)(P.win_chunks * CHUNK);
+    const uint32_t bpp = P.bpp;
+    const uint32_t n_warps = gridDim.x * warps_per_cta;
+    for (uint32_t tile = blockIdx.x * warps_per_cta + warp; tile < P.n_tiles; tile += n_warps) {
         const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
         const JobState js = JS[j];
         int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
@@ -865,30 +947,38 @@ __global__ void __launch_bounds__(256) raster_tiles(const EdgeRec *__restrict__ 
         const bool direct = n_slots <= DIRECT_MAX;
         const uint32_t e0 = direct ? js.vtx_begin : tile_off[tile];
         const uint32_t ne = direct ? n_slots : tile_off[tile + 1] - e0;
-        // the first team_lanes edges of the tile stay in registers for all its rows
+        // Few edges: 4 (or 2) lanes share an edge and split its cells.  The first pass of edges
+        // stays in registers for all rows of the tile.
+        const uint32_t lpe_log2 = ne <= 8 ? 2u : (ne <= 16 ? 1u : 0u);
+        const uint32_t lpe = 1u << lpe_log2, sub = lane & (lpe - 1), my_edge = lane >> lpe_log2, per_pass = 32u >> lpe_log2;
         EdgeRec mine;
         mine.flags = 0;
-        if (tl < ne) mine = E[direct ? e0 + tl : entries[e0 + tl]];
+        if (my_edge < ne) mine = E[direct ? e0 + my_edge : entries[e0 + my_edge]];
         for (int32_t ry = row0; ry < row_hi; ry++) {
-            // ---- (c) scatter: one lane per edge crossing this row ----
-            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) scatter_edge_row(mine, ry, cells, mask, (int32_t)P.W);
-            for (uint32_t i = tl + team_lanes; i < ne; i += team_lanes) {
-                const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
-                if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) scatter_edge_row(e, ry, cells, mask, (int32_t)P.W);
-            }
-            team_sync(T, team);
-            // ---- (d) resolve ----
-            int32_t carry = 0;
-            if (T > 1) {
-                int32_t s = segment_total(cells, mask, c_begin, c_end);
-                if (lane == 0) seg_tot[wt] = s;
-                team_sync(T, team);
-                for (uint32_t u = 0; u < wt; u++) carry += seg_tot[u];
-            }
+            EdgeRowState st;
+            st.cov = 0;
+            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) st = edge_row_setup(mine, ry, W, sub);
             uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
-            if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dst, P.W, c_begin, c_end, carry, color);
-            else resolve_row<FMT, false, ALIGNED>(cells, mask, dst, P.W, c_begin, c_end, carry, color);
-            team_sync(T, team);
+            int32_t carry = 0;
+            for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells) {
+                const int32_t win_hi = min(W, win_lo + win_cells);
+                // ---- (c) scatter ----
+                edge_row_scatter(st, win_lo, win_hi, cells, mask, lpe);
+                for (uint32_t i = my_edge + per_pass; i < ne; i += per_pass) {
+                    const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
+                    if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
+                        EdgeRowState s2 = edge_row_setup(e, ry, W, sub);
+                        edge_row_scatter(s2, win_lo, win_hi, cells, mask, lpe);
+                    }
+                }
+                __syncwarp();
+                // ---- (d) resolve ----
+                const uint32_t nch = ((uint32_t)(win_hi - win_lo) + CHUNK - 1) / CHUNK;
+                uint8_t *dwin = dst + (size_t)win_lo * bpp;
+                if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                else resolve_row<FMT, false, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                __syncwarp();
+            }
         }
     }
 }
@@ -904,12 +994,13 @@ __global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__re
     __syncwarp();
     uint8_t *d = dst + (size_t)blockIdx.x * n;
     const bool al = (n & 15u) == 0;
+    int32_t carry = 0;
     if (even_odd) {
-        if (al) resolve_row<FTL_MATTE8, true, true>(area, mask, d, n, 0, chunks, 0, 0);
-        else resolve_row<FTL_MATTE8, true, false>(area, mask, d, n, 0, chunks, 0, 0);
+        if (al) resolve_row<FTL_MATTE8, true, true>(area, mask, d, n, 0, chunks, carry, 0);
+        else resolve_row<FTL_MATTE8, true, false>(area, mask, d, n, 0, chunks, carry, 0);
     } else {
-        if (al) resolve_row<FTL_MATTE8, false, true>(area, mask, d, n, 0, chunks, 0, 0);
-        else resolve_row<FTL_MATTE8, false, false>(area, mask, d, n, 0, chunks, 0, 0);
+        if (al) resolve_row<FTL_MATTE8, false, true>(area, mask, d, n, 0, chunks, carry, 0);
+        else resolve_row<FTL_MATTE8, false, false>(area, mask, d, n, 0, chunks, carry, 0);
     }
 }
 
@@ -1127,16 +1218,15 @@ static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
     P->WP = P->chunks * CHUNK;
-    // one row team per 8 chunks (4096 px) of width: T = 1, 2, 4 or 8 warps share a row buffer
-    uint32_t T = 1, cpw_max = 8;
-    if (const char *ev = getenv("FTL_CHUNKS_PER_WARP")) cpw_max = (uint32_t)std::max(1, atoi(ev));  // tuning knob
-    while (T < 8 && P->chunks > cpw_max * T) T <<= 1;
-    P->team_warps = T;
-    P->team_words = (P->chunks * CHUNK + P->chunks + 8 + 3u) & ~3u;  // cells + masks + segment totals, 16-byte multiple
-    P->cta_warps = T > 4 ? 8 : 4;
-    size_t cta_bytes = (size_t)P->team_words * 4 * (P->cta_warps / T);
+    // each warp keeps one row window of up to 4 chunks (2048 px) in shared memory
+    uint32_t win = 4;
+    if (const char *ev = getenv("FTL_WIN_CHUNKS")) win = (uint32_t)std::min(32, std::max(1, atoi(ev)));  // tuning knob
+    P->win_chunks = std::min(P->chunks, win);
+    P->warp_words = (P->win_chunks * CHUNK + P->win_chunks + 3u) & ~3u;  // cells + masks, 16-byte multiple
+    P->cta_warps = 4;
+    size_t cta_bytes = (size_t)P->warp_words * 4 * P->cta_warps;
     if (cta_bytes > max_smem) {
-        set_error("raster width exceeds the shared-memory row tile");
+        set_error("row window exceeds shared memory");
         return FTL_ERR_TOO_WIDE;
     }
     uint32_t log2R = 3;  // band height: binning granularity only (a team keeps one row in shared memory)
@@ -1222,7 +1312,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     if (ops_bytes) CK(cudaMemcpyAsync(m.ops.p, m.pin_ops.p, ops_bytes, cudaMemcpyHostToDevice, m.st));
     CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
     m.P = P;
-    m.smem_bytes = (int)((size_t)P.team_words * 4 * (P.cta_warps / P.team_warps));
+    m.smem_bytes = (int)((size_t)P.warp_words * 4 * P.cta_warps);
     m.have_jobs = true;
     return FTL_OK;
 }
@@ -1326,7 +1416,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.team_warps};
+                                     P.n_tiles, P.win_chunks};
         if (!m.graph || key != m.graph_key) {
             m.drop_graph();
             cudaGraph_t g = nullptr;
@@ -1356,7 +1446,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
-    uint32_t grid = std::min<uint32_t>(div_up(P.n_tiles, P.cta_warps / P.team_warps), (uint32_t)(m.n_sms * occ));
+    uint32_t grid = std::min<uint32_t>(div_up(P.n_tiles, P.cta_warps), (uint32_t)(m.n_sms * occ));
     ProfSpan span{};
     const bool prof = g_profiling.load();
     if (prof) {
