@@ -628,20 +628,14 @@ __device__ __forceinline__ uint32_t cell_phys(uint32_t c) {
 // the per-cell deltas of the cells inside one column window into the shared
 // row buffer and can be resumed window after window.
 struct EdgeRowState {
-    int32_t cov;      // coverage of the row by this edge, 1..256; 0 = nothing to do
-    int32_t first;    // x_cov at cell min_pix
-    int32_t step;     // x_cov increment per cell
-    int32_t min_pix;  // leftmost cell (may be negative: folded into cell 0)
-    int32_t c0;       // max(min_pix, 0)
-    int32_t ed;       // +1 / -1 (fig.rs:286)
-    int32_t c;        // next cell of this lane
+    int32_t cov;   // coverage of the row by this edge, 1..256; 0 = nothing (left) to do
+    int32_t xc;    // x_cov of the next cell, already clamped to ONE
+    int32_t step;  // x_cov increment per cell
+    int32_t prev;  // X of the previous cell (0 before the first)
+    int32_t ed;    // +1 / -1 (fig.rs:286)
+    int32_t c;     // next cell
 };
-__device__ __forceinline__ int32_t edge_row_x(const EdgeRowState &st, int32_t k) {  // X(k) = min(pixel_cov(min(first + k*step, 1)), cov)
-    int64_t xc = (int64_t)st.first + (int64_t)k * (int64_t)st.step;
-    int32_t xk = pixel_cov((fx_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE));
-    return xk < st.cov ? xk : st.cov;
-}
-__device__ __forceinline__ EdgeRowState edge_row_setup(const EdgeRec &e, int32_t ry, int32_t W, uint32_t sub) {
+__device__ __forceinline__ EdgeRowState edge_row_setup(const EdgeRec &e, int32_t ry, int32_t W, int32_t win_lo) {
     EdgeRowState st;
     const bool starting = ry == e.ry0, ending = ry == e.ry1;
     const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
@@ -653,51 +647,58 @@ __device__ __forceinline__ EdgeRowState edge_row_setup(const EdgeRec &e, int32_t
     fx_t x0 = starting ? fx_sub(x_bot, fx_mul(e.inv_slope, FX_ONE - fr0)) : fx_sub(x_bot, e.inv_slope);
     fx_t x1 = ending ? fx_sub(x_bot, fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK)) : x_bot;
     fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
-    st.min_pix = fx_to_i32(min_x);
-    const int32_t max_pix = fx_to_i32(max_x);
-    if (st.cov < 0 || st.min_pix >= W) st.cov = 0;
+    const int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
+    if (st.cov < 0 || min_pix >= W) st.cov = 0;
     // first_cov / step_cov (fig.rs:305-321); full_cov = cov/256 in Fixed = cov << 8
-    fx_t rr = st.min_pix == max_pix ? fx_mul(fx_sub(FX_ONE, fx_fract(fx_avg(max_x, min_x))), (fx_t)(st.cov << 8))
-                                    : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
-    st.first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
+    fx_t rr = min_pix == max_pix ? fx_mul(fx_sub(FX_ONE, fx_fract(fx_avg(max_x, min_x))), (fx_t)(st.cov << 8))
+                                 : fx_mul(fx_sub(FX_ONE, fx_fract(min_x)), FX_HALF);
+    const fx_t first = e.step_pix > 0 ? fx_mul(rr, e.step_pix) : rr;
     st.step = e.step_pix > 0 ? e.step_pix : FX_ONE;
     st.ed = (e.flags & 2u) ? -1 : 1;
-    st.c0 = st.min_pix > 0 ? st.min_pix : 0;
-    st.c = st.c0 + (int32_t)sub;
+    // scan_area (fig.rs:285-302): X(k) = min(pixel_cov(min(first + k*step, 1)), cov); cell min_pix+k
+    // receives X(k)-X(k-1); cells left of 0 fold into cell 0, which receives X(-min_pix).
+    const int32_t c0 = min_pix > 0 ? min_pix : 0;
+    st.c = c0 > win_lo ? c0 : win_lo;  // a later pass of a wide row starts inside the span
+    int64_t xc = (int64_t)first + (int64_t)(st.c - min_pix) * (int64_t)st.step;
+    st.xc = (int32_t)(xc < (int64_t)FX_ONE ? xc : (int64_t)FX_ONE);
+    st.prev = 0;
+    if (st.c > c0) {
+        int64_t xq = xc - (int64_t)st.step;
+        int32_t xk = pixel_cov((fx_t)(xq < (int64_t)FX_ONE ? xq : (int64_t)FX_ONE));
+        st.prev = xk < st.cov ? xk : st.cov;
+        if (st.prev >= st.cov) st.cov = 0;
+    }
     return st;
 }
-// scan_area (fig.rs:285-302) for the cells of this lane inside [win_lo, win_hi): cell min_pix+k
-// receives X(k)-X(k-1); cells left of 0 fold into cell 0, which receives X(-min_pix).  `lpe` lanes
-// share the edge, each taking every lpe-th cell.
-__device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_lo, int32_t win_hi, int32_t *cells, uint32_t *mask, uint32_t lpe) {
-    if (st.cov <= 0) return;
-    if (st.c < win_lo) st.c += (int32_t)(((uint32_t)(win_lo - st.c) + lpe - 1) / lpe * lpe);
-    if (st.c >= win_hi) return;
-    int32_t xp = st.c > st.c0 ? edge_row_x(st, st.c - 1 - st.min_pix) : 0;
-    int32_t lo = 0x7FFFFFFF, hi = -1;
-    while (st.c < win_hi) {
-        if (xp >= st.cov) {  // every later cell receives 0
-            st.cov = 0;
+// The cells of [st.c, win_hi): adds each cell's delta into the shared row window (which starts at
+// column win_lo) and leaves `st` ready to continue in the next window.
+__device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_lo, int32_t win_hi, int32_t *cells, uint32_t *mask) {
+    if (st.cov <= 0 || st.c >= win_hi) return;
+    const int32_t first_rel = st.c - win_lo;
+    int32_t rel = first_rel;
+    const int32_t end_rel = win_hi - win_lo;
+    for (;;) {
+        int32_t xk = pixel_cov(st.xc);
+        if (xk > st.cov) xk = st.cov;
+        const int32_t d = xk - st.prev;
+        if (d != 0) atomicAdd(&cells[cell_phys((uint32_t)rel)], st.ed * d);
+        st.prev = xk;
+        rel++;
+        st.xc += st.step;  // both <= ONE: no overflow
+        if (st.xc > FX_ONE) st.xc = FX_ONE;
+        if (xk >= st.cov) {
+            st.cov = 0;  // finished: every later cell receives 0
             break;
         }
-        const int32_t xk = edge_row_x(st, st.c - st.min_pix);
-        const int32_t d = xk - xp;
-        if (d != 0) {
-            const int32_t rel = st.c - win_lo;
-            atomicAdd(&cells[cell_phys((uint32_t)rel)], st.ed * d);
-            lo = min(lo, rel);
-            hi = rel;
-        }
-        st.c += (int32_t)lpe;
-        xp = lpe == 1 ? xk : edge_row_x(st, st.c - 1 - st.min_pix);
+        if (rel >= end_rel) break;
     }
-    // mark the 16-cell groups [lo >> 4, hi >> 4] of the window as touched
-    if (hi >= 0)
-        for (uint32_t g = (uint32_t)lo >> 4, g1 = (uint32_t)hi >> 4; g <= g1;) {
-            const uint32_t top = min(g1, g | 31u);
-            atomicOr(&mask[g >> 5], ((2u << (top - g)) - 1u) << (g & 31u));
-            g = top + 1;
-        }
+    st.c = win_lo + rel;
+    // mark the 16-cell groups [first_rel >> 4, (rel - 1) >> 4] of the window as touched
+    for (uint32_t g = (uint32_t)first_rel >> 4, g1 = (uint32_t)(rel - 1) >> 4; g <= g1;) {
+        const uint32_t top = min(g1, g | 31u);
+        atomicOr(&mask[g >> 5], ((2u << (top - g)) - 1u) << (g & 31u));
+        g = top + 1;
+    }
 }
 
 // Four consecutive pixels: wrapped-i16 sums (p_i + base) -> alpha bytes
@@ -947,28 +948,25 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
         const bool direct = n_slots <= DIRECT_MAX;
         const uint32_t e0 = direct ? js.vtx_begin : tile_off[tile];
         const uint32_t ne = direct ? n_slots : tile_off[tile + 1] - e0;
-        // Few edges: 4 (or 2) lanes share an edge and split its cells.  The first pass of edges
-        // stays in registers for all rows of the tile.
-        const uint32_t lpe_log2 = ne <= 8 ? 2u : (ne <= 16 ? 1u : 0u);
-        const uint32_t lpe = 1u << lpe_log2, sub = lane & (lpe - 1), my_edge = lane >> lpe_log2, per_pass = 32u >> lpe_log2;
+        // The first 32 edges of the tile stay in registers for all its rows.
         EdgeRec mine;
         mine.flags = 0;
-        if (my_edge < ne) mine = E[direct ? e0 + my_edge : entries[e0 + my_edge]];
+        if (lane < ne) mine = E[direct ? e0 + lane : entries[e0 + lane]];
         for (int32_t ry = row0; ry < row_hi; ry++) {
             EdgeRowState st;
             st.cov = 0;
-            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) st = edge_row_setup(mine, ry, W, sub);
+            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) st = edge_row_setup(mine, ry, W, 0);
             uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
             int32_t carry = 0;
             for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells) {
                 const int32_t win_hi = min(W, win_lo + win_cells);
-                // ---- (c) scatter ----
-                edge_row_scatter(st, win_lo, win_hi, cells, mask, lpe);
-                for (uint32_t i = my_edge + per_pass; i < ne; i += per_pass) {
+                // ---- (c) scatter: one lane per edge crossing this row ----
+                edge_row_scatter(st, win_lo, win_hi, cells, mask);
+                for (uint32_t i = lane + 32; i < ne; i += 32) {
                     const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
                     if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
-                        EdgeRowState s2 = edge_row_setup(e, ry, W, sub);
-                        edge_row_scatter(s2, win_lo, win_hi, cells, mask, lpe);
+                        EdgeRowState s2 = edge_row_setup(e, ry, W, win_lo);
+                        edge_row_scatter(s2, win_lo, win_hi, cells, mask);
                     }
                 }
                 __syncwarp();
