@@ -5,7 +5,7 @@ Contract (see DESIGN.md "Measurement"):
   python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload heptagram|batch512]
 A step is one pass of the hot path over one batch of synthetic paths.  Default workload =
 BASELINE.json configs[1]: heptagram fills (NonZero / EvenOdd alternating) into 4096x4096 Matte8
-rasters, `--batch` rasters per step (default 64 = 1 GiB of output, far beyond the 126 MB L2).
+rasters, `--batch` rasters per step (default 256 = 4 GiB of output, far beyond the 126 MB L2).
   value : Gpx/s with the path ops already resident in HBM (ftl_batch_run), CUDA events on the
           library's stream, max over ranks.
   e2e   : the same metric through the C ABI with HOST buffers: ftl_batch_fill(host ops) then
@@ -149,13 +149,13 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512"])
-    ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 64 heptagram / 4096 batch512)")
+    ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    batch = args.batch or (64 if args.workload == "heptagram" else 4096)
+    batch = args.batch or (256 if args.workload == "heptagram" else 4096)
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

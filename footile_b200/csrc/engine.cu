@@ -921,7 +921,7 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED>
-__global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
