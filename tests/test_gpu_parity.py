@@ -453,3 +453,38 @@ def test_many_async_replays_then_read():
         o = oracle.Plotter(128, 128, oracle.MATTE8)
         o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
         assert np.array_equal(got[j], o.raster())
+
+
+# ---- two GPUs: row bands on two devices gathered over NCCL (skipped on a 1-GPU box) ----------------
+def _band_worker(rank, world, port, size, out_dir):
+    import os
+    import torch
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from footile_b200 import sharding
+    ops = scenes.random_polygons(0, 300, vertices=32, size=size, extent=300)
+    r0, r1 = sharding.band_rows(size, rank, world)
+    g = Plotter(Raster(size, size, Format.Matte8), device=rank, rows=(r0, r1))
+    g.fill(FillRule.EvenOdd, ops, (255,)).sync()
+    ptr, nbytes = g.device_ptr()
+    band = sharding.device_tensor(ptr, nbytes, rank).view(r1 - r0, size)
+    full = sharding.gather_bands(band, size, size)
+    if rank == 0:
+        np.save(os.path.join(out_dir, "full.npy"), full.cpu().numpy())
+    dist.destroy_process_group()
+
+
+def test_two_gpu_row_bands_nccl_gather(tmp_path):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    size = 1024
+    mp.spawn(_band_worker, args=(2, 29611, size, str(tmp_path)), nprocs=2, join=True)
+    got = np.load(tmp_path / "full.npy")
+    ops = scenes.random_polygons(0, 300, vertices=32, size=size, extent=300)
+    exp = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True).fill(1, ops, (255,)).raster()
+    assert np.array_equal(got, exp)
