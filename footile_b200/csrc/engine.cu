@@ -19,6 +19,7 @@
 //
 // Build flags: -fmad=false (Rust never fuses a*b+c), no fast-math.
 #include <cuda_runtime.h>
+#include <emmintrin.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -26,6 +27,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <thread>
 #include <string>
 #include <vector>
 
@@ -1002,6 +1004,41 @@ __global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__re
     }
 }
 
+// ---------------------------------------------------------------------------
+// packed read-back: rasters are mostly long constant spans, and PCIe is ~100x
+// slower than HBM, so device->host copies of large rasters travel as
+//   code[b]   : the byte value of 32-byte block b if the block is uniform
+//   bitmap[u] : bit i set = block 32u+i is literal (not uniform)
+//   off[u]    : literal blocks before unit u (exclusive scan of the popcounts)
+//   literals  : the literal blocks, 32 bytes each, in order
+// and are expanded into the caller's buffer by host threads.
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) pack_classify(const uint4 *__restrict__ src, size_t n_blocks, uint8_t *__restrict__ code,
+                                                     uint32_t *__restrict__ bitmap, uint32_t *__restrict__ cnt) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;  // n_blocks is a multiple of 32: warps are full or empty
+    if (b >= n_blocks) return;
+    const uint4 lo = src[2 * b], hi = src[2 * b + 1];
+    const uint32_t v = (lo.x & 0xFFu) * 0x01010101u;
+    const bool uniform = lo.x == v && lo.y == v && lo.z == v && lo.w == v && hi.x == v && hi.y == v && hi.z == v && hi.w == v;
+    code[b] = (uint8_t)(v & 0xFFu);
+    const uint32_t lit = __ballot_sync(0xFFFFFFFFu, !uniform);
+    if ((threadIdx.x & 31) == 0) {
+        bitmap[b >> 5] = lit;
+        cnt[b >> 5] = __popc(lit);
+    }
+}
+__global__ void __launch_bounds__(256) pack_literals(const uint4 *__restrict__ src, size_t n_blocks, const uint32_t *__restrict__ bitmap,
+                                                     const uint32_t *__restrict__ off, uint4 *__restrict__ lit) {
+    const size_t b = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint32_t m = bitmap[b >> 5], lane = threadIdx.x & 31;
+    if ((m >> lane) & 1u) {
+        const size_t k = (size_t)off[b >> 5] + __popc(m & ((1u << lane) - 1u));
+        lit[2 * k] = src[2 * b];
+        lit[2 * k + 1] = src[2 * b + 1];
+    }
+}
+
 // 64-bit FNV-1a per raster (parity checks of large batches): one CTA per
 // raster hashes 256 interleaved lanes, then lane digests are folded in order.
 __global__ void __launch_bounds__(256) fnv_rasters(const uint8_t *__restrict__ base, size_t raster_bytes, uint64_t *__restrict__ out) {
@@ -1076,7 +1113,8 @@ struct Engine::Impl {
     size_t max_smem = 0;
     DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc;
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
-    PinBuf pin_ring;
+    PinBuf pin_ring, pin_pack[2], pin_lit[2];
+    DevBuf pack_fixed, pack_cnt, pack_lit;
     // resident job set
     Params P{};
     bool have_jobs = false;
@@ -1136,10 +1174,10 @@ Engine::~Engine() {
             cudaStreamSynchronize(impl_->st);
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
-                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc})
+                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
-            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring}) b->release();
+            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1]}) b->release();
             cudaStreamDestroy(impl_->st);
         }
         delete impl_;
@@ -1688,15 +1726,148 @@ int Engine::copy_in(void *dptr, const void *src, size_t bytes) {
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;
 }
+// Expand packed units [u0, u1) into dst (host).  Streaming (non-temporal) stores: the output is
+// written once and far larger than the caches, so read-for-ownership traffic would halve the rate.
+static void unpack_units(uint8_t *dst, const uint8_t *code, const uint32_t *bitmap, const uint32_t *off, const uint8_t *lit, size_t u0, size_t u1) {
+    const bool aligned = ((uintptr_t)dst & 15u) == 0;
+    for (size_t u = u0; u < u1; u++) {
+        uint8_t *d = dst + u * 1024;
+        const uint8_t *c = code + u * 32;
+        const uint32_t m = bitmap[u];
+        const uint8_t *l = lit + (size_t)off[u] * 32;
+        if (!aligned) {
+            for (int i = 0; i < 32; i++) {
+                if ((m >> i) & 1u) {
+                    memcpy(d + 32 * i, l, 32);
+                    l += 32;
+                } else
+                    memset(d + 32 * i, c[i], 32);
+            }
+            continue;
+        }
+        __m128i *o = reinterpret_cast<__m128i *>(d);
+        if (m == 0) {
+            uint64_t w0, w1, w2, w3;
+            memcpy(&w0, c, 8); memcpy(&w1, c + 8, 8); memcpy(&w2, c + 16, 8); memcpy(&w3, c + 24, 8);
+            const uint64_t bc = (uint64_t)c[0] * 0x0101010101010101ull;
+            if (w0 == bc && w1 == bc && w2 == bc && w3 == bc) {  // one constant KiB
+                const __m128i v = _mm_set1_epi8((char)c[0]);
+                for (int i = 0; i < 64; i++) _mm_stream_si128(o + i, v);
+                continue;
+            }
+        }
+        for (int i = 0; i < 32; i++) {
+            if ((m >> i) & 1u) {
+                _mm_stream_si128(o + 2 * i, _mm_loadu_si128(reinterpret_cast<const __m128i *>(l)));
+                _mm_stream_si128(o + 2 * i + 1, _mm_loadu_si128(reinterpret_cast<const __m128i *>(l + 16)));
+                l += 32;
+            } else {
+                const __m128i v = _mm_set1_epi8((char)c[i]);
+                _mm_stream_si128(o + 2 * i, v);
+                _mm_stream_si128(o + 2 * i + 1, v);
+            }
+        }
+    }
+    _mm_sfence();
+}
+
+static void unpack_parallel(uint8_t *dst, const uint8_t *code, const uint32_t *bitmap, const uint32_t *off, const uint8_t *lit, size_t units,
+                            unsigned nt) {
+    if (nt <= 1 || units < 4096) {
+        unpack_units(dst, code, bitmap, off, lit, 0, units);
+        return;
+    }
+    const size_t per = (units + nt - 1) / nt;
+    std::vector<std::thread> th;
+    for (unsigned t = 0; t < nt; t++) {
+        size_t u0 = std::min(units, t * per), u1 = std::min(units, u0 + per);
+        if (u0 < u1) th.emplace_back(unpack_units, dst, code, bitmap, off, lit, u0, u1);
+    }
+    for (std::thread &t : th) t.join();
+}
+
+// Device -> host copy of rasters.  Large copies are packed on the device (see pack_classify),
+// moved in 256 MiB pieces, and expanded by host threads while the next piece is in flight.
 int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
     ENSURE_INIT();
+    Impl &m = *impl_;
     {
-        int rc = resolve_pending(*impl_);
+        int rc = resolve_pending(m);
         if (rc) return rc;
     }
-    CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, impl_->st));
-    CK(cudaStreamSynchronize(impl_->st));
-    return FTL_OK;
+    cudaStream_t st = m.st;
+    static const bool raw_only = getenv("FTL_RAW_READ") && atoi(getenv("FTL_RAW_READ")) != 0;
+    const size_t PACK_MIN = 4u << 20;
+    if (raw_only || bytes < PACK_MIN || (bytes & 1023u) != 0 || ((uintptr_t)dptr & 15u) != 0) {
+        CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        return FTL_OK;
+    }
+    unsigned nt = std::min(8u, std::thread::hardware_concurrency());  // the expansion is memory-bound well before 8 threads
+    if (const char *ev = getenv("FTL_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(ev));
+    nt = std::max(1u, std::min(nt, 64u));
+    const size_t PIECE = 256u << 20;
+    std::thread worker;
+    int rc = FTL_OK;
+    for (size_t at = 0, k = 0; at < bytes && rc == FTL_OK; at += PIECE, k++) {
+        const size_t len = std::min(PIECE, bytes - at);
+        const uint8_t *src = (const uint8_t *)dptr + at;
+        uint8_t *out = (uint8_t *)dst + at;
+        const size_t n_blocks = len / 32, units = n_blocks / 32;
+        // fixed part: [code n_blocks][bitmap units*4][off (units+1)*4]
+        const size_t code_bytes = n_blocks, bm_bytes = units * 4, off_bytes = ((units + 1) * 4 + 15) & ~(size_t)15;
+        const size_t fixed = code_bytes + bm_bytes + off_bytes;
+        PinBuf &pin_fix = m.pin_pack[k & 1], &pin_lit = m.pin_lit[k & 1];
+        auto stage = [&]() -> int {
+            int r;
+            if ((r = m.pack_fixed.ensure(fixed, st))) return r;
+            if ((r = m.pack_cnt.ensure(units * 4 + 16, st))) return r;
+            if ((r = m.tpart.ensure((size_t)div_up(units + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return r;
+            if ((r = pin_fix.ensure(fixed))) return r;
+            uint8_t *d_code = (uint8_t *)m.pack_fixed.p;
+            uint32_t *d_bm = (uint32_t *)(d_code + code_bytes);
+            uint32_t *d_off = (uint32_t *)(d_code + code_bytes + bm_bytes);
+            const uint32_t grid = div_up(n_blocks, 256);
+            pack_classify<<<grid, 256, 0, st>>>((const uint4 *)src, n_blocks, d_code, d_bm, (uint32_t *)m.pack_cnt.p); LAUNCHED();
+            if ((r = run_scan<AddU32>(st, (const uint32_t *)m.pack_cnt.p, (uint32_t)units, d_off, m.tpart))) return r;
+            CK(cudaMemcpyAsync(pin_fix.p, d_code, fixed, cudaMemcpyDeviceToHost, st));
+            CK(cudaStreamSynchronize(st));
+            const uint32_t *h_off = (const uint32_t *)((const uint8_t *)pin_fix.p + code_bytes + bm_bytes);
+            const size_t n_lit = h_off[units];
+            if (n_lit * 32 > len / 2) return -1;  // not compressible
+            if (n_lit) {
+                if ((r = m.pack_lit.ensure(n_lit * 32, st))) return r;
+                if ((r = pin_lit.ensure(n_lit * 32))) return r;
+                pack_literals<<<grid, 256, 0, st>>>((const uint4 *)src, n_blocks, d_bm, d_off, (uint4 *)m.pack_lit.p); LAUNCHED();
+                CK(cudaGetLastError());
+                CK(cudaMemcpyAsync(pin_lit.p, m.pack_lit.p, n_lit * 32, cudaMemcpyDeviceToHost, st));
+                CK(cudaStreamSynchronize(st));
+            }
+            return FTL_OK;
+        };
+        int r = stage();  // overlaps the expansion of the previous piece
+        if (worker.joinable()) worker.join();
+        if (r == -1) {  // plain copy of this piece
+            cudaError_t e1 = cudaMemcpyAsync(out, src, len, cudaMemcpyDeviceToHost, st);
+            cudaError_t e2 = cudaStreamSynchronize(st);
+            if (e1 != cudaSuccess || e2 != cudaSuccess) {
+                set_error(std::string("device to host copy: ") + cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+                rc = FTL_ERR_CUDA;
+            }
+            continue;
+        }
+        if (r) {
+            rc = r;
+            break;
+        }
+        const uint8_t *h_code = (const uint8_t *)pin_fix.p;
+        const uint32_t *h_bm = (const uint32_t *)(h_code + code_bytes);
+        const uint32_t *h_off = (const uint32_t *)(h_code + code_bytes + bm_bytes);
+        const uint8_t *h_lit = (const uint8_t *)pin_lit.p;
+        worker = std::thread(unpack_parallel, out, h_code, h_bm, h_off, h_lit, units, nt);
+    }
+    if (worker.joinable()) worker.join();
+    return rc;
 }
 
 }  // namespace ftl

@@ -488,3 +488,22 @@ def test_two_gpu_row_bands_nccl_gather(tmp_path):
     ops = scenes.random_polygons(0, 300, vertices=32, size=size, extent=300)
     exp = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True).fill(1, ops, (255,)).raster()
     assert np.array_equal(got, exp)
+
+
+# ---- packed read-back (PCIe transport encoding) returns exactly the device bytes ---------------------
+def test_packed_readback_roundtrip():
+    rng = np.random.default_rng(2)
+    w, h = 4096, 2048  # 8 MiB: above the packing threshold
+    for kind in ("noise", "mixed", "constant"):
+        if kind == "noise":
+            img = rng.integers(0, 256, (h, w)).astype(np.uint8)       # incompressible: falls back to the plain copy
+        elif kind == "constant":
+            img = np.full((h, w), 200, dtype=np.uint8)
+        else:
+            img = np.zeros((h, w), dtype=np.uint8)
+            img[100:900] = 255
+            img[:, 1000:1033] = rng.integers(0, 256, (h, 33)).astype(np.uint8)  # literal blocks straddling block borders
+            img[5, :] = np.arange(w) % 251
+            img[-1, -1] = 7
+        g = Plotter(Raster(w, h, Format.Matte8, img))
+        assert np.array_equal(g.raster().pixels, img), kind
