@@ -120,7 +120,7 @@ def cpu_run(wl, jobs, threads):
     import oracle
     size = wl["size"]
     chunks = [jobs[t::threads] for t in range(threads)]
-    plotters = [[oracle.Plotter(size, size, oracle.MATTE8) for _ in c] for c in chunks]
+    plotters = [[oracle.Plotter(size, size, wl.get("ofmt", oracle.MATTE8)) for _ in c] for c in chunks]
     for ps, c in zip(plotters, chunks):
         for p, j in zip(ps, c):
             if wl["tr"] is not None:
@@ -128,7 +128,7 @@ def cpu_run(wl, jobs, threads):
 
     def work(t):
         for p, j in zip(plotters[t], chunks[t]):
-            p.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], (255,))
+            p.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], wl.get("color", (255,)))
 
     t0 = time.perf_counter()
     if threads == 1:
@@ -151,17 +151,21 @@ def main():
     ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512"])
     ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
+    ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p"], help="pixel format of the rasters")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    batch = args.batch or (256 if args.workload == "heptagram" else 4096)
+    rgba = args.format == "rgba8p"
+    bpp = 4 if rgba else 1
+    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else (1024 if rgba else 4096))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     unit = "Gpx/s"
-    metric = "Gpx/s composited (%s)" % ("heptagram fill 4096^2 Matte8" if args.workload == "heptagram" else "100k-path batch 512^2 Matte8")
-    config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": "Matte8", "pixels": PIXELS_NOTE,
+    fmt_name = "Rgba8p" if rgba else "Matte8"
+    metric = "Gpx/s composited (%s %s)" % ("heptagram fill 4096^2" if args.workload == "heptagram" else "100k-path batch 512^2", fmt_name)
+    config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": fmt_name, "pixels": PIXELS_NOTE,
               "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
 
     # ---------------- reference arm: the oracle on all host cores ----------------
@@ -169,7 +173,9 @@ def main():
         if rank != 0:
             return
         wl = make_workload(args.workload, batch, 0)
-        config["workload"] = wl["desc"]
+        if rgba:
+            wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
+        config["workload"] = wl["desc"].replace("Matte8", fmt_name)
         config["raster"] = "%dx%d" % (wl["size"], wl["size"])
         cores = os.cpu_count() or 1
         per_step = max(cores, min(batch, cores * (2 if args.workload == "heptagram" else 64)))
@@ -203,17 +209,20 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     wl = make_workload(args.workload, batch, rank)
+    if rgba:
+        wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
     size = wl["size"]
-    config["workload"] = wl["desc"]
+    config["workload"] = wl["desc"].replace("Matte8", fmt_name)
     config["raster"] = "%dx%d" % (size, size)
-    b = Batch(size, size, Format.Matte8, batch, device=local_rank)
+    b = Batch(size, size, Format.Rgba8p if rgba else Format.Matte8, batch, device=local_rank)
+    colors = np.tile(np.array([200, 120, 40, 255], dtype=np.uint8), (batch, 1)) if rgba else None
     stream = torch.cuda.ExternalStream(b.stream(), device=local_rank)
     px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" and batch <= 512 else range(min(batch, 2)))
     if len(px_fill) == batch:
         px_step = float(sum(px_fill))
     else:  # heptagram: every fill has the same top row
         px_step = float(px_fill[0]) * batch
-    raster_bytes = size * size
+    raster_bytes = size * size * bpp
 
     def barrier():
         if world > 1:
@@ -229,7 +238,7 @@ def main():
         return float(t.item())
 
     # ---- value: ops resident in HBM ----
-    b.upload(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+    b.upload(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"], colors=colors)
     for _ in range(args.warmup):
         b.run()
     barrier()
@@ -261,13 +270,13 @@ def main():
     pinned = torch.empty(batch * raster_bytes, dtype=torch.uint8, pin_memory=True)
     e2e_steps = max(3, min(args.steps, 10))
     for _ in range(2):
-        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"], colors=colors)
         b.read_into(0, batch, pinned.data_ptr(), pinned.numel())
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(stream)
     for _ in range(e2e_steps):
-        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"])
+        b.fill(wl["ops"], wl["offs"], rules=wl["rules"], transforms=wl["tr"], colors=colors)
         b.read_into(0, batch, pinned.data_ptr(), pinned.numel())
     e1.record(stream)
     barrier()
@@ -281,15 +290,15 @@ def main():
     roof = None
     if tile_n:
         per_launch_ms = tile_ms / tile_n
-        achieved = px_step / (per_launch_ms * 1e-3) / 1e9
+        achieved = px_step * (8 if rgba else 1) / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload)
+                traffic = json.load(f).get(args.workload + ("_rgba8p" if rgba else ""))
         except Exception:
             pass
         roof = {"kernel": "raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step, "avg_launch_ms": per_launch_ms,
+                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step * (8 if rgba else 1), "bytes_per_px": 8 if rgba else 1, "avg_launch_ms": per_launch_ms,
                 "launches_timed": tile_n, "share_of_step": tile_ms / ms if ms else None}
 
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----

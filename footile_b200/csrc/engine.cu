@@ -728,12 +728,30 @@ __device__ __forceinline__ uint32_t quad_alpha(int32_t p0, int32_t p1, int32_t p
     }
 }
 
-__device__ __forceinline__ uint32_t blend_rgba(uint32_t px, uint32_t color, uint32_t alpha, uint32_t clr_a) {
+__device__ __forceinline__ uint32_t blend_rgba_general(uint32_t px, uint32_t color, uint32_t alpha, uint32_t clr_a) {
     uint32_t sa1 = 255u - pix::ch8_mul(alpha, clr_a);
     uint32_t o = 0;
 #pragma unroll
     for (int ch = 0; ch < 4; ch++) o |= pix::src_over_ch((px >> (8 * ch)) & 0xFF, (color >> (8 * ch)) & 0xFF, alpha, sa1) << (8 * ch);
     return o;
+}
+// Ch8 d * Ch8(255) on the four channels of a pixel at once: with pix's 12-bit multiply this is
+// d - 1 for 1 <= d <= 15 and d otherwise (pix_compat.cuh; checked exhaustively in tests/test_host.py).
+__device__ __forceinline__ uint32_t mul255_x4(uint32_t w) {
+    // plain integer ops on purpose: the __vset*4 video intrinsics (emulated through inline lop3 on
+    // sm_100a) were mis-scheduled under if-conversion in this kernel
+    uint32_t nz = w | (w >> 4);
+    nz |= nz >> 2;
+    nz |= nz >> 1;  // bit 0 of each byte: the byte is non-zero
+    uint32_t hi = w & 0xF0F0F0F0u;
+    hi |= hi >> 2;
+    hi |= hi >> 1;  // bit 4 of each byte: the byte is >= 16
+    return w - (nz & ~(hi >> 4) & 0x01010101u);
+}
+// SrcOver of one Rgba8p pixel (the 4-pixel and 512-pixel fast paths for alpha = 0 and for opaque
+// full coverage live in emit16 / resolve_row).
+__device__ __forceinline__ uint32_t blend_rgba(uint32_t px, uint32_t color, uint32_t alpha, uint32_t clr_a) {
+    return blend_rgba_general(px, color, alpha, clr_a);
 }
 
 // alpha of one pixel from the wrapped i16 sum (fig.rs:637-664; imgbuf.rs:54-66,157-167)
@@ -744,7 +762,7 @@ __device__ __forceinline__ uint32_t rule_alpha(int32_t sum) {
         int32_t c = (s & 0xFF) - (s & 0x100);
         s = c < 0 ? -c : c;
     }
-    return (uint32_t)__vimin_s32_relu(s, 255);
+    return (uint32_t)(s < 0 ? 0 : (s > 255 ? 255 : s));
 }
 
 // Output of one pixel.
@@ -784,12 +802,22 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
         for (int j = 0; j < 4; j++) {
             const uint32_t w = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
             if (ALIGNED && x + 4 * j + 4 <= W) {
-                uint4 t = reinterpret_cast<uint4 *>(d)[j];
-                t.x = blend_rgba(t.x, color, w & 0xFF, clr_a);
-                t.y = blend_rgba(t.y, color, (w >> 8) & 0xFF, clr_a);
-                t.z = blend_rgba(t.z, color, (w >> 16) & 0xFF, clr_a);
-                t.w = blend_rgba(t.w, color, w >> 24, clr_a);
-                reinterpret_cast<uint4 *>(d)[j] = t;
+                uint4 *q4 = reinterpret_cast<uint4 *>(d) + j;
+                if (w == 0xFFFFFFFFu && clr_a == 255) {  // four opaque pixels: no read
+                    const uint32_t c = mul255_x4(color);
+                    *q4 = make_uint4(c, c, c, c);
+                } else {
+                    uint4 t = *q4;
+                    if (w == 0) {
+                        t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
+                    } else {
+                        t.x = blend_rgba(t.x, color, w & 0xFF, clr_a);
+                        t.y = blend_rgba(t.y, color, (w >> 8) & 0xFF, clr_a);
+                        t.z = blend_rgba(t.z, color, (w >> 16) & 0xFF, clr_a);
+                        t.w = blend_rgba(t.w, color, w >> 24, clr_a);
+                    }
+                    *q4 = t;
+                }
             } else {
 #pragma unroll
                 for (uint32_t i = 0; i < 4; i++)
@@ -841,7 +869,22 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         const bool full = (ch + 1) * CHUNK <= W;
         if (!((dense >> i) & 1u)) {
             if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(q, q, q, q);
-            else emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
+            else if (FMT == FTL_RGBA8P && ALIGNED && full && (q == 0 || (q == 0xFFFFFFFFu && clr_a == 255))) {
+                // edge-free chunk of one alpha: 512 pixels = 2 KiB, consecutive lanes on consecutive 16 bytes
+                uint4 *p = reinterpret_cast<uint4 *>(dst) + ch * 128 + lane;
+                if (q == 0) {
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        uint4 t = p[32 * j];
+                        t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
+                        p[32 * j] = t;
+                    }
+                } else {
+                    const uint32_t c = mul255_x4(color);
+#pragma unroll
+                    for (int j = 0; j < 4; j++) p[32 * j] = make_uint4(c, c, c, c);
+                }
+            } else emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
             continue;
         }
         const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, i);

@@ -134,3 +134,11 @@ def test_host_stroker_matches_oracle(join, limit):
         got = _outline(join, limit, np.float32(0.3) * np.float32(0.3), ops, counts, wide)
         assert len(got) == len(exp)
         assert got.tobytes() == exp.tobytes()
+
+
+def test_ch8_mul_by_255_identity():
+    """The device fast path for alpha = 0 / opaque pixels uses d*255 = d-1 for 1<=d<=15 else d
+    (a consequence of pix's 12-bit Ch8 multiply); check it against the oracle's pix_compat exhaustively."""
+    for d in range(256):
+        got = int(oracle.src_over([d, 0], [0, 0], 0)[0])  # alpha 0: d' = 0 + d*(255-0)
+        assert got == (d - 1 if 1 <= d <= 15 else d), d
