@@ -798,8 +798,8 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
         }
     } else if (FMT == FTL_RGBA8P) {  // fig.rs:641-642,662-663 via pix (pix_compat.cuh)
         uint32_t *d = reinterpret_cast<uint32_t *>(dst) + x;
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {  // not unrolled: the general blend is large and this body is instantiated at six call sites
             const uint32_t w = j == 0 ? a0 : (j == 1 ? a1 : (j == 2 ? a2 : a3));
             if (ALIGNED && x + 4 * j + 4 <= W) {
                 uint4 *q4 = reinterpret_cast<uint4 *>(d) + j;
