@@ -87,6 +87,8 @@ def lib():
         L.orc_write_raster.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_last_info.restype = None
         L.orc_last_info.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_set_rows.restype = None
+        L.orc_set_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
         L.orc_get_pen_width.restype = C.c_float
         L.orc_get_pen_width.argtypes = [C.c_void_p]
         L.orc_debug_flatten.restype = C.c_size_t
@@ -202,6 +204,11 @@ class Plotter:
 
     def set_join(self, kind, miter_limit=4.0):
         lib().orc_set_join(self._h, kind, float(miter_limit))
+        return self
+
+    def set_rows(self, lo, hi):
+        """Order-free mode only: draw raster rows [lo, hi) only (stripe checks of huge rasters)."""
+        lib().orc_set_rows(self._h, int(lo), int(hi))
         return self
 
     def fill(self, rule, ops, clr=None):

@@ -418,7 +418,9 @@ FillInfo fill_sequential(const Fig &fig, int rule, RasterRef ras, const uint8_t 
 
 // Order-free closed form.  Checked against
 // fill_sequential() by tests/test_oracle_orderfree.py.
-FillInfo fill_orderfree(const Fig &fig, int rule, RasterRef ras, const uint8_t *clr, bool simd) {
+// rows_lo/rows_hi: only raster rows in [rows_lo, rows_hi) are drawn (stripe checks of huge rasters).
+FillInfo fill_orderfree(const Fig &fig, int rule, RasterRef ras, const uint8_t *clr, bool simd, int64_t rows_lo = 0,
+                        int64_t rows_hi = INT64_MAX) {
     FillInfo info = {FWD, 0, (uint32_t)fig.points.size()};
     uint32_t n = (uint32_t)fig.points.size();
     if (n == 0) return info;
@@ -432,10 +434,11 @@ FillInfo fill_orderfree(const Fig &fig, int rule, RasterRef ras, const uint8_t *
     int dir = widdershins(a, b) ? FWD : REV;
     int32_t top = fx_to_i32(p.y);
     info.dir = dir; info.top_row = top;
-    int64_t first_row = std::max(top, 0);
-    if (first_row >= (int64_t)ras.h) return info;
+    int64_t first_row = std::max<int64_t>(std::max(top, 0), rows_lo);
+    int64_t last_row = std::min<int64_t>(ras.h, rows_hi);
+    if (first_row >= last_row) return info;
     int32_t W = (int32_t)ras.w;
-    size_t rows = (size_t)(ras.h - first_row);
+    size_t rows = (size_t)(last_row - first_row);
     // i32 accumulators, truncated to i16 at resolve: the i16 wrapping sums of
     // the reference are a ring homomorphism image of these.
     std::vector<int32_t> acc(rows * (size_t)W, 0);
@@ -447,10 +450,10 @@ FillInfo fill_orderfree(const Fig &fig, int rule, RasterRef ras, const uint8_t *
             Edge e = edge_new(w, P[v], P[w], dd);
             int32_t ed = dd == dir ? 1 : -1;
             int32_t r0 = fx_to_i32(e.y_upper), r1 = fx_to_i32(e.y_lower);
-            for (int64_t r = r0; r <= r1; r++) {
+            for (int64_t r = std::max<int64_t>(r0, first_row + shift); r <= r1; r++) {
                 int64_t ry = r - shift;
                 if (ry < first_row) continue;
-                if (ry >= (int64_t)ras.h) break;
+                if (ry >= last_row) break;
                 fx_t x_bot = (fx_t)((uint32_t)e.x_bot + (uint32_t)(r - r0) * (uint32_t)e.inv_slope);
                 int32_t cov = (r == r1 ? pixel_cov(fx_fract(e.y_lower)) : 256) - (r == r0 ? pixel_cov(fx_fract(e.y_upper)) : 0);
                 if (cov <= 0) continue;
@@ -678,13 +681,14 @@ struct Plotter {
     uint32_t vid_cap = 65535;
     bool simd = true;
     bool orderfree = false;
+    int64_t rows_lo = 0, rows_hi = INT64_MAX;
     FillInfo last = {FWD, 0, 0};
     RasterRef ras() { return {px.data(), w, h, fmt}; }
     void fill(int rule, const PathOp *ops, size_t n, const uint8_t *clr) {                   // plotter.rs:339-350
         FigSink sink(vid_cap);
         Flattener(st, sink).run(ops, n);
         sink.fig.close();
-        last = orderfree ? fill_orderfree(sink.fig, rule, ras(), clr, simd)
+        last = orderfree ? fill_orderfree(sink.fig, rule, ras(), clr, simd, rows_lo, rows_hi)
                          : fill_sequential(sink.fig, rule, ras(), clr, simd, nullptr);
     }
     std::vector<PathOp> stroke_ops(const PathOp *ops, size_t n) {                            // plotter.rs:361-363
@@ -790,6 +794,8 @@ int orc_stroke(void *h, const orc_path_op *ops, size_t n, const uint8_t *clr) {
 void orc_read_raster(void *h, uint8_t *dst) { Plotter *p = (Plotter *)h; memcpy(dst, p->px.data(), p->px.size()); }
 void orc_write_raster(void *h, const uint8_t *src) { Plotter *p = (Plotter *)h; memcpy(p->px.data(), src, p->px.size()); }
 void orc_last_info(void *h, int32_t *out) { Plotter *p = (Plotter *)h; out[0] = p->last.dir; out[1] = p->last.top_row; out[2] = (int32_t)p->last.n_points; }
+// order-free mode only: restrict drawing to raster rows [lo, hi)
+void orc_set_rows(void *h, int64_t lo, int64_t hi) { Plotter *p = (Plotter *)h; p->rows_lo = lo; p->rows_hi = hi; }
 float orc_get_pen_width(void *h) { return ((Plotter *)h)->st.s_width; }
 
 // Probe: flattened Fixed points of a fill (after Fig intake + final close).
