@@ -126,6 +126,8 @@ struct Params {  // per-call constants, passed by value
     uint32_t log2R, R, n_bands, WP, chunks;  // rows per tile, bands per job, smem row stride (cells), 512-cell chunks per row
     uint32_t n_jobs, n_ops, n_tiles;
     uint32_t win_chunks, warp_words, cta_warps;  // chunks per row window, smem words per warp, warps per CTA
+    uint32_t n_win, n_bins;                      // windows per row; bins = n_tiles * n_win
+    uint32_t all_direct;                         // host-proven: every job has <= DIRECT_MAX vertices (no binning needed)
 };
 
 // ---------------------------------------------------------------------------
@@ -558,10 +560,51 @@ __device__ __forceinline__ bool edge_bands(const EdgeRec &e, const Params &P, ui
     return true;
 }
 
-// Counting sort of edges by (job,row band): pass FILL=false counts, pass
-// FILL=true writes edge ids at the scanned offsets.  Short edges are handled
-// by their own thread; an edge crossing many bands is spread over the warp.
-// Jobs with at most DIRECT_MAX edge slots are not binned at all.
+// Conservative range of row windows an edge can write to on the rows [ra, rb] of one band (both
+// inside the edge's own rows).  The span of a row is linear in the row, so the extremes are at the
+// two end rows, evaluated as edge_row_setup does; the scatter loop can run at most |dx/dy| + 2 cells
+// past the leftmost one.  Anything that would wrap 32-bit arithmetic falls back to "all windows".
+__device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32_t rb, const Params &P, uint32_t *w0, uint32_t *w1) {
+    *w0 = 0;
+    *w1 = P.n_win - 1;
+    if (P.n_win == 1) return;
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    const int64_t slope = e.inv_slope;
+    for (int t = 0; t < 2; t++) {
+        const int32_t r = t ? rb : ra;
+        const int64_t x_bot = (int64_t)e.x_bot0 + (int64_t)(r - e.ry0) * slope;
+        const int64_t x_top = x_bot - slope;
+        if (x_bot != (int32_t)x_bot || x_top != (int32_t)x_top) return;
+        lo = min(lo, min(x_bot, x_top));
+        hi = max(hi, max(x_bot, x_top));
+    }
+    const int64_t run = (slope < 0 ? -slope : slope) >> 16;
+    int64_t lo_pix = (lo >> 16) - 1, hi_pix = (hi >> 16) + run + 3;
+    const int64_t wmax = (int64_t)P.W - 1;
+    lo_pix = lo_pix < 0 ? 0 : (lo_pix > wmax ? wmax : lo_pix);
+    hi_pix = hi_pix < 0 ? 0 : (hi_pix > wmax ? wmax : hi_pix);
+    const uint32_t win_cells = P.win_chunks * 512u;
+    *w0 = (uint32_t)lo_pix / win_cells;
+    *w1 = (uint32_t)hi_pix / win_cells;
+}
+
+// Counting sort of edges by (job, row band, row window): pass FILL=false counts, pass FILL=true
+// writes edge ids at the scanned offsets.  Short edges are handled by their own thread; an edge
+// crossing many bands is spread over the warp.  Jobs with at most DIRECT_MAX edge slots are not
+// binned at all.
+template <bool FILL>
+__device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t tile, uint32_t band, const Params &P, uint32_t *tile_count,
+                                        const uint32_t *tile_off, uint32_t *entries) {
+    const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
+    const int32_t ra = max(e.ry0, row0), rb = min(min(e.ry1, row0 + (int32_t)P.R - 1), (int32_t)P.row_end - 1);
+    uint32_t w0, w1;
+    edge_windows(e, ra, rb, P, &w0, &w1);
+    for (uint32_t w = w0; w <= w1; w++) {
+        const uint32_t bin = tile * P.n_win + w;
+        const uint32_t slot = atomicAdd(&tile_count[bin], 1u);
+        if (FILL) entries[tile_off[bin] + slot] = k;
+    }
+}
 template <bool FILL>
 __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
                                                  const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
@@ -573,8 +616,10 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
     for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < nv; k0 += span) {
         uint32_t k = k0 + lane;
         uint32_t b0 = 0, nb = 0, tbase = 0;
+        EdgeRec e;
+        e.flags = 0;
         if (k < nv) {
-            EdgeRec e = E[k];
+            e = E[k];
             uint32_t b1;
             if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
                 const JobState &js = JS[e.job];
@@ -584,23 +629,16 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
                 }
             }
         }
-        if (nb > 0 && nb <= 4) {
-            for (uint32_t b = b0; b < b0 + nb; b++) {
-                uint32_t slot = atomicAdd(&tile_count[tbase + b], 1u);
-                if (FILL) entries[tile_off[tbase + b] + slot] = k;
-            }
-        }
+        if (nb > 0 && nb <= 4)
+            for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k, tbase + b, b, P, tile_count, tile_off, entries);
         uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
         while (tall) {
             int src = __ffs(tall) - 1;
             tall &= tall - 1;
             uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src);
             uint32_t stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
-            for (uint32_t b = lane; b < snb; b += 32) {
-                uint32_t t = stb + sb0 + b;
-                uint32_t slot = atomicAdd(&tile_count[t], 1u);
-                if (FILL) entries[tile_off[t] + slot] = k0 + src;
-            }
+            const EdgeRec es = E[k0 + src];
+            for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + src, stb + sb0 + b, sb0 + b, P, tile_count, tile_off, entries);
         }
     }
 }
@@ -965,7 +1003,7 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
 // window, with the running sum carried across windows.  Warps never wait for
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
-template <int FMT, bool ALIGNED>
+template <int FMT, bool ALIGNED, bool GENERAL>
 __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
@@ -990,24 +1028,34 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
         const unsigned long long raster = jobs[j].raster;
         const uint32_t rule = jobs[j].rule, color = jobs[j].color;
         const uint32_t n_slots = js.vtx_end - js.vtx_begin;
-        const bool direct = n_slots <= DIRECT_MAX;
-        const uint32_t e0 = direct ? js.vtx_begin : tile_off[tile];
-        const uint32_t ne = direct ? n_slots : tile_off[tile + 1] - e0;
-        // The first 32 edges of the tile stay in registers for all its rows.
+        // Edge list of the tile: the job's own edges (direct: at most DIRECT_MAX slots; the only case
+        // when GENERAL is false), or the (tile, window) bins.  With a single list for all windows the
+        // first 32 edges stay in registers for all rows of the tile.
+        const bool direct = !GENERAL || n_slots <= DIRECT_MAX;
+        const bool one_list = !GENERAL || direct || P.n_win == 1;
+        uint32_t e0 = direct ? js.vtx_begin : tile_off[tile * P.n_win];
+        uint32_t ne = direct ? n_slots : tile_off[tile * P.n_win + 1] - e0;
         EdgeRec mine;
         mine.flags = 0;
-        if (lane < ne) mine = E[direct ? e0 + lane : entries[e0 + lane]];
+        if (one_list && lane < ne) mine = E[direct ? e0 + lane : entries[e0 + lane]];
         for (int32_t ry = row0; ry < row_hi; ry++) {
             EdgeRowState st;
             st.cov = 0;
             if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) st = edge_row_setup(mine, ry, W, 0);
             uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
             int32_t carry = 0;
-            for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells) {
+            uint32_t bin = tile * P.n_win;
+            for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++) {
                 const int32_t win_hi = min(W, win_lo + win_cells);
                 // ---- (c) scatter: one lane per edge crossing this row ----
-                edge_row_scatter(st, win_lo, win_hi, cells, mask);
-                for (uint32_t i = lane + 32; i < ne; i += 32) {
+                uint32_t first = 32;
+                if (one_list) edge_row_scatter(st, win_lo, win_hi, cells, mask);
+                else {  // wide raster with many edges: each window has its own bin
+                    e0 = tile_off[bin];
+                    ne = tile_off[bin + 1] - e0;
+                    first = 0;
+                }
+                for (uint32_t i = lane + first; i < ne; i += 32) {
                     const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
                     if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
                         EdgeRowState s2 = edge_row_setup(e, ry, W, win_lo);
@@ -1232,11 +1280,16 @@ static int run_pipeline(Engine::Impl &m, bool exact);
 static int resolve_pending(Engine::Impl &m);
 
 typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *, const Counters *);
-static TileKernel tile_kernel(int fmt, bool aligned) {
+static TileKernel tile_kernel(int fmt, bool aligned, bool general) {
+    if (general) switch (fmt) {
+        case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true, true> : raster_tiles<FTL_MATTE8, false, true>;
+        case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true, true> : raster_tiles<FTL_GRAYA8P, false, true>;
+        default: return aligned ? raster_tiles<FTL_RGBA8P, true, true> : raster_tiles<FTL_RGBA8P, false, true>;
+        }
     switch (fmt) {
-    case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true> : raster_tiles<FTL_MATTE8, false>;
-    case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true> : raster_tiles<FTL_GRAYA8P, false>;
-    default: return aligned ? raster_tiles<FTL_RGBA8P, true> : raster_tiles<FTL_RGBA8P, false>;
+    case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true, false> : raster_tiles<FTL_MATTE8, false, false>;
+    case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true, false> : raster_tiles<FTL_GRAYA8P, false, false>;
+    default: return aligned ? raster_tiles<FTL_RGBA8P, true, false> : raster_tiles<FTL_RGBA8P, false, false>;
     }
 }
 
@@ -1267,9 +1320,9 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
     m->max_smem = prop.sharedMemPerBlockOptin;
     CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
     for (int f = 0; f < 3; f++)
-        for (int a = 0; a < 2; a++) {
-            CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
-            CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        for (int a = 0; a < 4; a++) {
+            CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+            CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         }
     CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
     if (const char *ev = getenv("FTL_NO_GRAPH")) m->use_graph = atoi(ev) == 0;
@@ -1301,6 +1354,7 @@ static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
     uint32_t win = 4;
     if (const char *ev = getenv("FTL_WIN_CHUNKS")) win = (uint32_t)std::min(32, std::max(1, atoi(ev)));  // tuning knob
     P->win_chunks = std::min(P->chunks, win);
+    P->n_win = (P->chunks + P->win_chunks - 1) / P->win_chunks;
     P->warp_words = (P->win_chunks * CHUNK + P->win_chunks + 3u) & ~3u;  // cells + masks, 16-byte multiple
     P->cta_warps = 4;
     size_t cta_bytes = (size_t)P->warp_words * 4 * P->cta_warps;
@@ -1361,6 +1415,19 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         return FTL_ERR_INVALID;
     }
     P.n_tiles = (uint32_t)nt;
+    if (nt * P.n_win >= 0x7FFFFFFFull) {
+        set_error("too many tiles for one call");
+        return FTL_ERR_INVALID;
+    }
+    P.n_bins = (uint32_t)(nt * P.n_win);
+    // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
+    P.all_direct = 1;
+    for (const HostJob &h : jobs) {
+        if (h.op_end - h.op_begin > DIRECT_MAX) P.all_direct = 0;
+        for (uint32_t i = h.op_begin; i < h.op_end && P.all_direct; i++)
+            if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) P.all_direct = 0;
+        if (!P.all_direct) break;
+    }
     // stage + upload ops and job descriptors
     size_t ops_bytes = n_ops * sizeof(ftl_path_op), jobs_bytes = jobs.size() * sizeof(JobDesc);
     if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
@@ -1420,10 +1487,11 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     if ((rc = m.jstate.ensure((size_t)P.n_jobs * sizeof(JobState), st))) return rc;
     if ((rc = m.cnt.ensure((size_t)(P.n_ops + 1) * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure(((size_t)P.n_ops + 1) * sizeof(SumHead), st))) return rc;
-    if ((rc = m.tcount.ensure((size_t)P.n_tiles * sizeof(uint32_t), st))) return rc;
-    if ((rc = m.toff.ensure(((size_t)P.n_tiles + 1) * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.tcount.ensure((size_t)P.n_bins * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.toff.ensure(((size_t)P.n_bins + 1) * sizeof(uint32_t), st))) return rc;
     if ((rc = m.partials.ensure((size_t)div_up(P.n_ops + 1, SCAN_BLOCK) * sizeof(SumHead), st))) return rc;
-    if ((rc = m.tpart.ensure((size_t)div_up(P.n_tiles + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.tpart.ensure((size_t)div_up(P.n_bins + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.entries.ensure(sizeof(uint32_t), st))) return rc;
     if (!exact) {
         if ((rc = m.vtx.ensure(sizeof(Vtx), st))) return rc;
         if ((rc = m.edges.ensure(sizeof(EdgeRec), st))) return rc;
@@ -1459,24 +1527,25 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
             flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt); LAUNCHED();
         }
         init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
-        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
         vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
         job_finalize<<<div_up(P.n_jobs, 128), 128, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (const uint32_t *)m.sub_last.p, P.n_jobs); LAUNCHED();
         edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p); LAUNCHED();
+        if (P.all_direct) return FTL_OK;  // every tile scans its job's own edges: nothing to bin
+        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
         bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
-        int r3 = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_tiles, (uint32_t *)m.toff.p, m.tpart);
+        int r3 = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_bins, (uint32_t *)m.toff.p, m.tpart);
         if (r3) return r3;
         if (sync_sizes) {
-            CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_tiles], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+            CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_bins], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
             CK(cudaStreamSynchronize(st));
             uint32_t n_entries = *(uint32_t *)m.pin_small.p;
             if ((r3 = m.entries.ensure((size_t)(n_entries ? n_entries : 1) * sizeof(uint32_t), st))) return r3;
             cap_e = (uint32_t)std::min<size_t>(m.entries.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF);
         }
-        set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_tiles, cap_e); LAUNCHED();
-        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_tiles * sizeof(uint32_t), st));
+        set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_bins, cap_e); LAUNCHED();
+        CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
         bin_edges<true><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
                                             (uint32_t *)m.entries.p); LAUNCHED();
         CK(cudaGetLastError());
@@ -1495,7 +1564,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.win_chunks};
+                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct};
         if (!m.graph || key != m.graph_key) {
             m.drop_graph();
             cudaGraph_t g = nullptr;
@@ -1521,7 +1590,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     // ---- (c)+(d) tiles ----
     int occ = 1;
     const bool aligned = P.fmt == FTL_MATTE8 ? (P.W % 16 == 0) : (P.fmt == FTL_RGBA8P ? (P.W % 4 == 0) : true);
-    TileKernel tk = tile_kernel((int)P.fmt, aligned);
+    TileKernel tk = tile_kernel((int)P.fmt, aligned, !P.all_direct);
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;

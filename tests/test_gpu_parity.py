@@ -507,3 +507,25 @@ def test_packed_readback_roundtrip():
             img[-1, -1] = 7
         g = Plotter(Raster(w, h, Format.Matte8, img))
         assert np.array_equal(g.raster().pixels, img), kind
+
+
+# ---- wide + dense: edges are binned per (band, row window); long shallow edges cross several windows ----
+@pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p])
+def test_wide_dense_window_bins(fmt):
+    rng = np.random.default_rng(99)
+    w, h = 9000, 40   # 5 windows of 2048 cells
+    ops = []
+    for _ in range(60):  # 60 polygons x 5 vertices = 300 edges > DIRECT_MAX, many nearly horizontal
+        n = 5
+        xs = rng.uniform(-1500, w + 1500, n)
+        ys = rng.uniform(-5, h + 5, n)
+        if rng.random() < 0.3:
+            ys = np.round(ys)
+        ops += list(poly([(float(x), float(y)) for x, y in zip(xs, ys)]))
+    for rule in (FillRule.NonZero, FillRule.EvenOdd):
+        g, o = both(w, h, fmt, vid_cap=1 << 30)
+        clr = (90, 60, 30, 200)
+        g.fill(rule, ops, clr)
+        o.fill(int(rule), ops, clr)
+        assert g.debug_last_fill() == o.last_info()
+        assert_same(g, o, "rule %d" % rule)
