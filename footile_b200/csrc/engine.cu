@@ -27,6 +27,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <mutex>
 #include <thread>
 #include <string>
 #include <vector>
@@ -1302,6 +1303,15 @@ static TileKernel tile_kernel(int fmt, bool aligned, bool general) {
         }                                                                    \
     } while (0)
 
+// Per-device facts and kernel attributes are set up once per process, not once per handle.
+struct DeviceInfo {
+    bool ready = false;
+    int n_sms = 0;
+    size_t max_smem = 0;
+};
+static DeviceInfo g_dev[64];
+static std::mutex g_dev_mu;
+
 static int engine_init(Engine::Impl *m, int device, void **stream_out) {
     int n = 0;
     cudaError_t e = cudaGetDeviceCount(&n);
@@ -1309,22 +1319,32 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
         set_error(std::string("no CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
         return FTL_ERR_NO_DEVICE;
     }
-    if (device < 0 || device >= n) {
+    if (device < 0 || device >= n || device >= 64) {
         set_error("device index out of range");
         return FTL_ERR_INVALID;
     }
     CK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    CK(cudaGetDeviceProperties(&prop, device));
-    m->n_sms = prop.multiProcessorCount;
-    m->max_smem = prop.sharedMemPerBlockOptin;
-    CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
-    for (int f = 0; f < 3; f++)
-        for (int a = 0; a < 4; a++) {
-            CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
-            CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    {
+        std::lock_guard<std::mutex> lock(g_dev_mu);
+        DeviceInfo &di = g_dev[device];
+        if (!di.ready) {
+            int v = 0;
+            CK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+            di.n_sms = v;
+            CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+            di.max_smem = (size_t)v;
+            for (int f = 0; f < 3; f++)
+                for (int a = 0; a < 4; a++) {
+                    CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
+                    CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                }
+            CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
+            di.ready = true;
         }
-    CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)m->max_smem));
+        m->n_sms = di.n_sms;
+        m->max_smem = di.max_smem;
+    }
+    CK(cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking));
     if (const char *ev = getenv("FTL_NO_GRAPH")) m->use_graph = atoi(ev) == 0;
     *stream_out = m->st;
     return FTL_OK;
