@@ -98,6 +98,14 @@ def make_workload(name, batch, rank):
         size = 512
         ops, offs, rules = scenes.random_curve_paths(rank * batch, batch)
         return dict(size=size, ops=ops, offs=offs, rules=rules, tr=None, desc="random quad/cubic paths (64 segments), 512x512 Matte8 per path")
+    if name == "fishy256":
+        size = 256
+        path = scenes.fishy_bench()
+        ops = np.tile(path, batch)
+        offs = np.arange(batch + 1, dtype=np.uint64) * np.uint64(len(path))
+        rules = np.zeros(batch, dtype=np.uint8)
+        tr = np.tile(np.array([2, 0, 0, 0, 2, 0], dtype=np.float32), (batch, 1))
+        return dict(size=size, ops=ops, offs=offs, rules=rules, tr=tr, desc="benches/fishyb.rs fill_256: fishy path, scale(2,2), 256x256 Matte8 per fill")
     raise SystemExit("unknown workload " + name)
 
 
@@ -116,30 +124,17 @@ def oracle_pixels(wl, sample):
 
 
 def cpu_run(wl, jobs, threads):
-    """Time the oracle over `jobs` (indices) using `threads` host threads; returns seconds (rasters pre-allocated)."""
+    """Seconds the oracle needs for `jobs` (indices) on `threads` C++ threads (rasters pre-allocated, timed in C++)."""
     import oracle
     size = wl["size"]
-    chunks = [jobs[t::threads] for t in range(threads)]
-    plotters = [[oracle.Plotter(size, size, wl.get("ofmt", oracle.MATTE8)) for _ in c] for c in chunks]
-    for ps, c in zip(plotters, chunks):
-        for p, j in zip(ps, c):
-            if wl["tr"] is not None:
-                p.set_transform(wl["tr"][j])
-
-    def work(t):
-        for p, j in zip(plotters[t], chunks[t]):
-            p.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], wl.get("color", (255,)))
-
-    t0 = time.perf_counter()
-    if threads == 1:
-        work(0)
-    else:
-        ths = [threading.Thread(target=work, args=(t,)) for t in range(threads)]
-        for th in ths:
-            th.start()
-        for th in ths:
-            th.join()
-    return time.perf_counter() - t0
+    jobs = list(jobs)
+    parts = [wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])] for j in jobs]
+    offs = np.zeros(len(jobs) + 1, dtype=np.uint64)
+    offs[1:] = np.cumsum([len(p) for p in parts])
+    ops = np.concatenate(parts)
+    rules = np.array([wl["rules"][j] for j in jobs], dtype=np.uint8)
+    tr = None if wl["tr"] is None else np.ascontiguousarray(np.array([wl["tr"][j] for j in jobs], dtype=np.float32))
+    return oracle.batch_fill_timed(size, size, wl.get("ofmt", oracle.MATTE8), ops, offs, rules, tr, wl.get("color", (255,)), threads, 1)
 
 
 def main():
@@ -148,7 +143,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512"])
+    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256"])
     ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
     ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p"], help="pixel format of the rasters")
@@ -158,13 +153,13 @@ def main():
         args.warmup = 3
     rgba = args.format == "rgba8p"
     bpp = 4 if rgba else 1
-    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else (1024 if rgba else 4096))
+    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else ((1024 if rgba else 4096) if args.workload == "batch512" else 16384))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     unit = "Gpx/s"
     fmt_name = "Rgba8p" if rgba else "Matte8"
-    metric = "Gpx/s composited (%s %s)" % ("heptagram fill 4096^2" if args.workload == "heptagram" else "100k-path batch 512^2", fmt_name)
+    metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2"}[args.workload], fmt_name)
     config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": fmt_name, "pixels": PIXELS_NOTE,
               "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
 
@@ -178,7 +173,7 @@ def main():
         config["workload"] = wl["desc"].replace("Matte8", fmt_name)
         config["raster"] = "%dx%d" % (wl["size"], wl["size"])
         cores = os.cpu_count() or 1
-        per_step = max(cores, min(batch, cores * (2 if args.workload == "heptagram" else 64)))
+        per_step = max(cores, min(batch, cores * {"heptagram": 2, "batch512": 64, "fishy256": 1024}[args.workload]))
         jobs = list(range(per_step))
         px = sum(oracle_pixels(wl, jobs))
         for _ in range(min(args.warmup, 2)):
@@ -187,7 +182,7 @@ def main():
         for _ in range(args.steps):
             t += cpu_run(wl, jobs, cores)
         v = px * args.steps / t / 1e9
-        sample = "%d fills per step on %d threads (one plotter per thread), rasters pre-allocated" % (per_step, cores)
+        sample = "%d fills per step on %d C++ threads (one Plotter per fill, rasters pre-allocated, timed inside the oracle)" % (per_step, cores)
         print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": args.steps,
                           "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "i32 fixed-point 16.16 / u8", "data": "synthetic", "config": config,
@@ -217,7 +212,7 @@ def main():
     b = Batch(size, size, Format.Rgba8p if rgba else Format.Matte8, batch, device=local_rank)
     colors = np.tile(np.array([200, 120, 40, 255], dtype=np.uint8), (batch, 1)) if rgba else None
     stream = torch.cuda.ExternalStream(b.stream(), device=local_rank)
-    px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" and batch <= 512 else range(min(batch, 2)))
+    px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" else range(min(batch, 2)))
     if len(px_fill) == batch:
         px_step = float(sum(px_fill))
     else:  # heptagram: every fill has the same top row
@@ -304,7 +299,7 @@ def main():
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1:
-        n_cpu = args.cpu_fills or (8 if args.workload == "heptagram" else 256)
+        n_cpu = args.cpu_fills or {"heptagram": 8, "batch512": 256, "fishy256": 4096}[args.workload]
         n_cpu = min(n_cpu, batch)
         jobs = list(range(n_cpu))
         cpu_run(wl, jobs[: max(1, n_cpu // 4)], 1)
@@ -312,9 +307,9 @@ def main():
         while t < 8.0 and reps < 50:
             t += cpu_run(wl, jobs, 1)
             reps += 1
-        cpx = sum(oracle_pixels(wl, jobs)) if args.workload == "batch512" else px_step / batch * n_cpu
+        cpx = px_step / batch * n_cpu
         cpu = {"value": cpx * reps / t / 1e9, "unit": unit, "cores": 1, "kind": "port",
-               "sample": "%d fills x %d repeats of this workload, single thread, SSSE3 accumulate, rasters pre-allocated" % (n_cpu, reps),
+               "sample": "%d fills x %d repeats of this workload, single thread, SSSE3 accumulate, rasters pre-allocated, timed inside the oracle" % (n_cpu, reps),
                "paths_per_s": n_cpu * reps / t}
 
     if rank == 0:

@@ -89,6 +89,9 @@ def lib():
         L.orc_last_info.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_set_rows.restype = None
         L.orc_set_rows.argtypes = [C.c_void_p, C.c_int64, C.c_int64]
+        L.orc_batch_fill_timed.restype = C.c_double
+        L.orc_batch_fill_timed.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p, C.c_uint32, C.c_uint32]
         L.orc_get_pen_width.restype = C.c_float
         L.orc_get_pen_width.argtypes = [C.c_void_p]
         L.orc_debug_flatten.restype = C.c_size_t
@@ -172,6 +175,18 @@ def fig_fill(w, h, fmt, rule, subs, clr=None, raster=None, mode=0, simd=True, vi
                        mode, 1 if simd else 0, vid_cap, area.ctypes.data if want_area else None, info.ctypes.data)
     d = {"dir": int(info[0]), "top_row": int(info[1]), "n_points": int(info[2])}
     return (ras, d, area) if want_area else (ras, d)
+
+
+def batch_fill_timed(w, h, fmt, ops, offs, rules=None, transforms=None, clr=(255, 255, 255, 255), threads=1, repeats=1):
+    """Seconds the oracle needs to fill job j = ops[offs[j]:offs[j+1]] into its own w x h raster, for all jobs,
+    `repeats` times, on `threads` C++ threads (rasters pre-allocated, timed inside C++)."""
+    a = np.ascontiguousarray(np.asarray(ops, dtype=OP_DTYPE))
+    o = np.ascontiguousarray(np.asarray(offs, dtype=np.uint64))
+    r = None if rules is None else np.ascontiguousarray(np.asarray(rules, dtype=np.uint8))
+    t = None if transforms is None else np.ascontiguousarray(np.asarray(transforms, dtype=np.float32))
+    c = _clr(clr, fmt)
+    return lib().orc_batch_fill_timed(w, h, fmt, len(o) - 1, a.ctypes.data, o.ctypes.data, None if r is None else r.ctypes.data,
+                                      None if t is None else t.ctypes.data, c.ctypes.data, int(threads), int(repeats))
 
 
 class Plotter:

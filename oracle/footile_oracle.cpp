@@ -36,6 +36,8 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
+#include <thread>
 #include <numeric>
 #include <vector>
 #if defined(__SSSE3__)
@@ -829,6 +831,38 @@ size_t orc_debug_stroke_ops(void *h, const orc_path_op *ops, size_t n, orc_path_
     std::vector<PathOp> o = ((Plotter *)h)->stroke_ops((const PathOp *)ops, n);
     for (size_t i = 0; i < o.size() && i < cap; i++) memcpy(&out[i], &o[i], sizeof(PathOp));
     return o.size();
+}
+
+// Timed multi-threaded batch (bench.py cpu_baseline / --impl reference): job j = ops[offs[j], offs[j+1])
+// filled into its own pre-allocated w x h raster with rules[j], transforms[6j..] (or identity), colour
+// clr; jobs are dealt round-robin to n_threads std::threads, one Plotter per job (the reference is
+// single-threaded per Plotter).  Returns the wall time of the fills in seconds (allocation excluded).
+double orc_batch_fill_timed(uint32_t w, uint32_t h, int fmt, uint32_t n_jobs, const orc_path_op *ops, const uint64_t *offs,
+                            const uint8_t *rules, const float *transforms, const uint8_t *clr, uint32_t n_threads, uint32_t repeats) {
+    std::vector<Plotter *> ps(n_jobs);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        Plotter *p = new Plotter();
+        p->w = w; p->h = h; p->fmt = fmt;
+        p->px.assign((size_t)w * h * fmt_bpp(fmt), 0);
+        if (transforms) memcpy(p->st.e, transforms + 6 * (size_t)j, 6 * sizeof(float));
+        ps[j] = p;
+    }
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](uint32_t t) {
+        for (uint32_t r = 0; r < repeats; r++)
+            for (uint32_t j = t; j < n_jobs; j += n_threads)
+                ps[j]->fill(rules ? rules[j] : 0, (const PathOp *)ops + offs[j], (size_t)(offs[j + 1] - offs[j]), clr);
+    };
+    auto t0 = std::chrono::steady_clock::now();
+    if (n_threads == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t t = 0; t < n_threads; t++) th.emplace_back(work, t);
+        for (auto &t : th) t.join();
+    }
+    double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    for (Plotter *p : ps) delete p;
+    return dt;
 }
 
 }  // extern "C"
