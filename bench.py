@@ -84,7 +84,7 @@ class ClockSampler:
 
 
 # ---- workloads -----------------------------------------------------------------
-def make_workload(name, batch, rank):
+def make_workload(name, batch, rank, outline_of=None):
     from footile_b200 import scenes
     if name == "heptagram":
         size = 4096
@@ -106,6 +106,18 @@ def make_workload(name, batch, rank):
         rules = np.zeros(batch, dtype=np.uint8)
         tr = np.tile(np.array([2, 0, 0, 0, 2, 0], dtype=np.float32), (batch, 1))
         return dict(size=size, ops=ops, offs=offs, rules=rules, tr=tr, desc="benches/fishyb.rs fill_256: fishy path, scale(2,2), 256x256 Matte8 per fill")
+    if name == "strokes4k":
+        # config 3: the six stroke scenes x30 with Round joins; the OUTLINES (what Plotter::stroke hands to fill,
+        # plotter.rs:361-364) are made once, outside the timed region, by `outline_of` (the product's device flatten +
+        # host stroker in our arm, the oracle's in the reference arm) and then filled NonZero into 3840x2160 Rgba8p.
+        t0 = time.perf_counter()
+        outs = [outline_of(p) for p in scenes.stroke_scenes(30.0).values()]
+        t_outline = time.perf_counter() - t0
+        parts = [outs[j % len(outs)] for j in range(batch)]
+        offs = np.zeros(batch + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(p) for p in parts])
+        return dict(size=0, w=3840, h=2160, ops=np.concatenate(parts), offs=offs, rules=np.zeros(batch, dtype=np.uint8), tr=None,
+                    outline_ms=1e3 * t_outline, desc="stroke.rs/stroke2.rs/round.rs/over.rs/teeth.rs/curve.rs x30, Round joins, butt ends: outline fill into 3840x2160 Rgba8p")
     raise SystemExit("unknown workload " + name)
 
 
@@ -113,20 +125,21 @@ def oracle_pixels(wl, sample):
     """Pixels per fill by the reference's dense-row convention, from the oracle's top_row."""
     import oracle
     px = []
+    W, H = wl.get("w", wl["size"]), wl.get("h", wl["size"])
     for j in sample:
         o = oracle.Plotter(8, 8, oracle.MATTE8)  # tiny raster: only (dir, top_row) are needed
         if wl["tr"] is not None:
             o.set_transform(wl["tr"][j])
         o.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], (255,))
         top = o.last_info()["top_row"]
-        px.append(wl["size"] * max(0, wl["size"] - max(top, 0)))
+        px.append(W * max(0, H - max(top, 0)))
     return px
 
 
 def cpu_run(wl, jobs, threads):
     """Seconds the oracle needs for `jobs` (indices) on `threads` C++ threads (rasters pre-allocated, timed in C++)."""
     import oracle
-    size = wl["size"]
+    W, H = wl.get("w", wl["size"]), wl.get("h", wl["size"])
     jobs = list(jobs)
     parts = [wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])] for j in jobs]
     offs = np.zeros(len(jobs) + 1, dtype=np.uint64)
@@ -134,7 +147,7 @@ def cpu_run(wl, jobs, threads):
     ops = np.concatenate(parts)
     rules = np.array([wl["rules"][j] for j in jobs], dtype=np.uint8)
     tr = None if wl["tr"] is None else np.ascontiguousarray(np.array([wl["tr"][j] for j in jobs], dtype=np.float32))
-    return oracle.batch_fill_timed(size, size, wl.get("ofmt", oracle.MATTE8), ops, offs, rules, tr, wl.get("color", (255,)), threads, 1)
+    return oracle.batch_fill_timed(W, H, wl.get("ofmt", oracle.MATTE8), ops, offs, rules, tr, wl.get("color", (255,)), threads, 1)
 
 
 def main():
@@ -143,7 +156,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256"])
+    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256", "strokes4k"])
     ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
     ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p"], help="pixel format of the rasters")
@@ -151,15 +164,15 @@ def main():
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    rgba = args.format == "rgba8p"
+    rgba = args.format == "rgba8p" or args.workload == "strokes4k"
     bpp = 4 if rgba else 1
-    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else ((1024 if rgba else 4096) if args.workload == "batch512" else 16384))
+    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else {"batch512": 1024 if rgba else 4096, "fishy256": 16384, "strokes4k": 36}[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     unit = "Gpx/s"
     fmt_name = "Rgba8p" if rgba else "Matte8"
-    metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2"}[args.workload], fmt_name)
+    metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2", "strokes4k": "stroke scenes x30 3840x2160"}[args.workload], fmt_name)
     config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": fmt_name, "pixels": PIXELS_NOTE,
               "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
 
@@ -167,13 +180,19 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        wl = make_workload(args.workload, batch, 0)
+        def oracle_outline(path):
+            import oracle
+            o = oracle.Plotter(8, 8, oracle.RGBA8P)
+            o.set_join(oracle.ROUND, 0.0)
+            return o.debug_stroke_ops(path)
+
+        wl = make_workload(args.workload, batch, 0, oracle_outline)
         if rgba:
             wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
         config["workload"] = wl["desc"].replace("Matte8", fmt_name)
-        config["raster"] = "%dx%d" % (wl["size"], wl["size"])
+        config["raster"] = "%dx%d" % (wl.get("w", wl["size"]), wl.get("h", wl["size"]))
         cores = os.cpu_count() or 1
-        per_step = max(cores, min(batch, cores * {"heptagram": 2, "batch512": 64, "fishy256": 1024}[args.workload]))
+        per_step = max(cores, min(batch, cores * {"heptagram": 2, "batch512": 64, "fishy256": 1024, "strokes4k": 1}[args.workload]))
         jobs = list(range(per_step))
         px = sum(oracle_pixels(wl, jobs))
         for _ in range(min(args.warmup, 2)):
@@ -203,13 +222,20 @@ def main():
     torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    wl = make_workload(args.workload, batch, rank)
+    def product_outline(path):
+        p = fb.Plotter(fb.Raster(8, 8, Format.Rgba8p), device=local_rank)
+        p.set_join(fb.JoinStyle.Round)
+        return p.debug_stroke_ops(path)  # device flatten + host stroker
+
+    wl = make_workload(args.workload, batch, rank, product_outline)
     if rgba:
         wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
-    size = wl["size"]
+    W, H = wl.get("w", wl["size"]), wl.get("h", wl["size"])
     config["workload"] = wl["desc"].replace("Matte8", fmt_name)
-    config["raster"] = "%dx%d" % (size, size)
-    b = Batch(size, size, Format.Rgba8p if rgba else Format.Matte8, batch, device=local_rank)
+    config["raster"] = "%dx%d" % (W, H)
+    if "outline_ms" in wl:
+        config["stroke_outline_ms_total_host"] = wl["outline_ms"]
+    b = Batch(W, H, Format.Rgba8p if rgba else Format.Matte8, batch, device=local_rank)
     colors = np.tile(np.array([200, 120, 40, 255], dtype=np.uint8), (batch, 1)) if rgba else None
     stream = torch.cuda.ExternalStream(b.stream(), device=local_rank)
     px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" else range(min(batch, 2)))
@@ -217,7 +243,11 @@ def main():
         px_step = float(sum(px_fill))
     else:  # heptagram: every fill has the same top row
         px_step = float(px_fill[0]) * batch
-    raster_bytes = size * size * bpp
+    raster_bytes = W * H * bpp
+    if args.workload == "strokes4k":  # config 3 draws over an opaque (64,128,64,255) raster (examples/stroke2.rs:20-21)
+        rect = fb.Path2D().absolute().move_to(0, 0).line_to(W, 0).line_to(W, H).line_to(0, H).close().finish()
+        b.fill(np.tile(rect, batch), np.arange(batch + 1, dtype=np.uint64) * np.uint64(len(rect)),
+               colors=np.tile(np.array([64, 128, 64, 255], dtype=np.uint8), (batch, 1))).sync()
 
     def barrier():
         if world > 1:
@@ -299,7 +329,7 @@ def main():
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----
     cpu = None
     if rank == 0 and world == 1:
-        n_cpu = args.cpu_fills or {"heptagram": 8, "batch512": 256, "fishy256": 4096}[args.workload]
+        n_cpu = args.cpu_fills or {"heptagram": 8, "batch512": 256, "fishy256": 4096, "strokes4k": 6}[args.workload]
         n_cpu = min(n_cpu, batch)
         jobs = list(range(n_cpu))
         cpu_run(wl, jobs[: max(1, n_cpu // 4)], 1)

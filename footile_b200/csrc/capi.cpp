@@ -67,7 +67,7 @@ int ftl_plotter_new_band(uint32_t width, uint32_t height, uint32_t row_begin, ui
     *out = nullptr;
     if (!fmt_ok(format)) return bad("unknown pixel format");
     if (row_begin > row_end || row_end > height) return bad("row band outside the raster");
-    if (width > 0x3FFFFFFFu || height > 0x3FFFFFFFu) return bad("raster too large");
+    if (width > (1u << 24) || height > (1u << 24)) return bad("raster too large");
     ftl_plotter *p = new ftl_plotter(device);
     p->geo.width = width; p->geo.height = height; p->geo.row_begin = row_begin; p->geo.row_end = row_end; p->geo.format = format;
     int rc = p->eng.alloc_raster(p->geo.bytes(), &p->raster);
@@ -211,7 +211,7 @@ int ftl_batch_new(uint32_t width, uint32_t height, int format, uint32_t capacity
     *out = nullptr;
     if (!fmt_ok(format)) return bad("unknown pixel format");
     if (capacity == 0) return bad("capacity is zero");
-    if (width > 0x3FFFFFFFu || height > 0x3FFFFFFFu) return bad("raster too large");
+    if (width > (1u << 24) || height > (1u << 24)) return bad("raster too large");
     ftl_batch *b = new ftl_batch(device);
     b->geo.width = width; b->geo.height = height; b->geo.row_begin = 0; b->geo.row_end = height; b->geo.format = format;
     b->capacity = capacity;

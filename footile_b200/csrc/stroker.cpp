@@ -98,7 +98,7 @@ struct Outline {
             Pt vr = normalize(pointy::right(pointy::sub(it.b, it.a)));
             Pt c = pointy::add(p.p, pointy::scale(vr, p.w / 2.0f));
             Pt ab = pointy::midpoint(it.a, it.b);
-            if (pointy::distance_sq(c, ab) <= sp.tol_sq || it.depth >= 24) line(it.b);
+            if (pointy::distance_sq(c, ab) <= sp.tol_sq || it.depth >= 16) line(it.b);  // same depth cap as the curve flattening
             else {
                 todo.push_back({c, it.b, it.depth + 1});
                 todo.push_back({it.a, c, it.depth + 1});

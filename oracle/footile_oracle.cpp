@@ -510,7 +510,7 @@ FillInfo fill_orderfree(const Fig &fig, int rule, RasterRef ras, const uint8_t *
 struct PathOp { uint32_t tag; float v[6]; };
 enum { OP_CLOSE = 0, OP_MOVE = 1, OP_LINE = 2, OP_QUAD = 3, OP_CUBIC = 4, OP_PENWIDTH = 5 };
 enum { JOIN_MITER = 0, JOIN_BEVEL = 1, JOIN_ROUND = 2 };
-const int MAX_DEPTH = 24;   // the reference recurses without bound (README.md:32-33); SURVEY A.6-12
+const int MAX_DEPTH = 16;   // the reference recurses without bound (README.md:32-33); SURVEY A.6-12.  4^16 covers any in-range curve at the minimum tolerance 0.01
 
 struct WidePt { Pt p; float w; };
 inline WidePt wmid(WidePt a, WidePt b) { return {pointy_compat::midpoint(a.p, b.p), (a.w + b.w) / 2.0f}; }  // geom.rs:31-35

@@ -529,3 +529,13 @@ def test_wide_dense_window_bins(fmt):
         o.fill(int(rule), ops, clr)
         assert g.debug_last_fill() == o.last_info()
         assert_same(g, o, "rule %d" % rule)
+
+
+def test_flatten_extreme_curves_hit_the_same_depth_cap():
+    # huge control polygons at the minimum tolerance: deep subdivision, same vertex list on both sides
+    g, o = both(64, 64, Format.Matte8, tol=0.01, vid_cap=1 << 30)
+    ops = [PathOp.Move(-30000, -30000), PathOp.Cubic(32000, -32000, 31000, 32000, -30000, 30000), PathOp.Quad(1e7, -1e7, 5, 5), PathOp.Close()]
+    gx, gs = g.debug_flatten(ops)
+    ox, os_ = o.debug_flatten(ops)
+    assert len(gx) > 1000
+    assert np.array_equal(gs, os_) and np.array_equal(gx, ox)
