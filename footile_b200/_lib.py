@@ -15,7 +15,7 @@ SYMBOLS = [
     "ftl_abi_version", "ftl_last_error", "ftl_device_count",
     "ftl_plotter_new", "ftl_plotter_new_band", "ftl_plotter_free", "ftl_width", "ftl_height",
     "ftl_set_tolerance", "ftl_set_transform", "ftl_set_join", "ftl_pen_width",
-    "ftl_fill", "ftl_stroke", "ftl_read_raster", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
+    "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
     "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
     "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream",
@@ -58,6 +58,8 @@ def lib():
         "ftl_pen_width": (f32, [vp]),
         "ftl_fill": (i32, [vp, i32, vp, sz, vp]),
         "ftl_stroke": (i32, [vp, vp, sz, vp]),
+        "ftl_fill_layers": (i32, [vp, u32, vp, vp, vp, vp]),
+        "ftl_stroke_outline": (i32, [vp, vp, sz, vp, sz, vp]),
         "ftl_read_raster": (i32, [vp, vp, sz]),
         "ftl_write_raster": (i32, [vp, vp, sz]),
         "ftl_sync": (i32, [vp]),

@@ -149,6 +149,33 @@ int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, con
     GUARD_END
 }
 
+int ftl_fill_layers(ftl_plotter *p, uint32_t n_layers, const ftl_path_op *ops, const uint64_t *op_offsets, const uint8_t *rules,
+                    const uint8_t *colors) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    if (n_layers == 0) return FTL_OK;
+    if (!op_offsets) return bad("op_offsets is null");
+    const size_t n_ops = (size_t)op_offsets[n_layers];
+    if (n_ops && !ops) return bad("ops is null");
+    std::vector<HostJob> jobs(n_layers);
+    for (uint32_t l = 0; l < n_layers; l++) {
+        HostJob &j = jobs[l];
+        if (op_offsets[l + 1] < op_offsets[l] || op_offsets[l + 1] > 0x7FFFFFFFull) return bad("op_offsets must be non-decreasing");
+        j.op_begin = (uint32_t)op_offsets[l];
+        j.op_end = (uint32_t)op_offsets[l + 1];
+        memcpy(j.e, p->e, sizeof(j.e));
+        j.tol_sq = p->tol_sq;
+        j.rule = rules ? rules[l] : FTL_NONZERO;
+        if (j.rule != FTL_NONZERO && j.rule != FTL_EVENODD) return bad("unknown fill rule");
+        if (colors) memcpy(j.color, colors + 4 * (size_t)l, 4);
+        j.raster = p->raster;
+    }
+    for (size_t i = 0; i < n_ops; i++)  // PenWidth persists on the plotter (plotter.rs:151-153)
+        if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
+    return p->eng.fill_layers(p->geo, jobs, ops, n_ops);
+    GUARD_END
+}
+
 static int stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, std::vector<ftl_path_op> *outline) {
     std::vector<float> opw;
     float final_w = stroke_widths(p->s_width, ops, n_ops, &opw);
@@ -172,6 +199,19 @@ int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8
     // self.fill(FillRule::NonZero, ops.iter(), clr) (plotter.rs:364): the outline goes through the
     // plotter's transform a second time, exactly as in the reference.
     return plot_fill(p, FTL_NONZERO, outline.data(), outline.size(), color);
+    GUARD_END
+}
+
+int ftl_stroke_outline(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap, size_t *n_out) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    if (n_ops && !ops) return bad("ops is null");
+    std::vector<ftl_path_op> outline;
+    int rc = stroke_ops(p, ops, n_ops, &outline);  // updates the persistent pen width like ftl_stroke
+    if (rc) return rc;
+    if (n_out) *n_out = outline.size();
+    if (out) memcpy(out, outline.data(), sizeof(ftl_path_op) * (outline.size() < cap ? outline.size() : cap));
+    return FTL_OK;
     GUARD_END
 }
 

@@ -129,6 +129,7 @@ struct Params {  // per-call constants, passed by value
     uint32_t win_chunks, warp_words, cta_warps;  // chunks per row window, smem words per warp, warps per CTA
     uint32_t n_win, n_bins;                      // windows per row; bins = n_tiles * n_win
     uint32_t all_direct;                         // host-proven: every job has <= DIRECT_MAX vertices (no binning needed)
+    uint32_t tile_begin, tile_end;               // tiles this launch of the tile kernel covers
 };
 
 // ---------------------------------------------------------------------------
@@ -1018,7 +1019,7 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
     const int32_t W = (int32_t)P.W, win_cells = (int32_t)(P.win_chunks * CHUNK);
     const uint32_t bpp = P.bpp;
     const uint32_t n_warps = gridDim.x * warps_per_cta;
-    for (uint32_t tile = blockIdx.x * warps_per_cta + warp; tile < P.n_tiles; tile += n_warps) {
+    for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps) {
         const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
         const JobState js = JS[j];
         int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
@@ -1211,6 +1212,7 @@ struct Engine::Impl {
     // resident job set
     Params P{};
     bool have_jobs = false;
+    bool layered = false;  // the jobs are layers of ONE raster: the tile kernel runs once per job, in order
     int smem_bytes = 0;
     // replays issued without a host round trip whose counters have not been checked yet
     uint32_t pending = 0;
@@ -1367,7 +1369,7 @@ static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typen
     return FTL_OK;
 }
 
-static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
+static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, uint32_t warp_slots, Params *P) {
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
@@ -1384,8 +1386,11 @@ static int choose_tiling(const Geometry &g, size_t max_smem, Params *P) {
         set_error("row window exceeds shared memory");
         return FTL_ERR_TOO_WIDE;
     }
-    uint32_t log2R = 3;  // band height: binning granularity only (a team keeps one row in shared memory)
+    // Band height: 8 rows per warp amortise the per-tile set-up; fewer rows per band when one launch
+    // would otherwise leave most of the GPU's warp slots empty (a single raster, a layered scene).
+    uint32_t log2R = 3;
     while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
+    while (log2R > 0 && (uint64_t)jobs_per_launch * div_up(g.rows(), 1u << log2R) < 2ull * warp_slots) log2R--;
     P->log2R = log2R; P->R = 1u << log2R;
     P->n_bands = div_up(g.rows(), P->R);
     return FTL_OK;
@@ -1409,7 +1414,7 @@ static int validate_ops(const ftl_path_op *ops, size_t n) {
     return FTL_OK;
 }
 
-int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
+int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered) {
     ENSURE_INIT();
     Impl &m = *impl_;
     {
@@ -1417,6 +1422,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         if (rc0) return rc0;
     }
     m.have_jobs = false;  // stays false if anything below fails
+    m.layered = layered;
     if (jobs.empty() || g.rows() == 0 || g.width == 0) {
         m.have_jobs = false;
         return FTL_OK;
@@ -1428,7 +1434,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     int rc = validate_ops(ops, n_ops);
     if (rc) return rc;
     Params P{};
-    rc = choose_tiling(g, m.max_smem, &P);
+    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), (uint32_t)m.n_sms * 16u, &P);
     if (rc) return rc;
     P.n_jobs = (uint32_t)jobs.size();
     P.n_ops = (uint32_t)n_ops;
@@ -1488,6 +1494,12 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
 
 int Engine::fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
     int rc = upload(g, jobs, ops, n_ops);
+    if (rc) return rc;
+    return replay();
+}
+
+int Engine::fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
+    int rc = upload(g, jobs, ops, n_ops, true);
     if (rc) return rc;
     return replay();
 }
@@ -1617,20 +1629,28 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
-    uint32_t grid = std::min<uint32_t>(div_up(P.n_tiles, P.cta_warps), (uint32_t)(m.n_sms * occ));
-    ProfSpan span{};
-    const bool prof = g_profiling.load();
-    if (prof) {
-        CK(cudaEventCreate(&span.a));
-        CK(cudaEventCreate(&span.b));
-        CK(cudaEventRecord(span.a, st));
-    }
-    tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, P, (const uint32_t *)m.toff.p,
-                                                 (const uint32_t *)m.entries.p, d_cnt); LAUNCHED();
-    if (prof) {
-        CK(cudaEventRecord(span.b, st));
-        std::lock_guard<std::mutex> lock(g_spans_mu);
-        g_spans.push_back(span);
+    // Independent rasters: one launch over all tiles.  Layers of one raster: one launch per job, in
+    // order, each over that job's tiles (the stages before ran once for all layers).
+    const uint32_t n_launches = m.layered ? P.n_jobs : 1u;
+    for (uint32_t l = 0; l < n_launches; l++) {
+        Params PL = P;
+        PL.tile_begin = m.layered ? l * P.n_bands : 0u;
+        PL.tile_end = m.layered ? (l + 1) * P.n_bands : P.n_tiles;
+        uint32_t grid = std::min<uint32_t>(div_up(PL.tile_end - PL.tile_begin, P.cta_warps), (uint32_t)(m.n_sms * occ));
+        ProfSpan span{};
+        const bool prof = g_profiling.load();
+        if (prof) {
+            CK(cudaEventCreate(&span.a));
+            CK(cudaEventCreate(&span.b));
+            CK(cudaEventRecord(span.a, st));
+        }
+        tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, PL, (const uint32_t *)m.toff.p,
+                                                     (const uint32_t *)m.entries.p, d_cnt); LAUNCHED();
+        if (prof) {
+            CK(cudaEventRecord(span.b, st));
+            std::lock_guard<std::mutex> lock(g_spans_mu);
+            g_spans.push_back(span);
+        }
     }
     CK(cudaGetLastError());
     if (!exact) {

@@ -58,8 +58,11 @@ public:
     // Fill jobs.  If `ops` is null the ops uploaded by the previous call (or by
     // upload()) are reused from HBM.
     int fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    // The jobs are layers drawn in order onto ONE raster (all jobs carry the same raster pointer):
+    // flatten / edge prep / binning run once for all layers, the tile kernel once per layer.
+    int fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
     // Upload only (device-resident replay).
-    int upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    int upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered = false);
     int replay();
 
     // Stroke-side flatten: raw f32 points with widths, per op (blocking).

@@ -121,6 +121,31 @@ class Plotter:
         _lib.check(_lib.lib().ftl_stroke(self._handle, a.ctypes.data if len(a) else None, len(a), c.ctypes.data))
         return self
 
+    def stroke_outline(self, ops):
+        """The outline ops `stroke` would fill (updates the persistent pen width like `stroke`)."""
+        a = as_ops(ops)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=OP_DTYPE)
+            n = C.c_size_t()
+            _lib.check(_lib.lib().ftl_stroke_outline(self._handle, a.ctypes.data if len(a) else None, len(a), out.ctypes.data, cap, C.byref(n)))
+            if n.value <= cap:
+                return out[: n.value].copy()
+            cap = n.value
+
+    def fill_layers(self, layers):
+        """Draw a scene in one pass: layers = [(rule, ops, color), ...] composited in order, equal to
+        calling fill() once per layer.  Use stroke_outline() to turn a stroke into a NonZero layer."""
+        arrs = [as_ops(o) for _, o, _ in layers]
+        offs = np.zeros(len(arrs) + 1, dtype=np.uint64)
+        offs[1:] = np.cumsum([len(a) for a in arrs])
+        ops = np.ascontiguousarray(np.concatenate(arrs)) if arrs else np.zeros(0, dtype=OP_DTYPE)
+        rules = np.array([int(r) for r, _, _ in layers], dtype=np.uint8)
+        colors = np.ascontiguousarray(np.array([_color(c, self._bpp) for _, _, c in layers], dtype=np.uint8).reshape(-1, 4))
+        _lib.check(_lib.lib().ftl_fill_layers(self._handle, len(layers), ops.ctypes.data if len(ops) else None, offs.ctypes.data,
+                                              rules.ctypes.data if len(layers) else None, colors.ctypes.data if len(layers) else None))
+        return self
+
     def sync(self):
         _lib.check(_lib.lib().ftl_sync(self._handle))
         return self

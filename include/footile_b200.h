@@ -97,6 +97,18 @@ int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, con
 /* Plotter::stroke(ops, clr) (plotter.rs:356-365). */
 int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
 
+/* A scene: n_layers fills drawn IN ORDER onto the plotter's raster by one pass of the device
+ * pipeline — the same pixels as n_layers ftl_fill calls (callers such as examples/fishy.rs:29-31 issue
+ * several fill/stroke calls per raster).  Layer l = ops[op_offsets[l] .. op_offsets[l+1]) with
+ * rules[l] (NonZero if NULL) and colors[4*l ..] (opaque white if NULL).  A stroke becomes a layer
+ * through ftl_stroke_outline (its outline, filled NonZero). */
+int ftl_fill_layers(ftl_plotter *p, uint32_t n_layers, const ftl_path_op *ops, const uint64_t *op_offsets,
+                    const uint8_t *rules, const uint8_t *colors);
+/* The outline Plotter::stroke would fill (stroker.rs:239-247 after plotter.rs:361-363): writes up to
+ * cap ops, returns the count in *n_out; updates the persistent pen width exactly like ftl_stroke. */
+int ftl_stroke_outline(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
+                       size_t *n_out);
+
 /* Plotter::raster() / into_raster() (plotter.rs:368-380): synchronise and copy
  * the owned rows to host memory.  nbytes must equal rows*width*bpp. */
 int ftl_read_raster(ftl_plotter *p, void *dst, size_t nbytes);

@@ -539,3 +539,42 @@ def test_flatten_extreme_curves_hit_the_same_depth_cap():
     ox, os_ = o.debug_flatten(ops)
     assert len(gx) > 1000
     assert np.array_equal(gs, os_) and np.array_equal(gx, ox)
+
+
+# ---- layered scene: many fills/strokes onto one raster in one pass ---------------------
+@pytest.mark.parametrize("fmt", [Format.Rgba8p, Format.Matte8, Format.Graya8p])
+def test_fill_layers_equals_sequential_calls(fmt):
+    rng = np.random.default_rng(21 + int(fmt))
+    w, h = 300, 200
+    bpp = {Format.Matte8: 1, Format.Graya8p: 2, Format.Rgba8p: 4}[fmt]
+    init = rng.integers(0, 256, (h, w * bpp)).astype(np.uint8)
+    g, o = both(w, h, fmt, init=init, join=JoinStyle.Round)
+    layers = []
+    for k in range(14):
+        path = random_path(rng, 250, int(rng.integers(2, 12)))
+        clr = rng.integers(0, 256, 4).astype(np.uint8)
+        clr[:3] = np.minimum(clr[:3], clr[3])
+        if fmt == Format.Graya8p:
+            clr[0] = min(clr[0], clr[1])
+        if k % 3 == 2:  # a stroke layer: its outline, filled NonZero
+            path = np.concatenate([np.array([PathOp.PenWidth(float(rng.uniform(1, 9)))], dtype=OP_DTYPE), path])
+            layers.append((FillRule.NonZero, g.stroke_outline(path), clr))
+            o.stroke(path, clr)
+        else:
+            rule = int(rng.integers(0, 2))
+            layers.append((rule, path, clr))
+            o.fill(rule, path, clr)
+    g.fill_layers(layers)
+    assert_same(g, o)
+    assert g.pen_width() == o.pen_width()
+
+
+def test_fishy_example_as_one_layered_call():  # examples/fishy.rs:29-31 in one pass
+    fish, eye = scenes.fishy_example()
+    g, o = both(128, 128, Format.Rgba8p)
+    g.fill_layers([(FillRule.NonZero, fish, (127, 96, 96, 255)), (FillRule.NonZero, g.stroke_outline(fish), (255, 208, 208, 255)),
+                   (FillRule.NonZero, g.stroke_outline(eye), (0, 0, 0, 255))])
+    o.fill(0, fish, (127, 96, 96, 255))
+    o.stroke(fish, (255, 208, 208, 255))
+    o.stroke(eye, (0, 0, 0, 255))
+    assert_same(g, o)
