@@ -1037,40 +1037,52 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
         const bool one_list = !GENERAL || direct || P.n_win == 1;
         uint32_t e0 = direct ? js.vtx_begin : tile_off[tile * P.n_win];
         uint32_t ne = direct ? n_slots : tile_off[tile * P.n_win + 1] - e0;
+        // Row groups: with few edges the 32 lanes are (row, edge) pairs of 4 (or 2) consecutive rows, so
+        // the per-(edge,row) set-up of several rows costs one pass; each row then scatters with its own lanes.
+        const uint32_t gl = !one_list ? 5u : (ne <= 8 ? 3u : (ne <= 16 ? 4u : 5u));
+        const uint32_t my_e = lane & ((1u << gl) - 1u), my_r = lane >> gl;
+        const int32_t rows_per_pass = (int32_t)(32u >> gl);
         EdgeRec mine;
         mine.flags = 0;
-        if (one_list && lane < ne) mine = E[direct ? e0 + lane : entries[e0 + lane]];
-        for (int32_t ry = row0; ry < row_hi; ry++) {
+        if (one_list && my_e < ne) mine = E[direct ? e0 + my_e : entries[e0 + my_e]];
+        for (int32_t ry_base = row0; ry_base < row_hi; ry_base += rows_per_pass) {
             EdgeRowState st;
             st.cov = 0;
-            if ((mine.flags & 1u) && ry >= mine.ry0 && ry <= mine.ry1) st = edge_row_setup(mine, ry, W, 0);
-            uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
-            int32_t carry = 0;
-            uint32_t bin = tile * P.n_win;
-            for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++) {
-                const int32_t win_hi = min(W, win_lo + win_cells);
-                // ---- (c) scatter: one lane per edge crossing this row ----
-                uint32_t first = 32;
-                if (one_list) edge_row_scatter(st, win_lo, win_hi, cells, mask);
-                else {  // wide raster with many edges: each window has its own bin
-                    e0 = tile_off[bin];
-                    ne = tile_off[bin + 1] - e0;
-                    first = 0;
-                }
-                for (uint32_t i = lane + first; i < ne; i += 32) {
-                    const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
-                    if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
-                        EdgeRowState s2 = edge_row_setup(e, ry, W, win_lo);
-                        edge_row_scatter(s2, win_lo, win_hi, cells, mask);
+            {
+                const int32_t my_ry = ry_base + (int32_t)my_r;
+                if ((mine.flags & 1u) && my_ry < row_hi && my_ry >= mine.ry0 && my_ry <= mine.ry1) st = edge_row_setup(mine, my_ry, W, 0);
+            }
+            for (int32_t rr = 0; rr < rows_per_pass && ry_base + rr < row_hi; rr++) {
+                const int32_t ry = ry_base + rr;
+                uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
+                int32_t carry = 0;
+                uint32_t bin = tile * P.n_win;
+                for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++) {
+                    const int32_t win_hi = min(W, win_lo + win_cells);
+                    // ---- (c) scatter: one lane per edge crossing this row ----
+                    uint32_t first = 32;
+                    if (one_list) {
+                        if ((int32_t)my_r == rr) edge_row_scatter(st, win_lo, win_hi, cells, mask);
+                    } else {  // wide raster with many edges: each window has its own bin
+                        e0 = tile_off[bin];
+                        ne = tile_off[bin + 1] - e0;
+                        first = 0;
                     }
+                    for (uint32_t i = lane + first; i < ne; i += 32) {
+                        const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
+                        if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
+                            EdgeRowState s2 = edge_row_setup(e, ry, W, win_lo);
+                            edge_row_scatter(s2, win_lo, win_hi, cells, mask);
+                        }
+                    }
+                    __syncwarp();
+                    // ---- (d) resolve ----
+                    const uint32_t nch = ((uint32_t)(win_hi - win_lo) + CHUNK - 1) / CHUNK;
+                    uint8_t *dwin = dst + (size_t)win_lo * bpp;
+                    if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                    else resolve_row<FMT, false, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                    __syncwarp();
                 }
-                __syncwarp();
-                // ---- (d) resolve ----
-                const uint32_t nch = ((uint32_t)(win_hi - win_lo) + CHUNK - 1) / CHUNK;
-                uint8_t *dwin = dst + (size_t)win_lo * bpp;
-                if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
-                else resolve_row<FMT, false, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
-                __syncwarp();
             }
         }
     }
