@@ -150,13 +150,109 @@ def cpu_run(wl, jobs, threads):
     return oracle.batch_fill_timed(W, H, wl.get("ofmt", oracle.MATTE8), ops, offs, rules, tr, wl.get("color", (255,)), threads, 1)
 
 
+def bigraster(args, rank, local_rank, world):
+    """BASELINE.json configs[4]: ONE 32768x32768 Matte8 raster, 160 000 closed 64-gons (10.24 M edges) in one fill,
+    rows split into `world` bands, one band per GPU, no collective (every rank gets the same ops and recomputes
+    (dir, top_row)).  Strong scaling: the work is fixed, `value` = pixels of the whole raster / slowest rank's time.
+    The reference arm times the order-free oracle on a bounded sample of 16-row stripes, one per host thread."""
+    from footile_b200 import scenes
+    size, polys = 32768, 160000
+    metric, unit = "Gpx/s composited (one 32768^2 Matte8 raster, 10.24 M edges, row bands)", "Gpx/s"
+    config = {"workload": "160 000 closed 64-gon sub-figures (seed 0xB160000^i) in ONE EvenOdd fill of a 32768x32768 Matte8 raster",
+              "raster": "32768x32768", "format": "Matte8", "bands": world, "pixels": PIXELS_NOTE,
+              "l2": "1 GiB raster and 164 MB of edges per fill: far beyond the 126 MB L2"}
+    ops = scenes.random_polygons(0, polys, vertices=64, size=size, extent=2048)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        import oracle
+        cores = os.cpu_count() or 1
+        rows_each = 16
+        rng = np.random.default_rng(5)
+        starts = [int(r) for r in rng.integers(0, size - rows_each, cores)]
+
+        def stripe(r0):
+            o = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True)
+            o.set_rows(r0, r0 + rows_each)
+            o.fill(1, ops, (255,))
+
+        ts = []
+        for _ in range(max(1, min(args.steps, 3))):
+            t0 = time.perf_counter()
+            ths = [threading.Thread(target=stripe, args=(r0,)) for r0 in starts]
+            for th in ths:
+                th.start()
+            for th in ths:
+                th.join()
+            ts.append(time.perf_counter() - t0)
+        t = min(ts)
+        v = size * rows_each * cores / t / 1e9
+        sample = "%d stripes of %d rows (order-free oracle, u32 vertex ids), one per thread on %d threads; every stripe walks all 10.24 M edges" % (cores, rows_each, cores)
+        print(json.dumps({"impl": "reference", "metric": metric, "value": v, "unit": unit, "n_gpus": args.gpus, "steps": len(ts), "warmup": 0,
+                          "ms_per_step": 1e3 * t, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32 fixed-point 16.16 / u8",
+                          "data": "synthetic", "config": config, "cpu_baseline": {"value": v, "unit": unit, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": v, "unit": unit, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import torch.distributed as dist
+    import footile_b200 as fb
+    from footile_b200 import Format, sharding
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    r0, r1 = sharding.band_rows(size, rank, world)
+
+    p = fb.Plotter.with_clear(size, size, Format.Matte8, device=local_rank, rows=(r0, r1))
+    for _ in range(max(1, min(args.warmup, 3))):
+        p.fill(1, ops, (255,))
+    p.sync()
+    if world > 1:
+        dist.barrier()
+    fb.set_profiling(True)
+    fb.tile_kernel_time(reset=True)
+    l0 = fb.launch_count()
+    steps = max(1, args.steps)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        p.fill(1, ops, (255,))
+    p.sync()
+    dt = sharding.max_over_ranks(time.perf_counter() - t0, device="cuda" if world > 1 else None)
+    launches = fb.launch_count() - l0
+    tile_ms, tile_n = fb.tile_kernel_time(reset=True)
+    fb.set_profiling(False)
+    top = p.debug_last_fill()["top_row"]
+    px = size * (size - max(top, 0))
+    value = px * steps / dt / 1e9
+    pinned = torch.empty((r1 - r0) * size, dtype=torch.uint8, pin_memory=True)
+    t0 = time.perf_counter()
+    for _ in range(2):
+        p.fill(1, ops, (255,))
+        fb._lib.check(fb._lib.lib().ftl_read_raster(p._handle, pinned.data_ptr(), pinned.numel()))
+    e2e_dt = sharding.max_over_ranks((time.perf_counter() - t0) / 2, device="cuda" if world > 1 else None)
+    peak, peak_kind = peaks()
+    if rank == 0:
+        per_launch_ms = tile_ms / max(tile_n, 1)
+        ach = px / world / (per_launch_ms * 1e-3) / 1e9
+        print(json.dumps({"metric": metric, "value": value, "unit": unit, "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / steps,
+                          "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "i32 fixed-point 16.16 / u8", "data": "synthetic",
+                          "config": config, "edges_per_s": polys * 64 * steps / dt,
+                          "timing": "host clock around fill+sync, max over ranks: every step includes the H2D copy of 291 MB of ops (the Plotter API re-sends them)",
+                          "e2e": {"value": px / e2e_dt / 1e9, "unit": unit, "h2d_bytes_per_step": int(ops.nbytes), "d2h_bytes_per_step": int((r1 - r0) * size), "ms_per_step": 1e3 * e2e_dt},
+                          "gpu_launches": int(launches),
+                          "roofline": {"kernel": "raster_tiles", "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "peak_kind": peak_kind,
+                                       "traffic": None, "avg_launch_ms": per_launch_ms, "note": "scatter/issue-bound: ~200 (edge,row) items per edge"},
+                          "cpu_baseline": None}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256", "strokes4k"])
+    ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256", "strokes4k", "bigraster"])
     ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
     ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p"], help="pixel format of the rasters")
@@ -166,15 +262,19 @@ def main():
         args.warmup = 3
     rgba = args.format == "rgba8p" or args.workload == "strokes4k"
     bpp = 4 if rgba else 1
-    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else {"batch512": 1024 if rgba else 4096, "fishy256": 16384, "strokes4k": 36}[args.workload])
+    batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else {"batch512": 1024 if rgba else 4096, "fishy256": 16384, "strokes4k": 36, "bigraster": 1}[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     unit = "Gpx/s"
     fmt_name = "Rgba8p" if rgba else "Matte8"
-    metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2", "strokes4k": "stroke scenes x30 3840x2160"}[args.workload], fmt_name)
+    metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2", "strokes4k": "stroke scenes x30 3840x2160", "bigraster": "one 32768^2 raster"}[args.workload], fmt_name)
     config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": fmt_name, "pixels": PIXELS_NOTE,
               "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
+
+    # ---------------- config 5: one huge raster split into row bands (strong scaling) ----------------
+    if args.workload == "bigraster":
+        return bigraster(args, rank, local_rank, world)
 
     # ---------------- reference arm: the oracle on all host cores ----------------
     if args.impl == "reference":

@@ -68,15 +68,25 @@ class Plotter:
     """
 
     def __init__(self, raster, device=0, rows=None):
-        self.fmt = raster.fmt
-        self._w, self._h = raster.width, raster.height
-        self._rows = (0, raster.height) if rows is None else (int(rows[0]), int(rows[1]))
+        self._setup(raster.width, raster.height, raster.fmt, device, rows, raster.pixels)
+
+    @classmethod
+    def with_clear(cls, width, height, fmt=Format.Matte8, device=0, rows=None):
+        """Plotter over a cleared raster (Raster::with_clear) without materialising it on the host."""
+        self = cls.__new__(cls)
+        self._setup(width, height, Format(fmt), device, rows, None)
+        return self
+
+    def _setup(self, width, height, fmt, device, rows, pixels):
+        self.fmt = fmt
+        self._w, self._h = int(width), int(height)
+        self._rows = (0, self._h) if rows is None else (int(rows[0]), int(rows[1]))
         self._bpp = BPP[self.fmt]
         self._handle = C.c_void_p()
-        L = _lib.lib()
-        band = np.ascontiguousarray(raster.pixels[self._rows[0]: self._rows[1]])
-        _lib.check(L.ftl_plotter_new_band(self._w, self._h, self._rows[0], self._rows[1], int(self.fmt),
-                                          band.ctypes.data if band.size else None, device, C.byref(self._handle)))
+        band = None if pixels is None else np.ascontiguousarray(pixels[self._rows[0]: self._rows[1]])
+        _lib.check(_lib.lib().ftl_plotter_new_band(self._w, self._h, self._rows[0], self._rows[1], int(self.fmt),
+                                                   band.ctypes.data if band is not None and band.size else None, device,
+                                                   C.byref(self._handle)))
 
     def __del__(self):
         h = getattr(self, "_handle", None)

@@ -29,7 +29,7 @@ def main():
     t0 = time.time()
     ops = scenes.random_polygons(0, args.polys, vertices=64, size=size, extent=2048)
     t_gen = time.time() - t0
-    g = Plotter(_Lazy(size, size, 0, size))
+    g = Plotter.with_clear(size, size, Format.Matte8)
     g.fill(args.rule, ops, (255,)).sync()  # warm-up: sizes the scratch buffers
     times = []
     for _ in range(3):
@@ -63,7 +63,7 @@ def main():
     band_times = []
     for k in range(args.bands):
         r0, r1 = k * size // args.bands, (k + 1) * size // args.bands
-        gb = Plotter(_Lazy(size, size, r0, r1), rows=(r0, r1))
+        gb = Plotter.with_clear(size, size, Format.Matte8, rows=(r0, r1))
         gb.fill(args.rule, ops, (255,)).sync()
         t0 = time.time()
         gb.fill(args.rule, ops, (255,)).sync()
@@ -74,26 +74,6 @@ def main():
     out["bands"] = {"n": args.bands, "mismatching": band_bad, "fill_s_each": band_times}
     print(json.dumps(out))
     return 0 if bad == 0 and band_bad == 0 else 1
-
-
-class _Lazy:
-    """A clear raster of which only rows [r0, r1) are materialised (avoids a 1 GiB host allocation per band)."""
-
-    def __init__(self, w, h, r0, r1):
-        self.width, self.height, self.fmt = w, h, Format.Matte8
-        self._r0, self._r1 = r0, r1
-
-    @property
-    def pixels(self):
-        return _Rows(self.width, self._r0, self._r1)
-
-
-class _Rows:
-    def __init__(self, w, r0, r1):
-        self._w, self._r0, self._r1 = w, r0, r1
-
-    def __getitem__(self, sl):
-        return np.zeros((self._r1 - self._r0, self._w), dtype=np.uint8)
 
 
 if __name__ == "__main__":
