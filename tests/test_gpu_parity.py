@@ -578,3 +578,39 @@ def test_fishy_example_as_one_layered_call():  # examples/fishy.rs:29-31 in one 
     o.stroke(fish, (255, 208, 208, 255))
     o.stroke(eye, (0, 0, 0, 255))
     assert_same(g, o)
+
+
+# ---- size-independent properties at BASELINE.json's full sizes ------------------------------------------
+def test_property_integer_translation_shifts_the_matte():
+    # a figure moved by whole pixels yields the same matte moved by whole pixels; coordinates are multiples of
+    # 1/8 px so that both the figure and its translate are exact in f32 and in Fixed
+    size, dx, dy = 4096, 37, 101
+    rng = np.random.default_rng(4)
+    pts = np.round(rng.uniform(300, 3600, (11, 2)) * 8) / 8
+    a = Plotter.with_clear(size, size, Format.Matte8).fill(FillRule.EvenOdd, poly([tuple(p) for p in pts]), (255,)).raster().pixels
+    b = Plotter.with_clear(size, size, Format.Matte8).fill(FillRule.EvenOdd, poly([(p[0] + dx, p[1] + dy) for p in pts]), (255,)).raster().pixels
+    assert a.any()
+    top = int(pts[:, 1].min())
+    assert np.array_equal(a[top: size - dy, : size - dx], b[top + dy:, dx:])
+
+
+def test_property_matte_fill_is_idempotent_and_deterministic_full_batch():
+    # config 4 at one step of its full size: 4096 paths; refilling changes nothing; two batches agree; a seeded
+    # sample of rasters equals the oracle and the device checksums equal the host checksums of those rasters
+    n = 4096
+    ops, offs, rules = scenes.random_curve_paths(0, n)
+    b1 = Batch(512, 512, Format.Matte8, n)
+    b1.fill(ops, offs, rules=rules)
+    s1 = b1.checksums()
+    b1.fill(ops, offs, rules=rules)
+    assert np.array_equal(s1, b1.checksums())
+    b2 = Batch(512, 512, Format.Matte8, n)
+    b2.fill(ops, offs, rules=rules)
+    assert np.array_equal(s1, b2.checksums())
+    assert len(np.unique(s1)) > n // 2
+    for j in np.random.default_rng(0).integers(0, n, 12):
+        o = oracle.Plotter(512, 512, oracle.MATTE8)
+        o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
+        exp = o.raster()
+        assert np.array_equal(b1.read(int(j), 1)[0], exp)
+        assert int(s1[j]) == fnv_expected(exp)
