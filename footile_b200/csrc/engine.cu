@@ -1381,7 +1381,7 @@ static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typen
     return FTL_OK;
 }
 
-static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, uint32_t warp_slots, Params *P) {
+static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, uint32_t warp_slots, bool all_direct, Params *P) {
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
@@ -1398,11 +1398,14 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
         set_error("row window exceeds shared memory");
         return FTL_ERR_TOO_WIDE;
     }
-    // Band height: 8 rows per warp amortise the per-tile set-up; fewer rows per band when one launch
-    // would otherwise leave most of the GPU's warp slots empty (a single raster, a layered scene).
-    uint32_t log2R = 3;
+    // Band height: 8 rows per warp amortise the per-tile set-up when every tile scans its job's own few
+    // edges; binned jobs do better with 4 (fewer edges per bin to test against each row); fewer rows per
+    // band when one launch would otherwise leave most of the GPU's warp slots empty (a single raster, a
+    // layer of a scene).
+    uint32_t log2R = all_direct ? 3 : 2;
     while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
     while (log2R > 0 && (uint64_t)jobs_per_launch * div_up(g.rows(), 1u << log2R) < 2ull * warp_slots) log2R--;
+    if (const char *ev = getenv("FTL_LOG2R")) log2R = (uint32_t)std::min(5, std::max(0, atoi(ev)));  // tuning knob
     P->log2R = log2R; P->R = 1u << log2R;
     P->n_bands = div_up(g.rows(), P->R);
     return FTL_OK;
@@ -1446,7 +1449,15 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     int rc = validate_ops(ops, n_ops);
     if (rc) return rc;
     Params P{};
-    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), (uint32_t)m.n_sms * 16u, &P);
+    // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
+    P.all_direct = 1;
+    for (const HostJob &h : jobs) {
+        if (h.op_end - h.op_begin > DIRECT_MAX) P.all_direct = 0;
+        for (uint32_t i = h.op_begin; i < h.op_end && P.all_direct; i++)
+            if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) P.all_direct = 0;
+        if (!P.all_direct) break;
+    }
+    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), (uint32_t)m.n_sms * 16u, P.all_direct != 0, &P);
     if (rc) return rc;
     P.n_jobs = (uint32_t)jobs.size();
     P.n_ops = (uint32_t)n_ops;
@@ -1461,14 +1472,6 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         return FTL_ERR_INVALID;
     }
     P.n_bins = (uint32_t)(nt * P.n_win);
-    // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
-    P.all_direct = 1;
-    for (const HostJob &h : jobs) {
-        if (h.op_end - h.op_begin > DIRECT_MAX) P.all_direct = 0;
-        for (uint32_t i = h.op_begin; i < h.op_end && P.all_direct; i++)
-            if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) P.all_direct = 0;
-        if (!P.all_direct) break;
-    }
     // stage + upload ops and job descriptors
     size_t ops_bytes = n_ops * sizeof(ftl_path_op), jobs_bytes = jobs.size() * sizeof(JobDesc);
     if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
