@@ -659,8 +659,7 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
 // q ^ ((q >> 3) & 3).
 constexpr uint32_t CHUNK = 512;
 __device__ __forceinline__ uint32_t cell_phys(uint32_t c) {
-    uint32_t q = c >> 2;
-    return ((q ^ ((q >> 3) & 3u)) << 2) | (c & 3u);
+    return c ^ ((c >> 3) & 0xCu);  // bits 3:2 (the quad within 4 quads) ^= bits 6:5
 }
 
 // Signed coverage of one edge on one raster row.  Closed form of
@@ -878,6 +877,15 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
     }
 }
 
+// One step of an inclusive add-scan over segments of WIDTH lanes: v += the value `d` lanes below,
+// predicated by the shuffle's own in-range result (no lane compare).
+template <int WIDTH>
+__device__ __forceinline__ void scan_step(int32_t &v, int d) {
+    asm volatile("{ .reg .pred p; .reg .s32 t; shfl.sync.up.b32 t|p, %0, %1, %2, 0xffffffff; @p add.s32 %0, %0, t; }"
+                 : "+r"(v)
+                 : "r"(d), "r"((32 - WIDTH) << 8));
+}
+
 // Resolve chunks [c_begin, c_end) of one row held in shared memory, by one
 // warp.  Per 512-cell chunk each lane owns 16 consecutive cells: it reads them
 // (4 LDS.128), zeroes them, scans them serially, one 5-step shuffle scan
@@ -903,13 +911,22 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     const uint32_t dense = __ballot_sync(0xFFFFFFFFu, mym != 0);
     uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);  // alpha of an edge-free span at the current sum
     uint4 *out4 = reinterpret_cast<uint4 *>(dst) + lane;
-    for (uint32_t i = 0; i < n; i++) {
-        const uint32_t ch = c_begin + i;
-        const uint32_t x = ch * CHUNK + lane * 16;
-        const bool full = (ch + 1) * CHUNK <= W;
-        if (!((dense >> i) & 1u)) {
-            if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(q, q, q, q);
-            else if (FMT == FTL_RGBA8P && ALIGNED && full && (q == 0 || (q == 0xFFFFFFFFu && clr_a == 255))) {
+    const uint32_t full_end = min(c_end, W / CHUNK);  // chunks below this index lie entirely inside the row
+    // Walk the chunks that hold edges (bits of `dense`); the edge-free chunks between them are runs of
+    // one constant alpha.
+    uint32_t pend = dense, ch = c_begin;
+    for (;;) {
+        const uint32_t nxt = c_begin + (pend ? (uint32_t)__ffs((int)pend) - 1u : n);
+        if (FMT == FTL_MATTE8 && ALIGNED) {
+            const uint32_t stop = min(nxt, full_end);
+            const uint4 v = make_uint4(q, q, q, q);
+#pragma unroll 1
+            for (; ch < stop; ch++) out4[ch * 32] = v;
+        }
+#pragma unroll 1
+        for (; ch < nxt; ch++) {
+            const uint32_t x = ch * CHUNK + lane * 16;
+            if (FMT == FTL_RGBA8P && ALIGNED && ch < full_end && (q == 0 || (q == 0xFFFFFFFFu && clr_a == 255))) {
                 // edge-free chunk of one alpha: 512 pixels = 2 KiB, consecutive lanes on consecutive 16 bytes
                 uint4 *p = reinterpret_cast<uint4 *>(dst) + ch * 128 + lane;
                 if (q == 0) {
@@ -925,9 +942,13 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
                     for (int j = 0; j < 4; j++) p[32 * j] = make_uint4(c, c, c, c);
                 }
             } else emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
-            continue;
         }
-        const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, i);
+        if (pend == 0) break;
+        pend &= pend - 1;
+        const uint32_t cur = ch++;  // == nxt: the chunk to resolve
+        const uint32_t x = cur * CHUNK + lane * 16;
+        const bool full = cur < full_end;
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, mym, cur - c_begin);
         if (__popc(m) <= 4) {
             // Sparse chunk: each touched 16-cell group is scanned by a half-warp (one cell per lane,
             // two groups per step); the other groups take the constant alpha of the sum reaching them.
@@ -941,24 +962,21 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
                 const int32_t gg = half ? g2 : g;
                 int32_t inc = 0;
                 if (gg >= 0) {
-                    int32_t *p = row + ch * CHUNK + (((uint32_t)gg * 4 + ((l16 >> 2) ^ (((uint32_t)gg >> 1) & 3u))) << 2) + (l16 & 3u);
+                    int32_t *p = row + cur * CHUNK + (((uint32_t)gg * 4 + ((l16 >> 2) ^ (((uint32_t)gg >> 1) & 3u))) << 2) + (l16 & 3u);
                     inc = *p;
                     *p = 0;
                 }
 #pragma unroll
-                for (int d = 1; d < 16; d <<= 1) {
-                    int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d, 16);
-                    if (l16 >= (uint32_t)d) inc += o;
-                }
+                for (int d = 1; d < 16; d <<= 1) scan_step<16>(inc, d);
                 const int32_t t_lo = __shfl_sync(0xFFFFFFFFu, inc, 15), t_hi = __shfl_sync(0xFFFFFFFFu, inc, 31);
-                if (gg >= 0) emit1<FMT>(dst, ch * CHUNK + (uint32_t)gg * 16 + l16, W, rule_alpha<EVEN_ODD>(carry + inc + (half ? t_lo : 0)), color, clr_a);
+                if (gg >= 0) emit1<FMT>(dst, cur * CHUNK + (uint32_t)gg * 16 + l16, W, rule_alpha<EVEN_ODD>(carry + inc + (half ? t_lo : 0)), color, clr_a);
                 if ((int32_t)lane > g) mybase += t_lo;
                 if (g2 >= 0 && (int32_t)lane > g2) mybase += t_hi;
                 carry += t_lo + t_hi;
             }
             if (!((m >> lane) & 1u)) {
                 const uint32_t qq = quad_alpha<EVEN_ODD>(0, 0, 0, 0, mybase);
-                if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(qq, qq, qq, qq);
+                if (FMT == FTL_MATTE8 && ALIGNED && full) out4[cur * 32] = make_uint4(qq, qq, qq, qq);
                 else emit16<FMT, ALIGNED>(dst, x, W, qq, qq, qq, qq, color, clr_a);
             }
             q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
@@ -966,7 +984,7 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         }
         int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
         if ((m >> lane) & 1u) {
-            int32_t *base = row + ch * CHUNK + lane * 16;
+            int32_t *base = row + cur * CHUNK + lane * 16;
             int4 *p0 = reinterpret_cast<int4 *>(base + ((0 ^ sw) << 2)), *p1 = reinterpret_cast<int4 *>(base + ((1 ^ sw) << 2));
             int4 *p2 = reinterpret_cast<int4 *>(base + ((2 ^ sw) << 2)), *p3 = reinterpret_cast<int4 *>(base + ((3 ^ sw) << 2));
             v0 = *p0; v1 = *p1; v2 = *p2; v3 = *p3;
@@ -981,17 +999,14 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         const int32_t o1 = v0.w, o2 = o1 + v1.w, o3 = o2 + v2.w, tot = o3 + v3.w;
         int32_t inc = tot;
 #pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            int32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if (lane >= d) inc += o;
-        }
+        for (int d = 1; d < 32; d <<= 1) scan_step<32>(inc, d);
         const int32_t b0 = carry + inc - tot;
         carry += __shfl_sync(0xFFFFFFFFu, inc, 31);
         const uint32_t a0 = quad_alpha<EVEN_ODD>(v0.x, v0.y, v0.z, v0.w, b0);
         const uint32_t a1 = quad_alpha<EVEN_ODD>(v1.x, v1.y, v1.z, v1.w, b0 + o1);
         const uint32_t a2 = quad_alpha<EVEN_ODD>(v2.x, v2.y, v2.z, v2.w, b0 + o2);
         const uint32_t a3 = quad_alpha<EVEN_ODD>(v3.x, v3.y, v3.z, v3.w, b0 + o3);
-        if (FMT == FTL_MATTE8 && ALIGNED && full) out4[ch * 32] = make_uint4(a0, a1, a2, a3);
+        if (FMT == FTL_MATTE8 && ALIGNED && full) out4[cur * 32] = make_uint4(a0, a1, a2, a3);
         else emit16<FMT, ALIGNED>(dst, x, W, a0, a1, a2, a3, color, clr_a);
         q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);
     }
@@ -1006,7 +1021,7 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED, bool GENERAL>
-__global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
@@ -1045,6 +1060,8 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
         EdgeRec mine;
         mine.flags = 0;
         if (one_list && my_e < ne) mine = E[direct ? e0 + my_e : entries[e0 + my_e]];
+        uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(row0 - (int32_t)P.row_begin) * P.pitch;
+        const uint32_t win_bytes = (uint32_t)win_cells * bpp;
         for (int32_t ry_base = row0; ry_base < row_hi; ry_base += rows_per_pass) {
             EdgeRowState st;
             st.cov = 0;
@@ -1052,12 +1069,13 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
                 const int32_t my_ry = ry_base + (int32_t)my_r;
                 if ((mine.flags & 1u) && my_ry < row_hi && my_ry >= mine.ry0 && my_ry <= mine.ry1) st = edge_row_setup(mine, my_ry, W, 0);
             }
-            for (int32_t rr = 0; rr < rows_per_pass && ry_base + rr < row_hi; rr++) {
+            const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
+            for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
                 const int32_t ry = ry_base + rr;
-                uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(ry - (int32_t)P.row_begin) * P.pitch;
                 int32_t carry = 0;
                 uint32_t bin = tile * P.n_win;
-                for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++) {
+                uint8_t *dwin = dst;
+                for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++, dwin += win_bytes) {
                     const int32_t win_hi = min(W, win_lo + win_cells);
                     // ---- (c) scatter: one lane per edge crossing this row ----
                     uint32_t first = 32;
@@ -1078,7 +1096,6 @@ __global__ void __launch_bounds__(128, 4) raster_tiles(const EdgeRec *__restrict
                     __syncwarp();
                     // ---- (d) resolve ----
                     const uint32_t nch = ((uint32_t)(win_hi - win_lo) + CHUNK - 1) / CHUNK;
-                    uint8_t *dwin = dst + (size_t)win_lo * bpp;
                     if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
                     else resolve_row<FMT, false, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
                     __syncwarp();
