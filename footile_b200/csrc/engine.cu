@@ -1013,6 +1013,142 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     carry_io = carry;
 }
 
+// ---------------------------------------------------------------------------
+// Analytic rows: tiles with at most 8 edges and no shared-memory scatter.
+// ---------------------------------------------------------------------------
+// The sum the reference accumulates at pixel x of a row is  sum_e ed_e * X_e(x)  (mod 2^16), where X_e
+// is edge e's running coverage (Edge::scan_area, fig.rs:285-302: the prefix of the deltas it adds):
+// 0 left of the edge's span, min(pixel_cov(min(first + k*step, ONE)), cov) on the span's k-th cell and
+// cov right of it.  With at most 8 edges the lanes of a warp are (row, edge) pairs of 4 rows: when the
+// spans of a row lie in distinct 16-pixel groups, a lane knows the constant sum left of its span from
+// an 8-lane exchange (`base`), builds the 16 alpha bytes of its group(s) in registers and stores them,
+// and the warp stores the constant spans between the edges cooperatively.  Rows where two spans share
+// a group, or a span covers more than two groups, are returned in a mask and take the shared-memory
+// path.  Nothing here touches shared memory.
+__device__ __forceinline__ uint32_t rule_alpha_rt(int32_t sum, bool even_odd) {
+    int32_t s = (int32_t)(int16_t)sum;
+    int32_t c = (s & 0xFF) - (s & 0x100);
+    c = c < 0 ? -c : c;
+    s = even_odd ? c : s;
+    return (uint32_t)min(max(s, 0), 255);
+}
+
+template <int FMT>
+__device__ __forceinline__ void fill_span(uint8_t *drow, uint32_t lo, uint32_t hi, uint32_t q, uint32_t W, uint32_t color, uint32_t clr_a) {
+    const uint32_t lane = threadIdx.x & 31;
+    if (FMT == FTL_MATTE8) {
+        uint4 *p = reinterpret_cast<uint4 *>(drow);
+        const uint4 v = make_uint4(q, q, q, q);
+#pragma unroll 1
+        for (uint32_t g = lo + lane; g < hi; g += 32) p[g] = v;
+    } else {
+#pragma unroll 1
+        for (uint32_t g = lo + lane; g < hi; g += 32) emit16<FMT, true>(drow, g * 16, W, q, q, q, q, color, clr_a);
+    }
+}
+
+// Rows ry_base .. ry_base + n_rows - 1 (n_rows <= 4) of one tile; `st` is this lane's (row my_r, edge)
+// state from edge_row_setup with win_lo = 0 (cov == 0: nothing on this row).  `dst` is the first row.
+// Returns the rows (bit r) that were NOT drawn and need the shared-memory path.
+template <int FMT>
+__device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32_t my_r, int32_t n_rows, int32_t W, uint8_t *dst, uint32_t pitch,
+                                                  bool even_odd, uint32_t color) {
+    const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    const uint32_t ngroups = (uint32_t)W >> 4;
+    const bool active = st.cov > 0 && (int32_t)my_r < n_rows;
+    // extent of the span: cells [st.c, c_last]
+    int32_t c_last = 0;
+    bool conflict = false;
+    if (active) {
+        int32_t xc = st.xc, c = st.c;
+        for (int j = 0;; j++) {
+            if (pixel_cov(xc) >= st.cov || c >= W - 1) break;
+            if (j >= 31) {
+                conflict = true;
+                break;
+            }
+            c++;
+            xc += st.step;
+            if (xc > FX_ONE) xc = FX_ONE;
+        }
+        c_last = c;
+    }
+    const uint32_t ga = active ? (uint32_t)st.c >> 4 : 0xFFFFu, gb = active ? (uint32_t)c_last >> 4 : 0u;
+    if (active && gb - ga > 1u) conflict = true;
+    const int32_t wgt = active ? st.ed * st.cov : 0;
+    // 8-lane exchange: constant sum left of the span, the group where the next span starts, overlaps
+    const uint32_t packed = ga | (gb << 16);
+    int32_t base = 0;
+    uint32_t next_ga = ngroups, min_ga = ga;
+#pragma unroll
+    for (int d = 1; d < 8; d++) {
+        const uint32_t o = __shfl_xor_sync(0xFFFFFFFFu, packed, d);
+        const int32_t ow = __shfl_xor_sync(0xFFFFFFFFu, wgt, d);
+        const uint32_t oga = o & 0xFFFFu, ogb = o >> 16;
+        if (ogb < ga) base += ow;
+        if (oga <= gb && ogb >= ga) conflict = true;
+        if (oga > gb) next_ga = min(next_ga, oga);
+        min_ga = min(min_ga, oga);
+    }
+    const uint32_t conf_bal = __ballot_sync(0xFFFFFFFFu, conflict);
+    uint32_t redo = 0;  // rows for the shared-memory path
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+        if (r < n_rows && ((conf_bal >> (8 * r)) & 0xFFu)) redo |= 1u << r;
+    const bool row_ok = (int32_t)my_r < n_rows && !((redo >> my_r) & 1u);
+    uint8_t *drow = dst + (size_t)my_r * pitch;
+    const uint32_t after = rule_alpha_rt(base + wgt, even_odd) * 0x01010101u;
+    // ---- the groups holding the span ----
+    if (active && row_ok) {
+        const uint32_t before = rule_alpha_rt(base, even_odd) * 0x01010101u;
+        // group ga: `before` left of the span start, `after` right of it, span cells inserted below
+        const uint32_t p0 = (uint32_t)st.c & 15u;
+        uint32_t a[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; j++) {
+            const uint32_t nb = p0 > 4 * j ? min(p0 - 4 * j, 4u) : 0u;  // bytes of word j left of the span
+            const uint32_t m = nb >= 4 ? 0xFFFFFFFFu : ((1u << (8 * nb)) - 1u);
+            a[j] = (before & m) | (after & ~m);
+        }
+        int32_t xc = st.xc, c = st.c;
+        uint32_t g = ga;
+        for (;;) {
+            int32_t xk = pixel_cov(xc);
+            if (xk > st.cov) xk = st.cov;
+            const uint32_t al = rule_alpha_rt(base + st.ed * xk, even_odd);
+            const uint32_t sh = ((uint32_t)c & 3u) * 8u, m = 0xFFu << sh, v = al << sh, wj = ((uint32_t)c >> 2) & 3u;
+#pragma unroll
+            for (uint32_t j = 0; j < 4; j++)
+                if (wj == j) a[j] = (a[j] & ~m) | v;
+            if (xk >= st.cov || c >= W - 1) break;
+            c++;
+            xc += st.step;
+            if (xc > FX_ONE) xc = FX_ONE;
+            if (((uint32_t)c & 15u) == 0) {  // the span continues in the next group
+                emit16<FMT, true>(drow, g * 16, (uint32_t)W, a[0], a[1], a[2], a[3], color, clr_a);
+                g++;
+                a[0] = a[1] = a[2] = a[3] = after;
+            }
+        }
+        emit16<FMT, true>(drow, g * 16, (uint32_t)W, a[0], a[1], a[2], a[3], color, clr_a);
+    }
+    // ---- the constant spans: right of every span, and left of the first one ----
+    const uint32_t owners = __ballot_sync(0xFFFFFFFFu, active && row_ok);
+    const uint32_t my_span = (gb + 1u) | (next_ga << 16);
+#pragma unroll 1
+    for (uint32_t m = owners; m; m &= m - 1) {
+        const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
+        const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span, s), q = __shfl_sync(0xFFFFFFFFu, after, s);
+        fill_span<FMT>(dst + (size_t)(s >> 3) * pitch, sp & 0xFFFFu, sp >> 16, q, (uint32_t)W, color, clr_a);
+    }
+#pragma unroll 1
+    for (int r = 0; r < n_rows; r++) {
+        const uint32_t hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
+        if (!((redo >> r) & 1u)) fill_span<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, (uint32_t)W, color, clr_a);
+    }
+    return redo;
+}
+
 // The tile kernel.  Every WARP owns a private shared-memory row window
 // (`win_chunks` chunks of 512 cells + their masks) and walks the rows of a
 // (job, band) tile on its own: its lanes scatter the coverage of the edges
@@ -1034,6 +1170,8 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) 
     const int32_t W = (int32_t)P.W, win_cells = (int32_t)(P.win_chunks * CHUNK);
     const uint32_t bpp = P.bpp;
     const uint32_t n_warps = gridDim.x * warps_per_cta;
+    // analytic rows need full 16-pixel groups on 16-byte boundaries and group indices below 0xFFFF
+    constexpr bool ANALYTIC = FMT == FTL_MATTE8 && ALIGNED && !GENERAL;
     for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps) {
         const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
         const JobState js = JS[j];
@@ -1070,7 +1208,10 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) 
                 if ((mine.flags & 1u) && my_ry < row_hi && my_ry >= mine.ry0 && my_ry <= mine.ry1) st = edge_row_setup(mine, my_ry, W, 0);
             }
             const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
+            uint32_t redo = 0xFFFFFFFFu;
+            if (ANALYTIC && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
             for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
+                if (!((redo >> rr) & 1u)) continue;
                 const int32_t ry = ry_base + rr;
                 int32_t carry = 0;
                 uint32_t bin = tile * P.n_win;
