@@ -1038,9 +1038,16 @@ __device__ __forceinline__ void fill_span(uint8_t *drow, uint32_t lo, uint32_t h
     const uint32_t lane = threadIdx.x & 31;
     if (FMT == FTL_MATTE8) {
         uint4 *p = reinterpret_cast<uint4 *>(drow);
-        const uint4 v = make_uint4(q, q, q, q);
+        uint32_t q0 = q, q1 = q, q2 = q, q3 = q;
+        asm volatile("" : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3));  // four resident registers: no per-store moves
+        const uint4 v = make_uint4(q0, q1, q2, q3);
+        uint32_t g = lo + lane;
 #pragma unroll 1
-        for (uint32_t g = lo + lane; g < hi; g += 32) p[g] = v;
+        for (; g + 32 < hi; g += 64) {
+            p[g] = v;
+            p[g + 32] = v;
+        }
+        if (g < hi) p[g] = v;
     } else {
 #pragma unroll 1
         for (uint32_t g = lo + lane; g < hi; g += 32) emit16<FMT, true>(drow, g * 16, W, q, q, q, q, color, clr_a);
@@ -1149,6 +1156,8 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
     return redo;
 }
 
+__device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
+
 // The tile kernel.  Every WARP owns a private shared-memory row window
 // (`win_chunks` chunks of 512 cells + their masks) and walks the rows of a
 // (job, band) tile on its own: its lanes scatter the coverage of the edges
@@ -1157,7 +1166,7 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED, bool GENERAL>
-__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
@@ -1172,8 +1181,17 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) 
     const uint32_t n_warps = gridDim.x * warps_per_cta;
     // analytic rows need full 16-pixel groups on 16-byte boundaries and group indices below 0xFFFF
     constexpr bool ANALYTIC = FMT == FTL_MATTE8 && ALIGNED && !GENERAL;
-    for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps) {
-        const uint32_t j = tile / P.n_bands, band = tile - j * P.n_bands;
+    uint32_t j = (P.tile_begin + blockIdx.x * warps_per_cta + warp) / P.n_bands, j_next = 0;
+    for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps, j = j_next) {
+        const uint32_t band = tile - j * P.n_bands;
+        // the records the next tile of this warp starts with: in flight while this tile is drawn
+        uint32_t vb_next = 0, ve_next = 0;
+        if (tile + n_warps < P.tile_end) {
+            j_next = (tile + n_warps) / P.n_bands;
+            prefetch_l1(&jobs[j_next]);
+            vb_next = JS[j_next].vtx_begin;
+            ve_next = JS[j_next].vtx_end;
+        }
         const JobState js = JS[j];
         int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
         int32_t row_hi = row0 + (int32_t)P.R;
@@ -1209,6 +1227,7 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 6 : 4) 
             }
             const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
             uint32_t redo = 0xFFFFFFFFu;
+            if (ry_base + rows_per_pass >= row_hi && vb_next + lane < ve_next && lane < 8) prefetch_l1(&E[vb_next + lane]);  // last pass
             if (ANALYTIC && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
             for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
                 if (!((redo >> rr) & 1u)) continue;
