@@ -661,6 +661,25 @@ constexpr uint32_t CHUNK = 512;
 __device__ __forceinline__ uint32_t cell_phys(uint32_t c) {
     return c ^ ((c >> 3) & 0xCu);  // bits 3:2 (the quad within 4 quads) ^= bits 6:5
 }
+// The row window is addressed through 32-bit shared-window addresses and explicit ld/st/red.shared:
+// a generic pointer makes the compiler rebuild the window base (S2UR CgaCtaId + ULEA) at every access.
+__device__ __forceinline__ uint32_t smem_addr(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sred_add(uint32_t a, int32_t v) { asm volatile("red.shared.add.s32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ void sred_or(uint32_t a, uint32_t v) { asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ uint32_t slds(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ssts(uint32_t a, uint32_t v) { asm volatile("st.shared.u32 [%0], %1;" ::"r"(a), "r"(v)); }
+__device__ __forceinline__ int4 slds4(uint32_t a) {
+    int4 v;
+    asm volatile("ld.shared.v4.s32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ssts4_zero(uint32_t a) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(0u));
+}
 
 // Signed coverage of one edge on one raster row.  Closed form of
 // Scanner::scan_continuing_edges / add_edge + Edge::scan_area
@@ -713,7 +732,7 @@ __device__ __forceinline__ EdgeRowState edge_row_setup(const EdgeRec &e, int32_t
 }
 // The cells of [st.c, win_hi): adds each cell's delta into the shared row window (which starts at
 // column win_lo) and leaves `st` ready to continue in the next window.
-__device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_lo, int32_t win_hi, int32_t *cells, uint32_t *mask) {
+__device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_lo, int32_t win_hi, uint32_t cells, uint32_t mask) {
     if (st.cov <= 0 || st.c >= win_hi) return;
     const int32_t first_rel = st.c - win_lo;
     int32_t rel = first_rel;
@@ -722,7 +741,7 @@ __device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_l
         int32_t xk = pixel_cov(st.xc);
         if (xk > st.cov) xk = st.cov;
         const int32_t d = xk - st.prev;
-        if (d != 0) atomicAdd(&cells[cell_phys((uint32_t)rel)], st.ed * d);
+        if (d != 0) sred_add(cells + 4u * cell_phys((uint32_t)rel), st.ed * d);
         st.prev = xk;
         rel++;
         st.xc += st.step;  // both <= ONE: no overflow
@@ -737,7 +756,7 @@ __device__ __forceinline__ void edge_row_scatter(EdgeRowState &st, int32_t win_l
     // mark the 16-cell groups [first_rel >> 4, (rel - 1) >> 4] of the window as touched
     for (uint32_t g = (uint32_t)first_rel >> 4, g1 = (uint32_t)(rel - 1) >> 4; g <= g1;) {
         const uint32_t top = min(g1, g | 31u);
-        atomicOr(&mask[g >> 5], ((2u << (top - g)) - 1u) << (g & 31u));
+        sred_or(mask + 4u * (g >> 5), ((2u << (top - g)) - 1u) << (g & 31u));
         g = top + 1;
     }
 }
@@ -877,6 +896,69 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
     }
 }
 
+// Pixels [16 * lo, 16 * hi) of a row (whole 16-pixel groups, 16-byte aligned) take one constant alpha
+// `a`: consecutive lanes on consecutive 16 bytes.  Matte8 stores; Graya8p / Rgba8p blend SrcOver with
+// the two cheap cases of pix (alpha 0: d * Ch8(255); opaque coverage of an opaque colour: no read).
+template <int FMT>
+__device__ __forceinline__ void fill_const(uint8_t *drow, uint32_t lo, uint32_t hi, uint32_t a, uint32_t color, uint32_t clr_a) {
+    const uint32_t lane = threadIdx.x & 31;
+    constexpr uint32_t U = FMT == FTL_MATTE8 ? 1u : (FMT == FTL_GRAYA8P ? 2u : 4u);  // uint4 per group
+    uint4 *p = reinterpret_cast<uint4 *>(drow);
+    uint32_t u = lo * U + lane;
+    const uint32_t end = hi * U;
+    if (FMT == FTL_MATTE8 || (a == 255u && clr_a == 255u)) {
+        uint32_t w = a * 0x01010101u;
+        if (FMT == FTL_RGBA8P) w = mul255_x4(color);
+        if (FMT == FTL_GRAYA8P) w = mul255_x4((color & 0xFFFFu) * 0x00010001u);
+        uint32_t q0 = w, q1 = w, q2 = w, q3 = w;
+        asm volatile("" : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3));  // four resident registers: no per-store moves
+        const uint4 v = make_uint4(q0, q1, q2, q3);
+#pragma unroll 1
+        for (; u + 32 < end; u += 64) {
+            p[u] = v;
+            p[u + 32] = v;
+        }
+        if (u < end) p[u] = v;
+    } else if (a == 0u) {
+#pragma unroll 1
+        for (; u + 96 < end; u += 128) {  // four loads in flight per lane
+            uint4 t0 = p[u], t1 = p[u + 32], t2 = p[u + 64], t3 = p[u + 96];
+            t0.x = mul255_x4(t0.x); t0.y = mul255_x4(t0.y); t0.z = mul255_x4(t0.z); t0.w = mul255_x4(t0.w);
+            t1.x = mul255_x4(t1.x); t1.y = mul255_x4(t1.y); t1.z = mul255_x4(t1.z); t1.w = mul255_x4(t1.w);
+            t2.x = mul255_x4(t2.x); t2.y = mul255_x4(t2.y); t2.z = mul255_x4(t2.z); t2.w = mul255_x4(t2.w);
+            t3.x = mul255_x4(t3.x); t3.y = mul255_x4(t3.y); t3.z = mul255_x4(t3.z); t3.w = mul255_x4(t3.w);
+            p[u] = t0; p[u + 32] = t1; p[u + 64] = t2; p[u + 96] = t3;
+        }
+#pragma unroll 1
+        for (; u < end; u += 32) {
+            uint4 t = p[u];
+            t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
+            p[u] = t;
+        }
+    } else {
+        const uint32_t sa1 = 255u - pix::ch8_mul(a, clr_a);
+#pragma unroll 1
+        for (; u < end; u += 32) {
+            uint4 t = p[u];
+#pragma unroll 1
+            for (int k = 0; k < 4; k++) {  // rolled: the general blend is large
+                const uint32_t wk = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
+                uint32_t o = 0;
+#pragma unroll
+                for (int ch = 0; ch < 4; ch++) {
+                    const uint32_t sc = FMT == FTL_RGBA8P ? (color >> (8 * ch)) & 0xFF : (color >> (8 * (ch & 1))) & 0xFF;
+                    o |= pix::src_over_ch((wk >> (8 * ch)) & 0xFF, sc, a, sa1) << (8 * ch);
+                }
+                if (k == 0) t.x = o;
+                else if (k == 1) t.y = o;
+                else if (k == 2) t.z = o;
+                else t.w = o;
+            }
+            p[u] = t;
+        }
+    }
+}
+
 // One step of an inclusive add-scan over segments of WIDTH lanes: v += the value `d` lanes below,
 // predicated by the shuffle's own in-range result (no lane compare).
 template <int WIDTH>
@@ -895,7 +977,7 @@ __device__ __forceinline__ void scan_step(int32_t &v, int d) {
 // word is zero holds no edge: its pixels take the constant alpha of the
 // running sum without touching shared memory.
 template <int FMT, bool EVEN_ODD, bool ALIGNED>
-__device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_t *dst, uint32_t W, uint32_t c_begin, uint32_t c_end,
+__device__ __forceinline__ void resolve_row(uint32_t row, uint32_t mask, uint8_t *dst, uint32_t W, uint32_t c_begin, uint32_t c_end,
                                             int32_t &carry_io, uint32_t color) {
     int32_t carry = carry_io;
     const uint32_t lane = threadIdx.x & 31;
@@ -905,8 +987,8 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     // the warp's chunk masks: lane i holds (and clears) the mask of chunk c_begin + i
     uint32_t mym = 0;
     if (lane < n) {
-        mym = mask[c_begin + lane];
-        if (mym) mask[c_begin + lane] = 0;
+        mym = slds(mask + 4u * (c_begin + lane));
+        if (mym) ssts(mask + 4u * (c_begin + lane), 0u);
     }
     const uint32_t dense = __ballot_sync(0xFFFFFFFFu, mym != 0);
     uint32_t q = quad_alpha<EVEN_ODD>(0, 0, 0, 0, carry);  // alpha of an edge-free span at the current sum
@@ -917,32 +999,13 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
     uint32_t pend = dense, ch = c_begin;
     for (;;) {
         const uint32_t nxt = c_begin + (pend ? (uint32_t)__ffs((int)pend) - 1u : n);
-        if (FMT == FTL_MATTE8 && ALIGNED) {
+        if (ALIGNED && ch < min(nxt, full_end)) {
             const uint32_t stop = min(nxt, full_end);
-            const uint4 v = make_uint4(q, q, q, q);
-#pragma unroll 1
-            for (; ch < stop; ch++) out4[ch * 32] = v;
+            fill_const<FMT>(dst, ch * 32u, stop * 32u, q & 0xFFu, color, clr_a);
+            ch = stop;
         }
 #pragma unroll 1
-        for (; ch < nxt; ch++) {
-            const uint32_t x = ch * CHUNK + lane * 16;
-            if (FMT == FTL_RGBA8P && ALIGNED && ch < full_end && (q == 0 || (q == 0xFFFFFFFFu && clr_a == 255))) {
-                // edge-free chunk of one alpha: 512 pixels = 2 KiB, consecutive lanes on consecutive 16 bytes
-                uint4 *p = reinterpret_cast<uint4 *>(dst) + ch * 128 + lane;
-                if (q == 0) {
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        uint4 t = p[32 * j];
-                        t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
-                        p[32 * j] = t;
-                    }
-                } else {
-                    const uint32_t c = mul255_x4(color);
-#pragma unroll
-                    for (int j = 0; j < 4; j++) p[32 * j] = make_uint4(c, c, c, c);
-                }
-            } else emit16<FMT, ALIGNED>(dst, x, W, q, q, q, q, color, clr_a);
-        }
+        for (; ch < nxt; ch++) emit16<FMT, ALIGNED>(dst, ch * CHUNK + lane * 16, W, q, q, q, q, color, clr_a);  // ragged last chunk
         if (pend == 0) break;
         pend &= pend - 1;
         const uint32_t cur = ch++;  // == nxt: the chunk to resolve
@@ -962,9 +1025,9 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
                 const int32_t gg = half ? g2 : g;
                 int32_t inc = 0;
                 if (gg >= 0) {
-                    int32_t *p = row + cur * CHUNK + (((uint32_t)gg * 4 + ((l16 >> 2) ^ (((uint32_t)gg >> 1) & 3u))) << 2) + (l16 & 3u);
-                    inc = *p;
-                    *p = 0;
+                    const uint32_t p = row + 4u * (cur * CHUNK + cell_phys((uint32_t)gg * 16u + l16));
+                    inc = (int32_t)slds(p);
+                    ssts(p, 0u);
                 }
 #pragma unroll
                 for (int d = 1; d < 16; d <<= 1) scan_step<16>(inc, d);
@@ -984,12 +1047,10 @@ __device__ __forceinline__ void resolve_row(int32_t *row, uint32_t *mask, uint8_
         }
         int4 v0 = make_int4(0, 0, 0, 0), v1 = v0, v2 = v0, v3 = v0;
         if ((m >> lane) & 1u) {
-            int32_t *base = row + cur * CHUNK + lane * 16;
-            int4 *p0 = reinterpret_cast<int4 *>(base + ((0 ^ sw) << 2)), *p1 = reinterpret_cast<int4 *>(base + ((1 ^ sw) << 2));
-            int4 *p2 = reinterpret_cast<int4 *>(base + ((2 ^ sw) << 2)), *p3 = reinterpret_cast<int4 *>(base + ((3 ^ sw) << 2));
-            v0 = *p0; v1 = *p1; v2 = *p2; v3 = *p3;
-            const int4 z = make_int4(0, 0, 0, 0);
-            *p0 = z; *p1 = z; *p2 = z; *p3 = z;
+            const uint32_t base = row + 4u * (cur * CHUNK + lane * 16);
+            const uint32_t p0 = base + ((0 ^ sw) << 4), p1 = base + ((1 ^ sw) << 4), p2 = base + ((2 ^ sw) << 4), p3 = base + ((3 ^ sw) << 4);
+            v0 = slds4(p0); v1 = slds4(p1); v2 = slds4(p2); v3 = slds4(p3);
+            ssts4_zero(p0); ssts4_zero(p1); ssts4_zero(p2); ssts4_zero(p3);
         }
         // lane-local inclusive prefix: 4 independent quad scans, then quad offsets
         v0.y += v0.x; v0.z += v0.y; v0.w += v0.z;
@@ -1031,27 +1092,6 @@ __device__ __forceinline__ uint32_t rule_alpha_rt(int32_t sum, bool even_odd) {
     c = c < 0 ? -c : c;
     s = even_odd ? c : s;
     return (uint32_t)min(max(s, 0), 255);
-}
-
-template <int FMT>
-__device__ __forceinline__ void fill_span(uint8_t *drow, uint32_t lo, uint32_t hi, uint32_t q, uint32_t W, uint32_t color, uint32_t clr_a) {
-    const uint32_t lane = threadIdx.x & 31;
-    if (FMT == FTL_MATTE8) {
-        uint4 *p = reinterpret_cast<uint4 *>(drow);
-        uint32_t q0 = q, q1 = q, q2 = q, q3 = q;
-        asm volatile("" : "+r"(q0), "+r"(q1), "+r"(q2), "+r"(q3));  // four resident registers: no per-store moves
-        const uint4 v = make_uint4(q0, q1, q2, q3);
-        uint32_t g = lo + lane;
-#pragma unroll 1
-        for (; g + 32 < hi; g += 64) {
-            p[g] = v;
-            p[g + 32] = v;
-        }
-        if (g < hi) p[g] = v;
-    } else {
-#pragma unroll 1
-        for (uint32_t g = lo + lane; g < hi; g += 32) emit16<FMT, true>(drow, g * 16, W, q, q, q, q, color, clr_a);
-    }
 }
 
 // Rows ry_base .. ry_base + n_rows - 1 (n_rows <= 4) of one tile; `st` is this lane's (row my_r, edge)
@@ -1104,11 +1144,11 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
         if (r < n_rows && ((conf_bal >> (8 * r)) & 0xFFu)) redo |= 1u << r;
     const bool row_ok = (int32_t)my_r < n_rows && !((redo >> my_r) & 1u);
     uint8_t *drow = dst + (size_t)my_r * pitch;
-    const uint32_t after = rule_alpha_rt(base + wgt, even_odd) * 0x01010101u;
+    const uint32_t after_a = rule_alpha_rt(base + wgt, even_odd), after = after_a * 0x01010101u;
     // ---- the groups holding the span ----
     if (active && row_ok) {
         const uint32_t before = rule_alpha_rt(base, even_odd) * 0x01010101u;
-        // group ga: `before` left of the span start, `after` right of it, span cells inserted below
+        // group ga: `before` left of the span start, `after` right of it; the span's cells are inserted
         const uint32_t p0 = (uint32_t)st.c & 15u;
         uint32_t a[4];
 #pragma unroll
@@ -1118,26 +1158,26 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
             a[j] = (before & m) | (after & ~m);
         }
         int32_t xc = st.xc, c = st.c;
-        uint32_t g = ga;
-        for (;;) {
-            int32_t xk = pixel_cov(xc);
-            if (xk > st.cov) xk = st.cov;
-            const uint32_t al = rule_alpha_rt(base + st.ed * xk, even_odd);
-            const uint32_t sh = ((uint32_t)c & 3u) * 8u, m = 0xFFu << sh, v = al << sh, wj = ((uint32_t)c >> 2) & 3u;
+#pragma unroll 1
+        for (uint32_t g = ga;; g++) {
+            bool done;
+            do {  // the span's cells inside group g
+                int32_t xk = pixel_cov(xc);
+                if (xk > st.cov) xk = st.cov;
+                const uint32_t al = rule_alpha_rt(base + st.ed * xk, even_odd);
+                const uint32_t sh = ((uint32_t)c & 3u) * 8u, m = 0xFFu << sh, v = al << sh, wj = ((uint32_t)c >> 2) & 3u;
 #pragma unroll
-            for (uint32_t j = 0; j < 4; j++)
-                if (wj == j) a[j] = (a[j] & ~m) | v;
-            if (xk >= st.cov || c >= W - 1) break;
-            c++;
-            xc += st.step;
-            if (xc > FX_ONE) xc = FX_ONE;
-            if (((uint32_t)c & 15u) == 0) {  // the span continues in the next group
-                emit16<FMT, true>(drow, g * 16, (uint32_t)W, a[0], a[1], a[2], a[3], color, clr_a);
-                g++;
-                a[0] = a[1] = a[2] = a[3] = after;
-            }
+                for (uint32_t j = 0; j < 4; j++)
+                    if (wj == j) a[j] = (a[j] & ~m) | v;
+                done = xk >= st.cov || c >= W - 1;
+                c++;
+                xc += st.step;
+                if (xc > FX_ONE) xc = FX_ONE;
+            } while (!done && ((uint32_t)c & 15u) != 0);
+            emit16<FMT, true>(drow, g * 16, (uint32_t)W, a[0], a[1], a[2], a[3], color, clr_a);
+            if (done) break;
+            a[0] = a[1] = a[2] = a[3] = after;  // the span continues in the next group
         }
-        emit16<FMT, true>(drow, g * 16, (uint32_t)W, a[0], a[1], a[2], a[3], color, clr_a);
     }
     // ---- the constant spans: right of every span, and left of the first one ----
     const uint32_t owners = __ballot_sync(0xFFFFFFFFu, active && row_ok);
@@ -1145,13 +1185,13 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
 #pragma unroll 1
     for (uint32_t m = owners; m; m &= m - 1) {
         const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
-        const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span, s), q = __shfl_sync(0xFFFFFFFFu, after, s);
-        fill_span<FMT>(dst + (size_t)(s >> 3) * pitch, sp & 0xFFFFu, sp >> 16, q, (uint32_t)W, color, clr_a);
+        const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span, s), q = __shfl_sync(0xFFFFFFFFu, after_a, s);
+        fill_const<FMT>(dst + (size_t)(s >> 3) * pitch, sp & 0xFFFFu, sp >> 16, q, color, clr_a);
     }
 #pragma unroll 1
     for (int r = 0; r < n_rows; r++) {
         const uint32_t hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
-        if (!((redo >> r) & 1u)) fill_span<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, (uint32_t)W, color, clr_a);
+        if (!((redo >> r) & 1u)) fill_const<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, color, clr_a);
     }
     return redo;
 }
@@ -1172,15 +1212,15 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) 
     if (C->overflow) return;
     extern __shared__ __align__(16) int32_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
-    int32_t *cells = smem + warp * P.warp_words;
-    uint32_t *mask = reinterpret_cast<uint32_t *>(cells + P.win_chunks * CHUNK);
-    for (uint32_t i = lane; i < P.warp_words; i += 32) cells[i] = 0;
+    const uint32_t cells = smem_addr(smem) + 4u * warp * P.warp_words, mask = cells + 4u * P.win_chunks * CHUNK;
+    for (uint32_t i = lane; i < P.warp_words; i += 32) ssts(cells + 4u * i, 0u);
     __syncwarp();
     const int32_t W = (int32_t)P.W, win_cells = (int32_t)(P.win_chunks * CHUNK);
     const uint32_t bpp = P.bpp;
     const uint32_t n_warps = gridDim.x * warps_per_cta;
-    // analytic rows need full 16-pixel groups on 16-byte boundaries and group indices below 0xFFFF
-    constexpr bool ANALYTIC = FMT == FTL_MATTE8 && ALIGNED && !GENERAL;
+    // analytic rows need full 16-pixel groups on 16-byte boundaries (and group indices below 0xFFFF)
+    constexpr bool ANALYTIC = ALIGNED && !GENERAL;
+    const bool analytic_ok = ANALYTIC && (P.W & 15u) == 0;
     uint32_t j = (P.tile_begin + blockIdx.x * warps_per_cta + warp) / P.n_bands, j_next = 0;
     for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps, j = j_next) {
         const uint32_t band = tile - j * P.n_bands;
@@ -1228,7 +1268,7 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) 
             const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
             uint32_t redo = 0xFFFFFFFFu;
             if (ry_base + rows_per_pass >= row_hi && vb_next + lane < ve_next && lane < 8) prefetch_l1(&E[vb_next + lane]);  // last pass
-            if (ANALYTIC && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
+            if (analytic_ok && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
             for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
                 if (!((redo >> rr) & 1u)) continue;
                 const int32_t ry = ry_base + rr;
@@ -1278,11 +1318,11 @@ __global__ void __launch_bounds__(32) accumulate_rows_kernel(const int16_t *__re
     const bool al = (n & 15u) == 0;
     int32_t carry = 0;
     if (even_odd) {
-        if (al) resolve_row<FTL_MATTE8, true, true>(area, mask, d, n, 0, chunks, carry, 0);
-        else resolve_row<FTL_MATTE8, true, false>(area, mask, d, n, 0, chunks, carry, 0);
+        if (al) resolve_row<FTL_MATTE8, true, true>(smem_addr(area), smem_addr(mask), d, n, 0, chunks, carry, 0);
+        else resolve_row<FTL_MATTE8, true, false>(smem_addr(area), smem_addr(mask), d, n, 0, chunks, carry, 0);
     } else {
-        if (al) resolve_row<FTL_MATTE8, false, true>(area, mask, d, n, 0, chunks, carry, 0);
-        else resolve_row<FTL_MATTE8, false, false>(area, mask, d, n, 0, chunks, carry, 0);
+        if (al) resolve_row<FTL_MATTE8, false, true>(smem_addr(area), smem_addr(mask), d, n, 0, chunks, carry, 0);
+        else resolve_row<FTL_MATTE8, false, false>(smem_addr(area), smem_addr(mask), d, n, 0, chunks, carry, 0);
     }
 }
 
@@ -1816,7 +1856,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
 
     // ---- (c)+(d) tiles ----
     int occ = 1;
-    const bool aligned = P.fmt == FTL_MATTE8 ? (P.W % 16 == 0) : (P.fmt == FTL_RGBA8P ? (P.W % 4 == 0) : true);
+    const bool aligned = P.W % (16u / P.bpp) == 0;  // rows start on 16-byte boundaries
     TileKernel tk = tile_kernel((int)P.fmt, aligned, !P.all_direct);
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
