@@ -205,6 +205,51 @@ def test_random_polygons_vs_oracle(fmt):
             assert_same(g, o, "it %d layer %d" % (it, layer))
 
 
+# Tiles with at most 8 edge slots on rasters whose width is a multiple of 16 take the analytic rows of
+# the tile kernel (no shared-memory scatter); rows where two spans share a 16-pixel group, or a span is
+# long (shallow edges), fall back to the shared-memory path inside the same tile.
+@pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p, Format.Graya8p])
+def test_analytic_rows_vs_oracle(fmt):
+    rng = np.random.default_rng(101 + int(fmt))
+    bpp = {Format.Matte8: 1, Format.Graya8p: 2, Format.Rgba8p: 4}[fmt]
+    for it in range(120):
+        w = int(rng.choice([16, 32, 48, 128, 272, 1040]))
+        h = int(rng.choice([1, 4, 5, 8, 19, 64]))
+        init = rng.integers(0, 256, (h, w * bpp)).astype(np.uint8)
+        g, o = both(w, h, fmt, init=init)
+        for layer in range(3):
+            kind = int(rng.integers(0, 5))
+            n = int(rng.integers(3, 9))  # <= 8 vertices in the whole job
+            if kind == 0:  # anywhere, partly outside
+                pts = np.stack([rng.uniform(-0.5 * w, 1.5 * w, n), rng.uniform(-0.5 * h, 1.5 * h, n)], axis=1)
+            elif kind == 1:  # steep edges: short spans
+                xs = np.sort(rng.uniform(0, w, n))
+                pts = np.stack([xs, rng.uniform(-1, h + 1, n)], axis=1)
+            elif kind == 2:  # shallow edges: long spans, fall back
+                pts = np.stack([rng.uniform(-w, 2 * w, n), rng.uniform(0, min(h, 3.0), n)], axis=1)
+            elif kind == 3:  # snapped to half pixels, coincident edges
+                pts = np.round(np.stack([rng.uniform(0, w, n), rng.uniform(0, h, n)], axis=1) * 2) / 2
+            else:  # two small sub-figures close to each other (spans sharing a group)
+                c = rng.uniform(0, w)
+                pts = np.stack([c + rng.uniform(-12, 12, n), rng.uniform(0, h, n)], axis=1)
+            if kind == 4 and n >= 6:
+                ops = list(poly([tuple(q) for q in pts[:3]])) + list(poly([tuple(q) for q in pts[3:]]))
+            else:
+                ops = list(poly([tuple(q) for q in pts], close=rng.random() < 0.8))
+            rule = int(rng.integers(0, 2))
+            clr = rng.integers(0, 256, 4).astype(np.uint8)
+            if rng.random() < 0.4:  # opaque colour: the no-read path
+                clr[3] = 255
+                clr[1] = 255 if fmt == Format.Graya8p else clr[1]
+            clr[:3] = np.minimum(clr[:3], clr[3])
+            if fmt == Format.Graya8p:
+                clr[0] = min(clr[0], clr[1])
+            g.fill(rule, ops, clr)
+            o.fill(rule, ops, clr)
+            assert g.debug_last_fill() == o.last_info()
+            assert_same(g, o, "it %d layer %d kind %d %dx%d" % (it, layer, kind, w, h))
+
+
 def test_negative_top_row_shift():
     ops = poly([(1.0, -2.5), (6.0, 3.0), (0.5, 5.0)])
     g, o = both(8, 8, Format.Matte8)
