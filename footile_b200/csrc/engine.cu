@@ -127,6 +127,7 @@ struct Params {  // per-call constants, passed by value
     uint32_t log2R, R, n_bands, WP, chunks;  // rows per tile, bands per job, smem row stride (cells), 512-cell chunks per row
     uint32_t n_jobs, n_ops, n_tiles;
     uint32_t win_chunks, warp_words, cta_warps;  // chunks per row window, smem words per warp, warps per CTA
+    uint32_t win_rows;                           // rows of a narrow raster (one window per row) a warp holds at once
     uint32_t n_win, n_bins;                      // windows per row; bins = n_tiles * n_win
     uint32_t all_direct;                         // host-proven: every job has <= DIRECT_MAX vertices (no binning needed)
     uint32_t tile_begin, tile_end;               // tiles this launch of the tile kernel covers
@@ -1206,13 +1207,13 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED, bool GENERAL>
-__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, FMT == FTL_MATTE8 ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
     extern __shared__ __align__(16) int32_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
-    const uint32_t cells = smem_addr(smem) + 4u * warp * P.warp_words, mask = cells + 4u * P.win_chunks * CHUNK;
+    const uint32_t cells = smem_addr(smem) + 4u * warp * P.warp_words, mask = cells + 4u * P.win_rows * P.win_chunks * CHUNK;
     for (uint32_t i = lane; i < P.warp_words; i += 32) ssts(cells + 4u * i, 0u);
     __syncwarp();
     const int32_t W = (int32_t)P.W, win_cells = (int32_t)(P.win_chunks * CHUNK);
@@ -1252,7 +1253,11 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) 
         // the per-(edge,row) set-up of several rows costs one pass; each row then scatters with its own lanes.
         const uint32_t gl = !one_list ? 5u : (ne <= 8 ? 3u : (ne <= 16 ? 4u : 5u));
         const uint32_t my_e = lane & ((1u << gl) - 1u), my_r = lane >> gl;
-        const int32_t rows_per_pass = (int32_t)(32u >> gl);
+        // Narrow rasters (one window per row) with lanes = edges: the window holds `win_rows` rows, every
+        // lane scatters all the rows of its edges in one pass, then the rows are resolved one by one.
+        const bool multi = gl == 5u && one_list && P.win_rows > 1u;
+        const int32_t rows_per_pass = multi ? (int32_t)P.win_rows : (int32_t)(32u >> gl);
+        const uint32_t row_bytes = 4u * P.win_chunks * CHUNK, rmask_bytes = 4u * P.win_chunks;
         EdgeRec mine;
         mine.flags = 0;
         if (one_list && my_e < ne) mine = E[direct ? e0 + my_e : entries[e0 + my_e]];
@@ -1263,41 +1268,50 @@ __global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 && !GENERAL) ? 5 : 4) 
             st.cov = 0;
             {
                 const int32_t my_ry = ry_base + (int32_t)my_r;
-                if ((mine.flags & 1u) && my_ry < row_hi && my_ry >= mine.ry0 && my_ry <= mine.ry1) st = edge_row_setup(mine, my_ry, W, 0);
+                if (!multi && (mine.flags & 1u) && my_ry < row_hi && my_ry >= mine.ry0 && my_ry <= mine.ry1) st = edge_row_setup(mine, my_ry, W, 0);
             }
             const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
             uint32_t redo = 0xFFFFFFFFu;
             if (ry_base + rows_per_pass >= row_hi && vb_next + lane < ve_next && lane < 8) prefetch_l1(&E[vb_next + lane]);  // last pass
             if (analytic_ok && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
+            const int32_t ry_last = ry_base + rr_end - 1;
             for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
                 if (!((redo >> rr) & 1u)) continue;
                 const int32_t ry = ry_base + rr;
+                const uint32_t rcells = multi ? cells + (uint32_t)rr * row_bytes : cells, rmask = multi ? mask + (uint32_t)rr * rmask_bytes : mask;
                 int32_t carry = 0;
                 uint32_t bin = tile * P.n_win;
                 uint8_t *dwin = dst;
                 for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++, dwin += win_bytes) {
                     const int32_t win_hi = min(W, win_lo + win_cells);
-                    // ---- (c) scatter: one lane per edge crossing this row ----
-                    uint32_t first = 32;
-                    if (one_list) {
-                        if ((int32_t)my_r == rr) edge_row_scatter(st, win_lo, win_hi, cells, mask);
-                    } else {  // wide raster with many edges: each window has its own bin
-                        e0 = tile_off[bin];
-                        ne = tile_off[bin + 1] - e0;
-                        first = 0;
-                    }
-                    for (uint32_t i = lane + first; i < ne; i += 32) {
-                        const EdgeRec e = E[direct ? e0 + i : entries[e0 + i]];
-                        if ((e.flags & 1u) && ry >= e.ry0 && ry <= e.ry1) {
-                            EdgeRowState s2 = edge_row_setup(e, ry, W, win_lo);
-                            edge_row_scatter(s2, win_lo, win_hi, cells, mask);
+                    // ---- (c) scatter: one lane per edge crossing this row (multi: all rows of the pass at once) ----
+                    if (!multi || rr == 0) {
+                        uint32_t first = 32;
+                        if (multi) first = 0;
+                        else if (one_list) {
+                            if ((int32_t)my_r == rr) edge_row_scatter(st, win_lo, win_hi, cells, mask);
+                        } else {  // wide raster with many edges: each window has its own bin
+                            e0 = tile_off[bin];
+                            ne = tile_off[bin + 1] - e0;
+                            first = 0;
                         }
+                        const int32_t ra = multi ? ry_base : ry, rb = multi ? ry_last : ry;
+                        for (uint32_t i = lane + first; i < ne; i += 32) {
+                            const EdgeRec e = (multi && i < 32) ? mine : E[direct ? e0 + i : entries[e0 + i]];
+                            if (!(e.flags & 1u)) continue;
+                            const int32_t r1 = min(e.ry1, rb);
+                            for (int32_t r = max(e.ry0, ra); r <= r1; r++) {
+                                EdgeRowState s2 = edge_row_setup(e, r, W, win_lo);
+                                const uint32_t ro = (uint32_t)(r - ra);
+                                edge_row_scatter(s2, win_lo, win_hi, cells + ro * row_bytes, mask + ro * rmask_bytes);
+                            }
+                        }
+                        __syncwarp();
                     }
-                    __syncwarp();
                     // ---- (d) resolve ----
                     const uint32_t nch = ((uint32_t)(win_hi - win_lo) + CHUNK - 1) / CHUNK;
-                    if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
-                    else resolve_row<FMT, false, ALIGNED>(cells, mask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                    if (rule == FTL_EVENODD) resolve_row<FMT, true, ALIGNED>(rcells, rmask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
+                    else resolve_row<FMT, false, ALIGNED>(rcells, rmask, dwin, (uint32_t)(W - win_lo), 0, nch, carry, color);
                     __syncwarp();
                 }
             }
@@ -1608,13 +1622,9 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     if (const char *ev = getenv("FTL_WIN_CHUNKS")) win = (uint32_t)std::min(32, std::max(1, atoi(ev)));  // tuning knob
     P->win_chunks = std::min(P->chunks, win);
     P->n_win = (P->chunks + P->win_chunks - 1) / P->win_chunks;
-    P->warp_words = (P->win_chunks * CHUNK + P->win_chunks + 3u) & ~3u;  // cells + masks, 16-byte multiple
+    P->win_rows = 1;
     P->cta_warps = 4;
-    size_t cta_bytes = (size_t)P->warp_words * 4 * P->cta_warps;
-    if (cta_bytes > max_smem) {
-        set_error("row window exceeds shared memory");
-        return FTL_ERR_TOO_WIDE;
-    }
+
     // Band height: 8 rows per warp amortise the per-tile set-up when every tile scans its job's own few
     // edges; binned jobs do better with 4 (fewer edges per bin to test against each row); fewer rows per
     // band when one launch would otherwise leave most of the GPU's warp slots empty (a single raster, a
@@ -1625,6 +1635,15 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     if (const char *ev = getenv("FTL_LOG2R")) log2R = (uint32_t)std::min(5, std::max(0, atoi(ev)));  // tuning knob
     P->log2R = log2R; P->R = 1u << log2R;
     P->n_bands = div_up(g.rows(), P->R);
+    // a narrow raster (one window per row) fills the window with several rows of the band
+    if (P->n_win == 1) P->win_rows = std::max(1u, std::min(win / P->win_chunks, P->R));
+    if (const char *ev = getenv("FTL_WIN_ROWS")) P->win_rows = P->n_win == 1 ? (uint32_t)std::min(8, std::max(1, atoi(ev))) : 1u;  // tuning knob
+    P->warp_words = (P->win_rows * (P->win_chunks * CHUNK + P->win_chunks) + 3u) & ~3u;  // cells + masks, 16-byte multiple
+    size_t cta_bytes = (size_t)P->warp_words * 4 * P->cta_warps;
+    if (cta_bytes > max_smem) {
+        set_error("row window exceeds shared memory");
+        return FTL_ERR_TOO_WIDE;
+    }
     return FTL_OK;
 }
 
