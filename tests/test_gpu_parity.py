@@ -554,6 +554,22 @@ def test_packed_readback_roundtrip():
         assert np.array_equal(g.raster().pixels, img), kind
 
 
+def test_hybrid_readback_large():
+    """>= 4 pieces of 256 MiB: packed pieces from the front, plain copies on a second stream from the back."""
+    rng = np.random.default_rng(5)
+    w, h = 32768, 40960  # 1.25 GiB = 5 pieces
+    img = np.zeros((h, w), dtype=np.uint8)
+    img[1000:9000] = 255
+    img[30000:30100] = rng.integers(0, 256, (100, w)).astype(np.uint8)
+    img[:, 5000:5040] = rng.integers(0, 256, (h, 40)).astype(np.uint8)
+    img[-1, -1] = 9
+    g = Plotter(Raster(w, h, Format.Matte8, img))
+    out = g.raster().pixels
+    assert out.shape == img.shape
+    for r0 in range(0, h, 4096):  # compare in slices: a full-size temporary is not needed
+        assert np.array_equal(out[r0:r0 + 4096], img[r0:r0 + 4096]), r0
+
+
 # ---- wide + dense: edges are binned per (band, row window); long shallow edges cross several windows ----
 @pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p])
 def test_wide_dense_window_bins(fmt):
