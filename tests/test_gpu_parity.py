@@ -554,8 +554,8 @@ def test_packed_readback_roundtrip():
         assert np.array_equal(g.raster().pixels, img), kind
 
 
-def test_hybrid_readback_large():
-    """>= 4 pieces of 256 MiB: packed pieces from the front, plain copies on a second stream from the back."""
+def test_packed_readback_large():
+    """Five pieces of 256 MiB: the packed read-back pipelines the pieces (device classify / PCIe / host expansion)."""
     rng = np.random.default_rng(5)
     w, h = 32768, 40960  # 1.25 GiB = 5 pieces
     img = np.zeros((h, w), dtype=np.uint8)
