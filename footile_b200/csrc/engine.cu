@@ -796,7 +796,7 @@ __device__ __forceinline__ uint32_t blend_rgba_general(uint32_t px, uint32_t col
 }
 // Ch8 d * Ch8(255) on the four channels of a pixel at once: with pix's 12-bit multiply this is
 // d - 1 for 1 <= d <= 15 and d otherwise (pix_compat.cuh; checked exhaustively in tests/test_host.py).
-__device__ __forceinline__ uint32_t mul255_x4(uint32_t w) {
+__device__ __forceinline__ uint32_t mul255_delta(uint32_t w) {  // w - (w * Ch8(255)) per byte: 1 for bytes 1..15
     // plain integer ops on purpose: the __vset*4 video intrinsics (emulated through inline lop3 on
     // sm_100a) were mis-scheduled under if-conversion in this kernel
     uint32_t nz = w | (w >> 4);
@@ -805,7 +805,14 @@ __device__ __forceinline__ uint32_t mul255_x4(uint32_t w) {
     uint32_t hi = w & 0xF0F0F0F0u;
     hi |= hi >> 2;
     hi |= hi >> 1;  // bit 4 of each byte: the byte is >= 16
-    return w - (nz & ~(hi >> 4) & 0x01010101u);
+    return nz & ~(hi >> 4) & 0x01010101u;
+}
+__device__ __forceinline__ uint32_t mul255_x4(uint32_t w) { return w - mul255_delta(w); }
+// Alpha 0 over 16 bytes of pixels (d * Ch8(255) per channel): most pixels do not change (only channel
+// values 1..15 do), and unchanged words are not written back - the blend then costs its read only.
+__device__ __forceinline__ void mul255_rmw(uint4 *p, const uint4 t) {
+    const uint32_t dx = mul255_delta(t.x), dy = mul255_delta(t.y), dz = mul255_delta(t.z), dw = mul255_delta(t.w);
+    if ((dx | dy | dz | dw) != 0u) *p = make_uint4(t.x - dx, t.y - dy, t.z - dz, t.w - dw);
 }
 // SrcOver of one Rgba8p pixel (the 4-pixel and 512-pixel fast paths for alpha = 0 and for opaque
 // full coverage live in emit16 / resolve_row).
@@ -868,7 +875,8 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
                 } else {
                     uint4 t = *q4;
                     if (w == 0) {
-                        t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
+                        mul255_rmw(q4, t);
+                        continue;
                     } else {
                         t.x = blend_rgba(t.x, color, w & 0xFF, clr_a);
                         t.y = blend_rgba(t.y, color, (w >> 8) & 0xFF, clr_a);
@@ -923,19 +931,14 @@ __device__ __forceinline__ void fill_const(uint8_t *drow, uint32_t lo, uint32_t 
     } else if (a == 0u) {
 #pragma unroll 1
         for (; u + 96 < end; u += 128) {  // four loads in flight per lane
-            uint4 t0 = p[u], t1 = p[u + 32], t2 = p[u + 64], t3 = p[u + 96];
-            t0.x = mul255_x4(t0.x); t0.y = mul255_x4(t0.y); t0.z = mul255_x4(t0.z); t0.w = mul255_x4(t0.w);
-            t1.x = mul255_x4(t1.x); t1.y = mul255_x4(t1.y); t1.z = mul255_x4(t1.z); t1.w = mul255_x4(t1.w);
-            t2.x = mul255_x4(t2.x); t2.y = mul255_x4(t2.y); t2.z = mul255_x4(t2.z); t2.w = mul255_x4(t2.w);
-            t3.x = mul255_x4(t3.x); t3.y = mul255_x4(t3.y); t3.z = mul255_x4(t3.z); t3.w = mul255_x4(t3.w);
-            p[u] = t0; p[u + 32] = t1; p[u + 64] = t2; p[u + 96] = t3;
+            const uint4 t0 = p[u], t1 = p[u + 32], t2 = p[u + 64], t3 = p[u + 96];
+            mul255_rmw(p + u, t0);
+            mul255_rmw(p + u + 32, t1);
+            mul255_rmw(p + u + 64, t2);
+            mul255_rmw(p + u + 96, t3);
         }
 #pragma unroll 1
-        for (; u < end; u += 32) {
-            uint4 t = p[u];
-            t.x = mul255_x4(t.x); t.y = mul255_x4(t.y); t.z = mul255_x4(t.z); t.w = mul255_x4(t.w);
-            p[u] = t;
-        }
+        for (; u < end; u += 32) mul255_rmw(p + u, p[u]);
     } else {
         const uint32_t sa1 = 255u - pix::ch8_mul(a, clr_a);
 #pragma unroll 1
@@ -1207,7 +1210,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED, bool GENERAL>
-__global__ void __launch_bounds__(128, FMT == FTL_MATTE8 ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 || !GENERAL) ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
