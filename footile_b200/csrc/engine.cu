@@ -811,8 +811,14 @@ __device__ __forceinline__ uint32_t mul255_x4(uint32_t w) { return w - mul255_de
 // Alpha 0 over 16 bytes of pixels (d * Ch8(255) per channel): most pixels do not change (only channel
 // values 1..15 do), and unchanged words are not written back - the blend then costs its read only.
 __device__ __forceinline__ void mul255_rmw(uint4 *p, const uint4 t) {
-    const uint32_t dx = mul255_delta(t.x), dy = mul255_delta(t.y), dz = mul255_delta(t.z), dw = mul255_delta(t.w);
-    if ((dx | dy | dz | dw) != 0u) *p = make_uint4(t.x - dx, t.y - dy, t.z - dz, t.w - dw);
+    // cheap test first: bit 4 of a byte of (lo + 15) is "low nibble != 0", of (hi + 15) "high nibble != 0"
+    // (nibbles spread to bytes cannot carry into the neighbour); a byte changes iff low != 0 and high == 0
+    const uint32_t K = 0x0F0F0F0Fu;
+    uint32_t any = ((t.x & K) + K) & ~(((t.x >> 4) & K) + K);
+    any |= ((t.y & K) + K) & ~(((t.y >> 4) & K) + K);
+    any |= ((t.z & K) + K) & ~(((t.z >> 4) & K) + K);
+    any |= ((t.w & K) + K) & ~(((t.w >> 4) & K) + K);
+    if (any & 0x10101010u) *p = make_uint4(mul255_x4(t.x), mul255_x4(t.y), mul255_x4(t.z), mul255_x4(t.w));
 }
 // SrcOver of one Rgba8p pixel (the 4-pixel and 512-pixel fast paths for alpha = 0 and for opaque
 // full coverage live in emit16 / resolve_row).
@@ -1210,7 +1216,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 // each other, and the small window keeps many warps resident per SM, which is
 // what hides the latency of the serial scatter -> scan -> store chain.
 template <int FMT, bool ALIGNED, bool GENERAL>
-__global__ void __launch_bounds__(128, (FMT == FTL_MATTE8 || !GENERAL) ? 5 : 4) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
+__global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
                                                        const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
     if (C->overflow) return;
