@@ -424,6 +424,11 @@ def main():
         roof = {"kernel": "raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step * (8 if rgba else 1), "bytes_per_px": 8 if rgba else 1, "avg_launch_ms": per_launch_ms,
                 "launches_timed": tile_n, "share_of_step": tile_ms / ms if ms else None}
+        if traffic:
+            roof["traffic_frac"] = traffic / (per_launch_ms * 1e-3) / 1e9 / peak  # measured DRAM bytes (ncu) over this run's launch time
+        if rgba:
+            roof["note"] = ("8 B/px is what the reference's per-pixel SrcOver loop reads and writes; here opaque spans are written unread and alpha-0 "
+                            "spans write back only the pixels that change, so real DRAM traffic is lower and frac may exceed 1 - traffic_frac is the measured share of the peak")
 
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----
     cpu = None

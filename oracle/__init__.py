@@ -92,6 +92,9 @@ def lib():
         L.orc_batch_fill_timed.restype = C.c_double
         L.orc_batch_fill_timed.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_uint32, C.c_uint32]
+        L.orc_batch_fill_checksums.restype = None
+        L.orc_batch_fill_checksums.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                               C.c_void_p, C.c_uint32, C.c_void_p]
         L.orc_get_pen_width.restype = C.c_float
         L.orc_get_pen_width.argtypes = [C.c_void_p]
         L.orc_debug_flatten.restype = C.c_size_t
@@ -187,6 +190,19 @@ def batch_fill_timed(w, h, fmt, ops, offs, rules=None, transforms=None, clr=(255
     c = _clr(clr, fmt)
     return lib().orc_batch_fill_timed(w, h, fmt, len(o) - 1, a.ctypes.data, o.ctypes.data, None if r is None else r.ctypes.data,
                                       None if t is None else t.ctypes.data, c.ctypes.data, int(threads), int(repeats))
+
+
+def batch_fill_checksums(w, h, fmt, ops, offs, rules=None, transforms=None, clr=(255, 255, 255, 255), threads=1):
+    """FNV checksum (the fold of ftl_batch_checksums) of every job's raster, computed by the oracle on `threads` threads."""
+    a = np.ascontiguousarray(np.asarray(ops, dtype=OP_DTYPE))
+    o = np.ascontiguousarray(np.asarray(offs, dtype=np.uint64))
+    r = None if rules is None else np.ascontiguousarray(np.asarray(rules, dtype=np.uint8))
+    t = None if transforms is None else np.ascontiguousarray(np.asarray(transforms, dtype=np.float32))
+    c = _clr(clr, fmt)
+    out = np.zeros(len(o) - 1, dtype=np.uint64)
+    lib().orc_batch_fill_checksums(w, h, fmt, len(o) - 1, a.ctypes.data, o.ctypes.data, None if r is None else r.ctypes.data,
+                                   None if t is None else t.ctypes.data, c.ctypes.data, int(threads), out.ctypes.data)
+    return out
 
 
 class Plotter:

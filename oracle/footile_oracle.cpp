@@ -865,4 +865,32 @@ double orc_batch_fill_timed(uint32_t w, uint32_t h, int fmt, uint32_t n_jobs, co
     return dt;
 }
 
+// Checksum of every job's raster (the 256-lane FNV-1a fold of ftl_batch_checksums) without keeping the
+// rasters: one Plotter per thread, cleared before each job.  Test infrastructure for full-size batches.
+void orc_batch_fill_checksums(uint32_t w, uint32_t h, int fmt, uint32_t n_jobs, const orc_path_op *ops, const uint64_t *offs,
+                              const uint8_t *rules, const float *transforms, const uint8_t *clr, uint32_t n_threads, uint64_t *out) {
+    if (n_threads < 1) n_threads = 1;
+    auto work = [&](uint32_t t) {
+        Plotter p;
+        p.w = w; p.h = h; p.fmt = fmt;
+        const size_t bytes = (size_t)w * h * fmt_bpp(fmt);
+        for (uint32_t j = t; j < n_jobs; j += n_threads) {
+            p.px.assign(bytes, 0);
+            if (transforms) memcpy(p.st.e, transforms + 6 * (size_t)j, 6 * sizeof(float));
+            p.fill(rules ? rules[j] : 0, (const PathOp *)ops + offs[j], (size_t)(offs[j + 1] - offs[j]), clr);
+            uint64_t lane[256];
+            for (int i = 0; i < 256; i++) lane[i] = 0xcbf29ce484222325ull;
+            const uint8_t *b = p.px.data();
+            for (size_t i = 0; i < bytes; i++) lane[i & 255] = (lane[i & 255] ^ b[i]) * 0x100000001b3ull;
+            uint64_t g = 0xcbf29ce484222325ull;
+            for (int i = 0; i < 256; i++)
+                for (int k = 0; k < 8; k++) g = (g ^ ((lane[i] >> (8 * k)) & 0xFF)) * 0x100000001b3ull;
+            out[j] = g;
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 0; t < n_threads; t++) th.emplace_back(work, t);
+    for (auto &t : th) t.join();
+}
+
 }  // extern "C"

@@ -392,6 +392,23 @@ def test_config4_batch_matches_oracle():
     assert got.any()
 
 
+def test_config4_full_size_100k_paths_checksums():
+    """BASELINE config 4 at its full size: all 100 000 random 64-curve paths, each into its own 512^2 Matte8
+    raster (25.6 GiB resident in HBM), every raster's device checksum against the oracle's."""
+    import os
+    total, size, chunk = 100_000, 512, 12_500
+    threads = min(32, os.cpu_count() or 1)
+    b = Batch(size, size, Format.Matte8, chunk)
+    for first in range(0, total, chunk):
+        ops, offs, rules = scenes.random_curve_paths(first, chunk)
+        b.clear()  # rows above a figure's top row keep their content (fig.rs:497): every chunk starts from zero
+        b.fill(ops, offs, rules=rules)
+        got = b.checksums()
+        exp = oracle.batch_fill_checksums(size, size, oracle.MATTE8, ops, offs, rules=rules, clr=(255,), threads=threads)
+        bad = np.nonzero(got != exp)[0]
+        assert bad.size == 0, "paths %s differ" % (first + bad[:8])
+
+
 def test_config4_batch_transforms_colors_rgba():
     n, size = 12, 64
     rng = np.random.default_rng(3)
