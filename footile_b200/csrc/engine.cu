@@ -1230,7 +1230,7 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
     const uint32_t n_warps = gridDim.x * warps_per_cta;
     // analytic rows need full 16-pixel groups on 16-byte boundaries (and group indices below 0xFFFF)
     constexpr bool ANALYTIC = ALIGNED && !GENERAL;
-    const bool analytic_ok = ANALYTIC && (P.W & 15u) == 0;
+    const bool analytic_ok = ANALYTIC && (P.W & 15u) == 0 && (P.W >> 4) < 0xFFFFu;
     uint32_t j = (P.tile_begin + blockIdx.x * warps_per_cta + warp) / P.n_bands, j_next = 0;
     for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps, j = j_next) {
         const uint32_t band = tile - j * P.n_bands;
