@@ -130,6 +130,7 @@ struct Params {  // per-call constants, passed by value
     uint32_t win_rows;                           // rows of a narrow raster (one window per row) a warp holds at once
     uint32_t n_win, n_bins;                      // windows per row; bins = n_tiles * n_win
     uint32_t all_direct;                         // host-proven: every job has <= DIRECT_MAX vertices (no binning needed)
+    uint32_t all_tiny;                           // host-proven: every job has <= 8 vertices (every tile can take the analytic rows)
     uint32_t tile_begin, tile_end;               // tiles this launch of the tile kernel covers
 };
 
@@ -1696,7 +1697,9 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     Params P{};
     // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
     P.all_direct = 1;
+    P.all_tiny = 1;
     for (const HostJob &h : jobs) {
+        if (h.op_end - h.op_begin > 8u) P.all_tiny = 0;
         if (h.op_end - h.op_begin > DIRECT_MAX) P.all_direct = 0;
         for (uint32_t i = h.op_begin; i < h.op_end && P.all_direct; i++)
             if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) P.all_direct = 0;
@@ -1889,6 +1892,11 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
+    // A launch whose tiles all take the analytic rows into Matte8 rasters is a stream of stores with little
+    // else to hide: 3 CTAs per SM (12 warps) measured 13 % faster than 5 at every batch size tried
+    // (fewer concurrent write streams); everything that reads or scatters wants all the warps it can get.
+    if (P.fmt == FTL_MATTE8 && P.all_direct && P.all_tiny && aligned && (P.W & 15u) == 0) occ = std::min(occ, 3);
+    if (const char *ev = getenv("FTL_OCC")) occ = std::max(1, std::min(5, atoi(ev)));  // tuning knob
     // Independent rasters: one launch over all tiles.  Layers of one raster: one launch per job, in
     // order, each over that job's tiles (the stages before ran once for all layers).
     const uint32_t n_launches = m.layered ? P.n_jobs : 1u;
