@@ -1634,6 +1634,7 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     P->n_win = (P->chunks + P->win_chunks - 1) / P->win_chunks;
     P->win_rows = 1;
     P->cta_warps = 4;
+    if (const char *ev = getenv("FTL_CTA_WARPS")) P->cta_warps = (uint32_t)std::min(4, std::max(1, atoi(ev)));  // tuning knob
 
     // Band height: 8 rows per warp amortise the per-tile set-up when every tile scans its job's own few
     // edges; binned jobs do better with 4 (fewer edges per bin to test against each row); fewer rows per
@@ -1893,10 +1894,11 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
     // A launch whose tiles all take the analytic rows into Matte8 rasters is a stream of stores with little
-    // else to hide: 3 CTAs per SM (12 warps) measured 13 % faster than 5 at every batch size tried
-    // (fewer concurrent write streams); everything that reads or scatters wants all the warps it can get.
-    if (P.fmt == FTL_MATTE8 && P.all_direct && P.all_tiny && aligned && (P.W & 15u) == 0) occ = std::min(occ, 3);
-    if (const char *ev = getenv("FTL_OCC")) occ = std::max(1, std::min(5, atoi(ev)));  // tuning knob
+    // else to hide, and the wider the rows the fewer resident warps it wants: 1024/2048-px rows are fastest
+    // at 5 CTAs per SM, 4096-px rows at 3 (13 % faster than 5 at every batch size tried), 8192-px rows at 2
+    // (tools/occ_probe.py).  Everything that reads or scatters wants all the warps it can get.
+    if (P.fmt == FTL_MATTE8 && P.all_direct && P.all_tiny && aligned && (P.W & 15u) == 0) occ = std::min(occ, P.W >= 6144u ? 2 : (P.W >= 3072u ? 3 : 5));
+    if (const char *ev = getenv("FTL_OCC")) occ = std::max(1, std::min(16, atoi(ev)));  // tuning knob
     // Independent rasters: one launch over all tiles.  Layers of one raster: one launch per job, in
     // order, each over that job's tiles (the stages before ran once for all layers).
     const uint32_t n_launches = m.layered ? P.n_jobs : 1u;
