@@ -1,0 +1,407 @@
+// front_kernels.cuh — stages (a)+(b): counters, flatten, edge preparation, binning
+// Included by engine.cu inside namespace ftl (one translation unit: the kernels share Params / EdgeRec / ...).
+#pragma once
+
+// ---------------------------------------------------------------------------
+// capacity guards: scratch buffers are sized from the previous call, so the
+// pipeline runs without a host round trip; if a count exceeds its buffer the
+// call draws nothing and the host repeats it with exact sizes.
+// ---------------------------------------------------------------------------
+__global__ void set_vertex_count(Counters *C, const SumHead *__restrict__ off, uint32_t n_ops, uint32_t cap_v) {
+    uint32_t nv = off[n_ops].sum;
+    if (nv > cap_v) {
+        C->overflow = 1;
+        C->need_v = nv;
+        nv = 0;
+    }
+    C->nv = nv;
+}
+__global__ void set_entry_count(Counters *C, const uint32_t *__restrict__ toff, uint32_t n_tiles, uint32_t cap_e) {
+    uint32_t n = toff[n_tiles];
+    C->n_entries = n;
+    if (n > cap_e) {
+        C->overflow = 1;
+        C->need_e = n;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (a) flatten — plotter.rs:175-332 + fig.rs:428-461
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t job_of_op(const JobDesc *jobs, uint32_t n_jobs, uint32_t i) {
+    uint32_t lo = 0, hi = n_jobs;  // last job with op_begin <= i
+    while (hi - lo > 1) {
+        uint32_t mid = (lo + hi) >> 1;
+        if (jobs[mid].op_begin <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+struct PenInfo {
+    pointy::Pt pen;
+    bool starts_sub;
+};
+// Pen position when op i runs: the end point of the previous drawing op, or
+// the origin after Close / at the start of the ops (plotter.rs:128-130,
+// 200-203); PenWidth does not move the pen.
+__device__ __forceinline__ PenInfo find_pen(const ftl_path_op *ops, uint32_t op_begin, uint32_t i) {
+    int64_t k = (int64_t)i - 1;
+    while (k >= (int64_t)op_begin && ops[k].tag >= FTL_OP_PENWIDTH) k--;
+    if (k < (int64_t)op_begin || ops[k].tag == FTL_OP_CLOSE) return {{0.0f, 0.0f}, true};
+    const ftl_path_op &o = ops[k];
+    int at = o.tag == FTL_OP_QUAD ? 2 : (o.tag == FTL_OP_CUBIC ? 4 : 0);
+    return {{o.v[at], o.v[at + 1]}, false};
+}
+
+struct WPt {
+    pointy::Pt p;
+    float w;
+};
+template <bool WIDE>
+__device__ __forceinline__ WPt wmid(WPt a, WPt b) {  // WidePt::midpoint (geom.rs:31-35)
+    WPt r;
+    r.p = pointy::midpoint(a.p, b.p);
+    r.w = WIDE ? (a.w + b.w) / 2.0f : 0.0f;
+    return r;
+}
+
+// Point sink of one op.  Fill mode converts to Fixed and drops a point equal
+// to its predecessor (fig.rs:436-440); wide mode keeps raw f32 + width for the
+// host stroker.
+template <bool WIDE, bool EMIT>
+struct OpSink {
+    uint32_t n = 0;
+    bool force;
+    int32_t px = 0, py = 0;
+    Vtx *vout = nullptr;
+    float *wout = nullptr;
+    uint32_t sub = 0, job = 0;
+    __device__ __forceinline__ void put(WPt q) {
+        if (WIDE) {
+            if (EMIT) {
+                wout[3 * (size_t)n] = q.p.x;
+                wout[3 * (size_t)n + 1] = q.p.y;
+                wout[3 * (size_t)n + 2] = q.w;
+            }
+            n++;
+        } else {
+            int32_t fx = fx_from_f32(q.p.x), fy = fx_from_f32(q.p.y);
+            if (force || fx != px || fy != py) {
+                if (EMIT) vout[n] = {fx, fy, sub, job};
+                n++;
+            }
+            force = false;
+            px = fx;
+            py = fy;
+        }
+    }
+};
+
+template <bool WIDE, bool EMIT>
+__device__ void flatten_quad(WPt a, WPt b, WPt c, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:248-265
+    WPt sb[MAX_DEPTH], sc[MAX_DEPTH];
+    uint8_t sd[MAX_DEPTH];
+    int sp = 0, depth = 0;
+    for (;;) {
+        WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), ab_bc = wmid<WIDE>(ab, bc), ac = wmid<WIDE>(a, c);
+        if (pointy::distance_sq(ab_bc.p, ac.p) <= tol_sq || depth >= MAX_DEPTH) {
+            sink.put(c);
+            if (sp == 0) break;
+            sp--;
+            a = c; b = sb[sp]; c = sc[sp]; depth = sd[sp];
+        } else {
+            sb[sp] = bc; sc[sp] = c; sd[sp] = (uint8_t)(depth + 1); sp++;
+            b = ab; c = ab_bc; depth++;
+        }
+    }
+}
+
+template <bool WIDE, bool EMIT>
+__device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:311-332
+    WPt sb[MAX_DEPTH], sc[MAX_DEPTH], sdd[MAX_DEPTH];
+    uint8_t sd[MAX_DEPTH];
+    int sp = 0, depth = 0;
+    for (;;) {
+        WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), cd = wmid<WIDE>(c, d);
+        WPt ab_bc = wmid<WIDE>(ab, bc), bc_cd = wmid<WIDE>(bc, cd);
+        WPt pe = wmid<WIDE>(ab_bc, bc_cd), ad = wmid<WIDE>(a, d);
+        if (pointy::distance_sq(pe.p, ad.p) <= tol_sq || depth >= MAX_DEPTH) {
+            sink.put(d);
+            if (sp == 0) break;
+            sp--;
+            a = d; b = sb[sp]; c = sc[sp]; d = sdd[sp]; depth = sd[sp];
+        } else {
+            sb[sp] = bc_cd; sc[sp] = cd; sdd[sp] = d; sd[sp] = (uint8_t)(depth + 1); sp++;
+            b = ab; c = ab_bc; d = pe; depth++;
+        }
+    }
+}
+
+// One thread per PathOp.  Pass 1 (EMIT=false) counts the vertices the op
+// contributes; after the scan, pass 2 (EMIT=true) repeats the identical
+// subdivision and writes them at the scanned offset, so the output order is
+// the reference's depth-first order.
+template <bool WIDE, bool EMIT>
+__global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
+                                                   const float *__restrict__ opw, SumHead *__restrict__ cnt,
+                                                   const SumHead *__restrict__ off, Vtx *__restrict__ vout,
+                                                   float *__restrict__ wout, const Counters *__restrict__ C) {
+    if (EMIT && C && C->overflow) return;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
+        const ftl_path_op op = ops[i];
+        OpSink<WIDE, EMIT> sink;
+        uint32_t j = job_of_op(jobs, P.n_jobs, i);
+        const JobDesc &jd = jobs[j];
+        bool starts = false;
+        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+            PenInfo pi = find_pen(ops, jd.op_begin, i);
+            starts = pi.starts_sub || op.tag == FTL_OP_MOVE;  // Move closes the current sub-figure (plotter.rs:210)
+            float e[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+            sink.force = starts;
+            if (EMIT) {
+                SumHead o = off[i];
+                if (WIDE) sink.wout = wout + 3 * (size_t)o.sum;
+                else {
+                    sink.vout = vout + o.sum;
+                    sink.sub = starts ? o.sum : o.head;
+                    sink.job = j;
+                }
+            }
+            float w_pen = WIDE ? opw[2 * (size_t)i] : 0.0f, w_now = WIDE ? opw[2 * (size_t)i + 1] : 0.0f;
+            WPt a = {pointy::transform(e, pi.pen), w_pen};
+            if (!WIDE && !starts) {
+                sink.px = fx_from_f32(a.p.x);
+                sink.py = fx_from_f32(a.p.y);
+            }
+            if (op.tag == FTL_OP_MOVE || op.tag == FTL_OP_LINE) {  // plotter.rs:208-224
+                sink.put({pointy::transform(e, {op.v[0], op.v[1]}), w_now});
+            } else if (op.tag == FTL_OP_QUAD) {  // plotter.rs:233-242
+                WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), WIDE ? (w_pen + w_now) / 2.0f : 0.0f};
+                WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w_now};
+                flatten_quad<WIDE, EMIT>(a, b, c, jd.tol_sq, sink);
+            } else {  // plotter.rs:286-305; float_lerp(a,b,t) = b + (a-b)*t (geom.rs:14-16)
+                float w0 = WIDE ? w_now + (w_pen - w_now) * (1.0f / 3.0f) : 0.0f;
+                float w1 = WIDE ? w_now + (w_pen - w_now) * (2.0f / 3.0f) : 0.0f;
+                WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), w0};
+                WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w1};
+                WPt d = {pointy::transform(e, {op.v[4], op.v[5]}), w_now};
+                flatten_cubic<WIDE, EMIT>(a, b, c, d, jd.tol_sq, sink);
+            }
+        }
+        if (!EMIT) cnt[i] = {sink.n, starts ? 0u : NONE32};
+    }
+}
+
+// ---------------------------------------------------------------------------
+// (b) edge prep
+// ---------------------------------------------------------------------------
+// Sub-figure closing (fig.rs:373-383): the last vertex of a sub-figure is
+// dropped when it equals the first.  Dropped vertices stay in the array as
+// holes and are skipped.
+__device__ __forceinline__ bool vtx_is_last(const Vtx *V, uint32_t nv, uint32_t k) { return k + 1 >= nv || V[k + 1].sub == k + 1; }
+__device__ __forceinline__ bool vtx_same(const Vtx &a, const Vtx &b) { return a.x == b.x && a.y == b.y; }
+__device__ __forceinline__ unsigned long long vtx_key(const Vtx &v) {  // (y,x) order of fig.rs:464-472
+    return ((unsigned long long)((uint32_t)v.y ^ 0x80000000u) << 32) | (unsigned long long)((uint32_t)v.x ^ 0x80000000u);
+}
+// Forward ring neighbour of a live vertex (fig.rs:143-152)
+__device__ __forceinline__ uint32_t vtx_next_fwd(const Vtx *V, uint32_t nv, uint32_t k, const Vtx &v, bool last) {
+    if (last) return v.sub;
+    if (vtx_is_last(V, nv, k + 1) && vtx_same(V[k + 1], V[v.sub])) return v.sub;
+    return k + 1;
+}
+
+__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    JobState s;
+    s.top_key = ~0ull; s.top_vid = NONE32; s.dir = 0; s.top_row = 0; s.first_row = 0x7FFFFFFF; s.shift = 0;
+    s.vtx_begin = off ? off[jobs[j].op_begin].sum : 0u;
+    s.vtx_end = off ? off[jobs[j].op_end].sum : 0u;
+    s.pad[0] = s.pad[1] = s.pad[2] = 0;
+    JS[j] = s;
+}
+
+// Top-left vertex, pass 1: minimum (y,x) over the live vertices of each job (fig.rs:493-494).
+__global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        if (vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub])) continue;
+        atomicMin(&JS[v.job].top_key, vtx_key(v));
+    }
+}
+// Pass 2: the stable sort keeps the lowest vertex id among equal keys; also
+// records each sub-figure's last live vertex for the Reverse ring neighbour.
+__global__ void __launch_bounds__(256) vtx_topvid(const Vtx *__restrict__ V, Counters *__restrict__ C, JobState *JS,
+                                                  uint32_t *__restrict__ sub_last) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        bool last = vtx_is_last(V, nv, k);
+        bool pop = last && vtx_same(v, V[v.sub]);
+        if (last) sub_last[v.sub] = pop ? (k > v.sub ? k - 1 : NONE32) : k;
+        if (pop) atomicAdd(&C->n_popped, 1u);
+        else if (vtx_key(v) == JS[v.job].top_key) atomicMin(&JS[v.job].top_vid, k);
+    }
+}
+
+// Fig::get_dir on the top-left vertex + top_row (fig.rs:402-411,495-496)
+__global__ void job_finalize(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS, const uint32_t *__restrict__ sub_last,
+                             uint32_t n_jobs) {
+    uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_jobs) return;
+    uint32_t k = JS[j].top_vid;
+    if (k == NONE32) return;  // no vertices: first_row stays INT_MAX, nothing is drawn (fig.rs:491)
+    const uint32_t nv = C->nv;
+    Vtx v = V[k];
+    uint32_t f = vtx_next_fwd(V, nv, k, v, vtx_is_last(V, nv, k));
+    uint32_t r = k > v.sub ? k - 1 : sub_last[v.sub];
+    Vtx pf = V[f], pr = V[r];
+    fx_t ax = fx_sub(pr.x, v.x), ay = fx_sub(pr.y, v.y);
+    fx_t bx = fx_sub(pf.x, v.x), by = fx_sub(pf.y, v.y);
+    bool widdershins = fx_mul(ax, by) > fx_mul(bx, ay);  // fig.rs:116-119
+    int32_t top = fx_to_i32(v.y);
+    JS[j].dir = widdershins ? 0 : 1;
+    JS[j].top_row = top;
+    JS[j].first_row = top > 0 ? top : 0;
+    JS[j].shift = top < 0 ? top : 0;
+}
+
+// Edge::new (fig.rs:179-210), with rows already mapped to raster rows and the
+// sign against the figure direction resolved.
+__device__ __forceinline__ EdgeRec make_edge(const Vtx &p0, const Vtx &p1, uint32_t job, uint32_t dd, const JobState &js) {
+    EdgeRec e;
+    fx_t dx = fx_sub(p1.x, p0.x), dy = fx_sub(p1.y, p0.y);
+    e.step_pix = dx != 0 ? fx_min(fx_abs(fx_div(dy, dx)), FX_ONE) : 0;
+    e.inv_slope = fx_div(dx, dy);
+    fx_t y_bot = fx_sub(fx_floor(fx_add(p0.y, FX_ONE)), p0.y);
+    e.x_bot0 = fx_add(p0.x, fx_mul(e.inv_slope, y_bot));
+    e.ry0 = fx_to_i32(p0.y) - js.shift;
+    e.ry1 = fx_to_i32(p1.y) - js.shift;
+    e.fr = (uint32_t)fx_fract(p0.y) | ((uint32_t)fx_fract(p1.y) << 16);
+    e.job = job;
+    e.flags = 1u | ((dd != (uint32_t)js.dir ? 1u : 0u) << 1);
+    return e;
+}
+
+// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most
+// one edge, directed from its upper to its lower vertex.  This is the same
+// set of edges the reference creates in update_edges/add_edge (fig.rs:576-600)
+// when it visits both neighbours of every vertex.
+__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, const Counters *__restrict__ C, const JobState *__restrict__ JS,
+                                                  EdgeRec *__restrict__ E) {
+    const uint32_t nv = C->nv;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
+        Vtx v = V[k];
+        bool last = vtx_is_last(V, nv, k);
+        bool pop = last && vtx_same(v, V[v.sub]);
+        EdgeRec e;
+        e.flags = 0;
+        if (!pop) {
+            uint32_t w = vtx_next_fwd(V, nv, k, v, last);
+            if (w != k) {
+                Vtx q = V[w];
+                if (q.y > v.y) e = make_edge(v, q, v.job, 0u, JS[v.job]);        // v is upper; w is v's Forward neighbour
+                else if (q.y < v.y) e = make_edge(q, v, v.job, 1u, JS[v.job]);   // w is upper; v is w's Reverse neighbour
+            }
+        }
+        if (e.flags) E[k] = e;
+        else E[k].flags = 0;
+    }
+}
+
+// Band range of an edge inside this device's rows; returns false if none.
+__device__ __forceinline__ bool edge_bands(const EdgeRec &e, const Params &P, uint32_t *b0, uint32_t *b1) {
+    int32_t lo = e.ry0, hi = e.ry1;  // ry0 >= first_row >= 0 by construction
+    if (lo < (int32_t)P.row_begin) lo = (int32_t)P.row_begin;
+    if (hi > (int32_t)P.row_end - 1) hi = (int32_t)P.row_end - 1;
+    if (lo > hi) return false;
+    *b0 = (uint32_t)(lo - (int32_t)P.row_begin) >> P.log2R;
+    *b1 = (uint32_t)(hi - (int32_t)P.row_begin) >> P.log2R;
+    return true;
+}
+
+// Conservative range of row windows an edge can write to on the rows [ra, rb] of one band (both
+// inside the edge's own rows).  The span of a row is linear in the row, so the extremes are at the
+// two end rows, evaluated as edge_row_setup does; the scatter loop can run at most |dx/dy| + 2 cells
+// past the leftmost one.  Anything that would wrap 32-bit arithmetic falls back to "all windows".
+__device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32_t rb, const Params &P, uint32_t *w0, uint32_t *w1) {
+    *w0 = 0;
+    *w1 = P.n_win - 1;
+    if (P.n_win == 1) return;
+    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    const int64_t slope = e.inv_slope;
+    for (int t = 0; t < 2; t++) {
+        const int32_t r = t ? rb : ra;
+        const int64_t x_bot = (int64_t)e.x_bot0 + (int64_t)(r - e.ry0) * slope;
+        const int64_t x_top = x_bot - slope;
+        if (x_bot != (int32_t)x_bot || x_top != (int32_t)x_top) return;
+        lo = min(lo, min(x_bot, x_top));
+        hi = max(hi, max(x_bot, x_top));
+    }
+    const int64_t run = (slope < 0 ? -slope : slope) >> 16;
+    int64_t lo_pix = (lo >> 16) - 1, hi_pix = (hi >> 16) + run + 3;
+    const int64_t wmax = (int64_t)P.W - 1;
+    lo_pix = lo_pix < 0 ? 0 : (lo_pix > wmax ? wmax : lo_pix);
+    hi_pix = hi_pix < 0 ? 0 : (hi_pix > wmax ? wmax : hi_pix);
+    const uint32_t win_cells = P.win_chunks * 512u;
+    *w0 = (uint32_t)lo_pix / win_cells;
+    *w1 = (uint32_t)hi_pix / win_cells;
+}
+
+// Counting sort of edges by (job, row band, row window): pass FILL=false counts, pass FILL=true
+// writes edge ids at the scanned offsets.  Short edges are handled by their own thread; an edge
+// crossing many bands is spread over the warp.  Jobs with at most DIRECT_MAX edge slots are not
+// binned at all.
+template <bool FILL>
+__device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t tile, uint32_t band, const Params &P, uint32_t *tile_count,
+                                        const uint32_t *tile_off, uint32_t *entries) {
+    const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
+    const int32_t ra = max(e.ry0, row0), rb = min(min(e.ry1, row0 + (int32_t)P.R - 1), (int32_t)P.row_end - 1);
+    uint32_t w0, w1;
+    edge_windows(e, ra, rb, P, &w0, &w1);
+    for (uint32_t w = w0; w <= w1; w++) {
+        const uint32_t bin = tile * P.n_win + w;
+        const uint32_t slot = atomicAdd(&tile_count[bin], 1u);
+        if (FILL) entries[tile_off[bin] + slot] = k;
+    }
+}
+template <bool FILL>
+__global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
+                                                 const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
+                                                 const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ entries) {
+    if (FILL && C->overflow) return;
+    const uint32_t nv = C->nv;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t span = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < nv; k0 += span) {
+        uint32_t k = k0 + lane;
+        uint32_t b0 = 0, nb = 0, tbase = 0;
+        EdgeRec e;
+        e.flags = 0;
+        if (k < nv) {
+            e = E[k];
+            uint32_t b1;
+            if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
+                const JobState &js = JS[e.job];
+                if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
+                    nb = b1 - b0 + 1;
+                    tbase = e.job * P.n_bands;
+                }
+            }
+        }
+        if (nb > 0 && nb <= 4)
+            for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k, tbase + b, b, P, tile_count, tile_off, entries);
+        uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
+        while (tall) {
+            int src = __ffs(tall) - 1;
+            tall &= tall - 1;
+            uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src);
+            uint32_t stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
+            const EdgeRec es = E[k0 + src];
+            for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + src, stb + sb0 + b, sb0 + b, P, tile_count, tile_off, entries);
+        }
+    }
+}
