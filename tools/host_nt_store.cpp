@@ -1,3 +1,6 @@
+// host_nt_store.cpp — streaming-store (non-temporal) bandwidth of the host with 4/8/12/16 threads and 128/256/512-bit
+// stores: the ceiling of the packed read-back's expansion (Engine::copy_out), which writes every raster byte once.
+// Build: g++ -O2 -pthread -o host_nt_store host_nt_store.cpp
 #include <immintrin.h>
 #include <thread>
 #include <vector>
