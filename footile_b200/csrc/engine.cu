@@ -904,7 +904,11 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
     unsigned nt = std::min(8u, std::thread::hardware_concurrency());  // the expansion is memory-bound well before 8 threads
     if (const char *ev = getenv("FTL_HOST_THREADS")) nt = (unsigned)std::max(1, atoi(ev));
     nt = std::max(1u, std::min(nt, 64u));
-    const size_t PIECE = 256u << 20;
+    // About eight pieces per read: each piece costs two stream synchronisations and a set of host threads
+    // (~0.3 ms), a pipeline of N pieces exposes 1/N of the staging + expansion at its ends (4 GiB: 256 MiB
+    // pieces 128 Gpx/s, 512 MiB 150, 1 GiB 138).
+    size_t PIECE = std::min<size_t>(512u << 20, std::max<size_t>(64u << 20, ((bytes / 8) + (1u << 20) - 1) & ~(size_t)((1u << 20) - 1)));
+    if (const char *ev = getenv("FTL_PIECE_MB")) PIECE = (size_t)std::max(16, std::min(1024, atoi(ev))) << 20;  // tuning knob
     std::thread worker;
     int rc = FTL_OK;
     for (size_t at = 0, k = 0; at < bytes && rc == FTL_OK; at += PIECE, k++) {
