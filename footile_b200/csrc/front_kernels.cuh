@@ -226,10 +226,28 @@ __global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, c
 // Top-left vertex, pass 1: minimum (y,x) over the live vertices of each job (fig.rs:493-494).
 __global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS) {
     const uint32_t nv = C->nv;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
-        Vtx v = V[k];
-        if (vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub])) continue;
-        atomicMin(&JS[v.job].top_key, vtx_key(v));
+    const uint32_t stride = gridDim.x * blockDim.x;
+    // whole warps iterate together (k0 is the warp's first vertex): vertices are stored job after job, so a
+    // warp usually holds one job and issues ONE atomic for its 32 keys (one raster with 10 M vertices would
+    // otherwise serialise 10 M atomics on one address)
+    for (uint32_t k0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; k0 < nv; k0 += stride) {
+        const uint32_t k = k0 + (threadIdx.x & 31u);
+        unsigned long long key = ~0ull;
+        uint32_t job = NONE32;
+        if (k < nv) {
+            const Vtx v = V[k];
+            job = v.job;
+            if (!(vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub]))) key = vtx_key(v);
+        }
+        const uint32_t job0 = __shfl_sync(0xFFFFFFFFu, job, 0);
+        if (__all_sync(0xFFFFFFFFu, job == job0 || job == NONE32)) {
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+                const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, d);
+                key = o < key ? o : key;
+            }
+            if ((threadIdx.x & 31u) == 0 && key != ~0ull) atomicMin(&JS[job0].top_key, key);
+        } else if (key != ~0ull) atomicMin(&JS[job].top_key, key);
     }
 }
 // Pass 2: the stable sort keeps the lowest vertex id among equal keys; also
