@@ -885,7 +885,7 @@ static void unpack_parallel(uint8_t *dst, const uint8_t *code, const uint32_t *b
 }
 
 // Device -> host copy of rasters.  Large copies are packed on the device (see pack_classify),
-// moved in 256 MiB pieces, and expanded by host threads while the next piece is in flight.
+// moved in about eight pieces per read (64-512 MiB), and expanded by host threads while the next piece is in flight.
 int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
     ENSURE_INIT();
     Impl &m = *impl_;
