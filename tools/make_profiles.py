@@ -65,6 +65,10 @@ def main():
         traffic["heptagram_rgba8p"] = ncu_summary(os.path.join(G, "prof_tiles_rgba_%s.ncu-rep" % rnd), os.path.join(P, "%s_raster_tiles_heptagram_rgba8p_ncu.csv" % rnd))
     if os.path.exists(os.path.join(G, "prof_tiles_b512_%s.ncu-rep" % rnd)):
         traffic["batch512"] = ncu_summary(os.path.join(G, "prof_tiles_b512_%s.ncu-rep" % rnd), os.path.join(P, "%s_raster_tiles_batch512_ncu.csv" % rnd))
+    for wl in ("strokes4k", "fishy256"):
+        rep = os.path.join(G, "prof_tiles_%s_%s.ncu-rep" % (wl, rnd))
+        if os.path.exists(rep):
+            traffic[wl + ("_rgba8p" if wl == "strokes4k" else "")] = ncu_summary(rep, os.path.join(P, "%s_raster_tiles_%s_ncu.csv" % (rnd, wl)))
     traffic["source"] = "profiles/%s_raster_tiles_*_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum of one raster_tiles launch (ncu --set full)" % rnd
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     for name in ("launches_%s.csv" % rnd, "launches_b512_%s.csv" % rnd):
