@@ -415,6 +415,17 @@ int ftl_debug_flatten(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, int3
     return FTL_OK;
     GUARD_END
 }
+int ftl_debug_edges(ftl_plotter *p, int32_t *rec, size_t cap, size_t *n_edges) {
+    GUARD_BEGIN
+    if (!p || !n_edges || (!rec && cap)) return bad("null argument");
+    std::vector<int32_t> v;
+    int rc = p->eng.debug_edges(&v);
+    if (rc) return rc;
+    *n_edges = v.size() / 6;
+    memcpy(rec, v.data(), std::min(v.size(), cap * 6) * sizeof(int32_t));
+    return FTL_OK;
+    GUARD_END
+}
 int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]) {
     GUARD_BEGIN
     if (!p || !info) return bad("null argument");

@@ -651,6 +651,33 @@ int Engine::last_fill_info(FillInfo *info) {
     return FTL_OK;
 }
 
+int Engine::debug_edges(std::vector<int32_t> *out) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    out->clear();
+    if (!m.have_jobs) return FTL_OK;
+    {
+        int rc = resolve_pending(m);
+        if (rc) return rc;
+    }
+    JobState js;
+    CK(cudaStreamSynchronize(m.st));
+    CK(cudaMemcpy(&js, m.jstate.p, sizeof(js), cudaMemcpyDeviceToHost));
+    const uint32_t n = js.vtx_end - js.vtx_begin;
+    if (n == 0) return FTL_OK;
+    std::vector<EdgeRec> e(n);
+    CK(cudaMemcpy(e.data(), (const EdgeRec *)m.edges.p + js.vtx_begin, (size_t)n * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
+    for (const EdgeRec &r : e) {
+        if (!(r.flags & 1u)) continue;
+        // raster row -> geometry row: + shift; the fractions are kept beside the rows
+        const int32_t y_upper = (int32_t)(((uint32_t)(r.ry0 + js.shift) << 16) | (r.fr & 0xFFFFu));
+        const int32_t y_lower = (int32_t)(((uint32_t)(r.ry1 + js.shift) << 16) | (r.fr >> 16));
+        const int32_t rec[6] = {r.x_bot0, r.inv_slope, r.step_pix, y_upper, y_lower, (r.flags & 2u) ? -1 : 1};
+        out->insert(out->end(), rec, rec + 6);
+    }
+    return FTL_OK;
+}
+
 int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, std::vector<int32_t> *xy,
                           std::vector<uint32_t> *subs) {
     ENSURE_INIT();

@@ -73,6 +73,9 @@ public:
     int debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops,
                       std::vector<int32_t> *xy, std::vector<uint32_t> *subs);
     int last_fill_info(FillInfo *info);
+    // Probe: the edge records stage (b) built for job 0 of the last fill, 6 values per edge:
+    // x_bot, inv_slope, step_pix, y_upper, y_lower (Fixed), sign (+1 / -1) (fig.rs:47-66,179-210,286).
+    int debug_edges(std::vector<int32_t> *out);
     int accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows);
     int checksums(const void *rasters, size_t raster_bytes, uint32_t count, uint64_t *out);
 

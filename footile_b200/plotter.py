@@ -198,6 +198,17 @@ class Plotter:
         _lib.check(_lib.lib().ftl_debug_last_fill(self._handle, info.ctypes.data))
         return {"dir": int(info[0]), "top_row": int(info[1]), "n_points": int(info[2])}
 
+    def debug_edges(self):
+        """(n, 6) int32 edges of the last fill: x_bot, inv_slope, step_pix, y_upper, y_lower, sign (stage (b) probe)."""
+        n = C.c_size_t(0)
+        cap = 1024
+        while True:
+            out = np.zeros((cap, 6), dtype=np.int32)
+            _lib.check(_lib.lib().ftl_debug_edges(self._handle, out.ctypes.data, cap, C.byref(n)))
+            if n.value <= cap:
+                return out[:n.value]
+            cap = n.value
+
     def debug_stroke_ops(self, ops):
         a = as_ops(ops)
         cap = 1 << 16

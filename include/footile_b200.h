@@ -171,6 +171,10 @@ int ftl_debug_flatten(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, int3
                       size_t *n_points, uint32_t *subs, size_t sub_cap, size_t *n_subs);
 /* (dir, top_row, n_points) of the last fill (fig.rs:495-496); dir 0 = Forward. */
 int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]);
+/* Stage (b) probe: the edges of the last ftl_fill (Edge::new, fig.rs:179-210, with the winding sign of fig.rs:286), in no
+ * particular order: 6 int32 per edge = x_bot, inv_slope, step_pix, y_upper, y_lower (Fixed 16.16), sign (+1/-1).
+ * Writes min(*n_edges, cap) records. */
+int ftl_debug_edges(ftl_plotter *p, int32_t *rec, size_t cap, size_t *n_edges);
 /* The outline ops Plotter::stroke hands to fill (stroker.rs:239-247). */
 int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
                          size_t *n_out);

@@ -95,6 +95,8 @@ def lib():
         L.orc_batch_fill_checksums.restype = None
         L.orc_batch_fill_checksums.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                                C.c_void_p, C.c_uint32, C.c_void_p]
+        L.orc_debug_edges.restype = C.c_size_t
+        L.orc_debug_edges.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t]
         L.orc_get_pen_width.restype = C.c_float
         L.orc_get_pen_width.argtypes = [C.c_void_p]
         L.orc_debug_flatten.restype = C.c_size_t
@@ -283,6 +285,17 @@ class Plotter:
             if npts <= cap and ns.value <= cap:
                 return xy[:npts].copy(), subs[: ns.value].copy()
             cap = max(npts, ns.value)
+
+    def debug_edges(self, ops):
+        """(n, 6) int32: x_bot, inv_slope, step_pix, y_upper, y_lower, sign of every edge Fig::fill builds (fig.rs:179-210,286)."""
+        a, p, n_ops = _ops(ops)
+        cap = 1 << 14
+        while True:
+            out = np.zeros((cap, 6), dtype=np.int32)
+            n = lib().orc_debug_edges(self._h, p, n_ops, out.ctypes.data, cap)
+            if n <= cap:
+                return out[:n]
+            cap = n
 
     def debug_flatten_wide(self, ops):
         a, p, n = _ops(ops)

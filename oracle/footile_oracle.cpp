@@ -833,6 +833,40 @@ size_t orc_debug_stroke_ops(void *h, const orc_path_op *ops, size_t n, orc_path_
     return o.size();
 }
 
+// Probe: the edges Fig::fill builds for these ops (Edge::new, fig.rs:179-210), each with the sign
+// Edge::scan_area gives it (fig.rs:286: +1 when the edge runs with the figure's direction), in ring order.
+// 6 int32 per edge: x_bot, inv_slope, step_pix, y_upper, y_lower, sign.  Returns the number of edges.
+size_t orc_debug_edges(void *h, const orc_path_op *ops, size_t n, int32_t *rec, size_t cap) {
+    Plotter *p = (Plotter *)h;
+    FigSink sink(p->vid_cap);
+    Flattener(p->st, sink).run((const PathOp *)ops, n);
+    sink.fig.close();
+    const Fig &fig = sink.fig;
+    const std::vector<FxPt> &P = fig.points;
+    const uint32_t np = (uint32_t)P.size();
+    if (np == 0) return 0;
+    uint32_t v0 = 0;
+    for (uint32_t v = 1; v < np; v++)
+        if (P[v].y < P[v0].y || (P[v].y == P[v0].y && P[v].x < P[v0].x)) v0 = v;
+    Ring ring(fig);
+    FxPt q = P[v0], pf = P[ring.next(v0, FWD)], pr = P[ring.next(v0, REV)];
+    FxPt a = {fx_sub(pr.x, q.x), fx_sub(pr.y, q.y)}, b = {fx_sub(pf.x, q.x), fx_sub(pf.y, q.y)};
+    const int dir = widdershins(a, b) ? FWD : REV;
+    size_t ne = 0;
+    for (uint32_t v = 0; v < np; v++)
+        for (int dd = FWD; dd <= REV; dd++) {
+            uint32_t w = ring.next(v, dd);
+            if (w == v || !(P[w].y > P[v].y)) continue;
+            Edge e = edge_new(w, P[v], P[w], dd);
+            if (ne < cap) {
+                int32_t *r = rec + 6 * ne;
+                r[0] = e.x_bot; r[1] = e.inv_slope; r[2] = e.step_pix; r[3] = e.y_upper; r[4] = e.y_lower; r[5] = dd == dir ? 1 : -1;
+            }
+            ne++;
+        }
+    return ne;
+}
+
 // Timed multi-threaded batch (bench.py cpu_baseline / --impl reference): job j = ops[offs[j], offs[j+1])
 // filled into its own pre-allocated w x h raster with rules[j], transforms[6j..] (or identity), colour
 // clr; jobs are dealt round-robin to n_threads std::threads, one Plotter per job (the reference is

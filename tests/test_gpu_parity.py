@@ -144,6 +144,23 @@ def test_flatten_vertices_bit_exact(seed):
         assert np.array_equal(gx, ox)
 
 
+# ---- (b): Edge::new on the device against the reference's (fig.rs:179-210), with the winding sign (fig.rs:286) ----
+@pytest.mark.parametrize("seed", range(4))
+def test_edges_bit_exact(seed):
+    rng = np.random.default_rng(400 + seed)
+    for it in range(12):
+        size = int(rng.choice([16, 64, 300, 2000]))
+        path = random_path(rng, size, int(rng.integers(2, 24)))
+        rule = int(rng.integers(0, 2))
+        g, o = both(size, size, Format.Matte8)
+        g.fill(rule, path, (255,))
+        got = g.debug_edges()
+        exp = o.debug_edges(path)
+        assert got.shape == exp.shape, (it, got.shape, exp.shape)
+        key = lambda a: a[np.lexsort(a.T[::-1])]  # the device builds one edge per ring slot, the oracle walks the ring: compare as sets
+        assert np.array_equal(key(got), key(exp)), "it %d" % it
+
+
 def test_flatten_degenerate_sequences():
     # de-dup, closing-point pop, Move/Move, Line right after Close, leading Close
     cases = [
