@@ -446,6 +446,34 @@ def main():
     h2d = int(wl["ops"].nbytes + batch * 64)
     d2h = int(batch * raster_bytes)
 
+    # ---- config 3 only: the public call itself, Plotter::stroke (device flatten -> host stroker -> device fill) ----
+    api_stroke = None
+    if args.workload == "strokes4k" and rank == 0:
+        from footile_b200 import scenes as _scenes
+        paths = list(_scenes.stroke_scenes(30.0).values())
+        bg = np.tile(np.array([64, 128, 64, 255], dtype=np.uint8), (H, W))
+        plotters = []
+        for _ in paths:
+            pl = fb.Plotter(fb.Raster(W, H, Format.Rgba8p, bg), device=local_rank)
+            pl.set_join(fb.JoinStyle.Round)
+            plotters.append(pl)
+        for pl, path in zip(plotters, paths):  # warm-up
+            pl.stroke(path, (255, 255, 0, 255))
+            pl.sync()
+        reps = 3
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            for pl, path in zip(plotters, paths):
+                pl.stroke(path, (255, 255, 0, 255))
+            for pl in plotters:
+                pl.sync()
+        dt = time.perf_counter() - t0
+        n_calls = reps * len(paths)
+        api_stroke = {"calls": n_calls, "ms_per_stroke": 1e3 * dt / n_calls, "strokes_per_s": n_calls / dt,
+                      "value": px_step / batch * n_calls / dt / 1e9, "unit": unit,
+                      "what": "ftl_stroke through the Plotter mirror, one call per scene, rasters stay in HBM: device flatten, D2H, host stroker, H2D, device fill"}
+        del plotters
+
     # ---- roofline of the tile kernel (pixel term: 1 B/px store for Matte8) ----
     peak, peak_kind = peaks()
     roof = None
@@ -489,7 +517,8 @@ def main():
                           "dtype": "i32 fixed-point 16.16 / u8", "data": "synthetic", "config": config, "paths_per_s": paths_per_s,
                           "clocks": clocks, "e2e": {"value": e2e_val, "unit": unit, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                                                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps},
-                          "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu}))
+                          "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
+                          **({"plotter_stroke": api_stroke} if api_stroke else {})}))
     if world > 1:
         dist.destroy_process_group()
 
