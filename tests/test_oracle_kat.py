@@ -248,3 +248,39 @@ def test_plotter_overlapping_smoke():
         p = oracle.Plotter(16, 16, oracle.MATTE8, orderfree=orderfree)
         p.fill(oracle.NONZERO, path, (255,))
         assert p.raster().shape == (16, 16)
+
+
+def test_batch_checksums_match_the_fold_of_ftl_batch_checksums():
+    """orc_batch_fill_checksums (used by the full-size config 4 parity test) = 256 interleaved FNV-1a lanes folded in order."""
+    from footile_b200 import scenes
+    ops, offs, rules = scenes.random_curve_paths(7, 5, size=512)
+    sums = oracle.batch_fill_checksums(512, 512, oracle.MATTE8, ops, offs, rules=rules, clr=(255,), threads=2)
+    prime = np.uint64(0x100000001b3)
+    for j in range(5):
+        o = oracle.Plotter(512, 512, oracle.MATTE8)
+        o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
+        lanes = np.ascontiguousarray(o.raster()).reshape(-1, 256).astype(np.uint64)
+        h = np.full(256, 0xcbf29ce484222325, dtype=np.uint64)
+        with np.errstate(over="ignore"):
+            for row in lanes:
+                h = (h ^ row) * prime
+            g = np.uint64(0xcbf29ce484222325)
+            for v in h:
+                for k in range(8):
+                    g = (g ^ ((v >> np.uint64(8 * k)) & np.uint64(0xFF))) * prime
+        assert int(g) == int(sums[j]), j
+
+
+def test_debug_edges_of_a_triangle():
+    """Edge::new (fig.rs:179-210) on the fig_9x1 triangle (0,0)(9,1)(0,1): one shallow edge and one vertical one."""
+    o = oracle.Plotter(9, 1, oracle.MATTE8)
+    from footile_b200 import Path2D
+    path = Path2D().absolute().move_to(0.0, 0.0).line_to(9.0, 1.0).line_to(0.0, 1.0).close().finish()
+    e = o.debug_edges(path)
+    assert e.shape == (2, 6)  # the horizontal side builds no edge (fig.rs:589: only edges going down)
+    one = 1 << 16
+    by_slope = {int(r[1]): r for r in e}
+    shallow, vertical = by_slope[9 * one], by_slope[0]
+    assert int(shallow[2]) == one // 9 and int(shallow[0]) == 9 * one and int(shallow[3]) == 0 and int(shallow[4]) == one
+    assert int(vertical[2]) == 0 and int(vertical[0]) == 0 and int(vertical[3]) == 0 and int(vertical[4]) == one
+    assert int(shallow[5]) == -int(vertical[5])  # the two sides wind opposite ways
