@@ -481,7 +481,11 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
         uint32_t nv_hint = cap_v;
         if (P.n_ops > 0) {
             flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
-            int r2 = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials);
+            const bool small_ops = !sync_sizes && P.n_ops <= SCAN_SMALL_MAX;  // one-block scan + the capacity guard in one launch
+            int r2 = FTL_OK;
+            if (small_ops) {
+                scan_small<SumHeadOp><<<1, SCAN_THREADS, 0, st>>>((const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, FinVertexCount{d_cnt, cap_v}); LAUNCHED();
+            } else r2 = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials);
             if (r2) return r2;
             if (sync_sizes) {
                 CK(cudaMemcpyAsync(m.pin_small.p, &((SumHead *)m.off.p)[P.n_ops].sum, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -494,7 +498,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 cap_v = (uint32_t)std::min<size_t>({m.vtx.cap / sizeof(Vtx), m.edges.cap / sizeof(EdgeRec), m.sub_last.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF});
                 nv_hint = nv;
             }
-            set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED();
+            if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
             flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt); LAUNCHED();
         }
         init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
@@ -506,7 +510,11 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
         if (P.all_direct) return FTL_OK;  // every tile scans its job's own edges: nothing to bin
         CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
         bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
-        int r3 = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_bins, (uint32_t *)m.toff.p, m.tpart);
+        const bool small_bins = !sync_sizes && P.n_bins <= SCAN_SMALL_MAX;
+        int r3 = FTL_OK;
+        if (small_bins) {
+            scan_small<AddU32><<<1, SCAN_THREADS, 0, st>>>((const uint32_t *)m.tcount.p, P.n_bins, (uint32_t *)m.toff.p, FinEntryCount{d_cnt, cap_e}); LAUNCHED();
+        } else r3 = run_scan<AddU32>(st, (const uint32_t *)m.tcount.p, P.n_bins, (uint32_t *)m.toff.p, m.tpart);
         if (r3) return r3;
         if (sync_sizes) {
             CK(cudaMemcpyAsync(m.pin_small.p, &((uint32_t *)m.toff.p)[P.n_bins], sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
@@ -515,7 +523,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
             if ((r3 = m.entries.ensure((size_t)(n_entries ? n_entries : 1) * sizeof(uint32_t), st))) return r3;
             cap_e = (uint32_t)std::min<size_t>(m.entries.cap / sizeof(uint32_t), (size_t)0x7FFFFFFF);
         }
-        set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_bins, cap_e); LAUNCHED();
+        if (!small_bins) { set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_bins, cap_e); LAUNCHED(); }
         CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
         bin_edges<true><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
                                             (uint32_t *)m.entries.p); LAUNCHED();

@@ -25,6 +25,32 @@ __global__ void set_entry_count(Counters *C, const uint32_t *__restrict__ toff, 
     }
 }
 
+// the same guards as functors for scan_small (the scan's grand total is the count)
+struct FinVertexCount {
+    Counters *C;
+    uint32_t cap_v;
+    __device__ void operator()(const SumHead &total) const {
+        uint32_t nv = total.sum;
+        if (nv > cap_v) {
+            C->overflow = 1;
+            C->need_v = nv;
+            nv = 0;
+        }
+        C->nv = nv;
+    }
+};
+struct FinEntryCount {
+    Counters *C;
+    uint32_t cap_e;
+    __device__ void operator()(uint32_t total) const {
+        C->n_entries = total;
+        if (total > cap_e) {
+            C->overflow = 1;
+            C->need_e = total;
+        }
+    }
+};
+
 // ---------------------------------------------------------------------------
 // (a) flatten — plotter.rs:175-332 + fig.rs:428-461
 // ---------------------------------------------------------------------------

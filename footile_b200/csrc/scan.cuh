@@ -110,3 +110,38 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(const typename Op::T 
         if (base + i + 1 == n) out[n] = run;
     }
 }
+
+// Small inputs: one block does the whole scan (a chunk of SCAN_BLOCK items per iteration, the running total
+// carried in a register) instead of three launches, and hands the grand total to `fin` (thread 0) — the
+// capacity guards set_vertex_count / set_entry_count ride along, so a replay saves three or four kernel
+// boundaries per scan.  Same outputs as the 3-phase scan: exclusive, n + 1 values.
+template <class Op, class Fin>
+__global__ void __launch_bounds__(SCAN_THREADS) scan_small(const typename Op::T *in, uint32_t n, typename Op::T *out, Fin fin) {
+    typedef typename Op::T T;
+    T carry = Op::identity();
+    for (uint32_t base0 = 0; base0 < n; base0 += SCAN_BLOCK) {
+        const uint32_t base = base0 + threadIdx.x * SCAN_ITEMS;
+        T v[SCAN_ITEMS];
+        T acc = Op::identity();
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            v[i] = base + i < n ? in[base + i] : Op::identity();
+            acc = Op::combine(acc, v[i]);
+        }
+        T tot;
+        T ex = block_exclusive<Op>(acc, &tot);
+        T run = Op::combine(carry, ex);
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            if (base + i < n) out[base + i] = run;
+            run = Op::combine(run, v[i]);
+        }
+        carry = Op::combine(carry, tot);
+    }
+    if (threadIdx.x == 0) {
+        out[n] = carry;
+        fin(carry);
+    }
+}
+constexpr uint32_t SCAN_SMALL_MAX = 4 * SCAN_BLOCK;
+
