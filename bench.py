@@ -291,19 +291,22 @@ def main():
     ap.add_argument("--workload", default="heptagram", choices=["heptagram", "batch512", "fishy256", "strokes4k", "bigraster"])
     ap.add_argument("--batch", type=int, default=0, help="fills per step per GPU (default 256 heptagram / 4096 batch512)")
     ap.add_argument("--cpu-fills", type=int, default=0, help="fills in the cpu_baseline sample (default: sized for ~10 s)")
-    ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p"], help="pixel format of the rasters")
+    ap.add_argument("--format", default="matte8", choices=["matte8", "rgba8p", "graya8p"], help="pixel format of the rasters")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for runs under ncu)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
-    rgba = args.format == "rgba8p" or args.workload == "strokes4k"
-    bpp = 4 if rgba else 1
+    graya = args.format == "graya8p" and args.workload != "strokes4k"
+    rgba = args.format == "rgba8p" or args.workload == "strokes4k" or graya  # "rgba": a read-modify-write (SrcOver) format
+    bpp = 2 if graya else (4 if rgba else 1)
+    ofmt_id = 1 if graya else 2  # oracle.GRAYA8P / oracle.RGBA8P
+    rmw_color = (120, 255, 0, 0) if graya else (200, 120, 40, 255)  # opaque colour (gray, alpha) / (r, g, b, a)
     batch = args.batch or ((64 if rgba else 256) if args.workload == "heptagram" else {"batch512": 1024 if rgba else 4096, "fishy256": 16384, "strokes4k": 36, "bigraster": 1}[args.workload])
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     unit = "Gpx/s"
-    fmt_name = "Rgba8p" if rgba else "Matte8"
+    fmt_name = "Graya8p" if graya else ("Rgba8p" if rgba else "Matte8")
     metric = "Gpx/s composited (%s %s)" % ({"heptagram": "heptagram fill 4096^2", "batch512": "100k-path batch 512^2", "fishy256": "fishyb fill_256 batch 256^2", "strokes4k": "stroke scenes x30 3840x2160", "bigraster": "one 32768^2 raster"}[args.workload], fmt_name)
     config = {"workload": None, "fills_per_step_per_gpu": batch, "raster": None, "format": fmt_name, "pixels": PIXELS_NOTE,
               "l2": "each step writes fills_per_step rasters (>= 1 GiB per GPU) - outputs far exceed the 126 MB L2; inputs are a few KB"}
@@ -324,7 +327,7 @@ def main():
 
         wl = make_workload(args.workload, batch, 0, oracle_outline)
         if rgba:
-            wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
+            wl["ofmt"], wl["color"] = ofmt_id, rmw_color[:2] if graya else rmw_color
         config["workload"] = wl["desc"].replace("Matte8", fmt_name)
         config["raster"] = "%dx%d" % (wl.get("w", wl["size"]), wl.get("h", wl["size"]))
         cores = os.cpu_count() or 1
@@ -365,14 +368,14 @@ def main():
 
     wl = make_workload(args.workload, batch, rank, product_outline)
     if rgba:
-        wl["ofmt"], wl["color"] = 2, (200, 120, 40, 255)
+        wl["ofmt"], wl["color"] = ofmt_id, rmw_color[:2] if graya else rmw_color
     W, H = wl.get("w", wl["size"]), wl.get("h", wl["size"])
     config["workload"] = wl["desc"].replace("Matte8", fmt_name)
     config["raster"] = "%dx%d" % (W, H)
     if "outline_ms" in wl:
         config["stroke_outline_ms_total_host"] = wl["outline_ms"]
-    b = Batch(W, H, Format.Rgba8p if rgba else Format.Matte8, batch, device=local_rank)
-    colors = np.tile(np.array([200, 120, 40, 255], dtype=np.uint8), (batch, 1)) if rgba else None
+    b = Batch(W, H, Format.Graya8p if graya else (Format.Rgba8p if rgba else Format.Matte8), batch, device=local_rank)
+    colors = np.tile(np.array(rmw_color, dtype=np.uint8), (batch, 1)) if rgba else None
     stream = torch.cuda.ExternalStream(b.stream(), device=local_rank)
     px_fill = oracle_pixels(wl, range(batch) if args.workload == "batch512" else range(min(batch, 2)))
     if len(px_fill) == batch:
@@ -479,20 +482,20 @@ def main():
     roof = None
     if tile_n:
         per_launch_ms = tile_ms / tile_n
-        achieved = px_step * (8 if rgba else 1) / (per_launch_ms * 1e-3) / 1e9
+        achieved = px_step * (2 * bpp if rgba else 1) / (per_launch_ms * 1e-3) / 1e9
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-                traffic = json.load(f).get(args.workload + ("_rgba8p" if rgba else ""))
+                traffic = json.load(f).get(args.workload + ("_graya8p" if graya else ("_rgba8p" if rgba else "")))
         except Exception:
             pass
         roof = {"kernel": "raster_tiles", "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step * (8 if rgba else 1), "bytes_per_px": 8 if rgba else 1, "avg_launch_ms": per_launch_ms,
+                "peak_kind": peak_kind, "traffic": traffic, "algorithmic_bytes_per_launch": px_step * (2 * bpp if rgba else 1), "bytes_per_px": 2 * bpp if rgba else 1, "avg_launch_ms": per_launch_ms,
                 "launches_timed": tile_n, "share_of_step": tile_ms / ms if ms else None}
         if traffic:
             roof["traffic_frac"] = traffic / (per_launch_ms * 1e-3) / 1e9 / peak  # measured DRAM bytes (ncu) over this run's launch time
         if rgba:
-            roof["note"] = ("8 B/px is what the reference's per-pixel SrcOver loop reads and writes; here opaque spans are written unread and alpha-0 "
+            roof["note"] = ("read + write of every pixel (8 B/px Rgba8p, 4 B/px Graya8p) is what the reference's per-pixel SrcOver loop moves; here opaque spans are written unread and alpha-0 "
                             "spans write back only the pixels that change, so real DRAM traffic is lower and frac may exceed 1 - traffic_frac is the measured share of the peak")
 
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----
