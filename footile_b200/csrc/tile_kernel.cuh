@@ -255,6 +255,40 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
         }
     } else {  // Graya8p
         uint16_t *d = reinterpret_cast<uint16_t *>(dst) + x;
+        if (ALIGNED && x + 16 <= W) {
+            // two 16-byte words of 8 pixels each: opaque full coverage is written unread, alpha 0 goes through
+            // the changed-byte test, anything else is blended in registers (one load and one store per 8 pixels)
+            uint4 *q4 = reinterpret_cast<uint4 *>(d);
+#pragma unroll 1
+            for (int h = 0; h < 2; h++) {
+                const uint32_t wl = h == 0 ? a0 : a2, wh = h == 0 ? a1 : a3;  // alphas of pixels 8h .. 8h+7
+                if ((wl & wh) == 0xFFFFFFFFu && clr_a == 255) {
+                    const uint32_t c = mul255_x4((color & 0xFFFFu) * 0x00010001u);
+                    q4[h] = make_uint4(c, c, c, c);
+                    continue;
+                }
+                uint4 t = q4[h];
+                if ((wl | wh) == 0) {
+                    mul255_rmw(q4 + h, t);
+                    continue;
+                }
+                uint32_t w[4] = {t.x, t.y, t.z, t.w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {  // word k holds pixels 2k and 2k+1 of this half
+                    const uint32_t aw = k < 2 ? wl : wh;
+                    uint32_t o = 0;
+#pragma unroll
+                    for (int e = 0; e < 2; e++) {
+                        const uint32_t al = (aw >> (8 * (2 * (k & 1) + e))) & 0xFF, p = (w[k] >> (16 * e)) & 0xFFFFu;
+                        const uint32_t sa1 = 255u - pix::ch8_mul(al, clr_a);
+                        o |= (pix::src_over_ch(p & 0xFF, color & 0xFF, al, sa1) | (pix::src_over_ch(p >> 8, (color >> 8) & 0xFF, al, sa1) << 8)) << (16 * e);
+                    }
+                    w[k] = o;
+                }
+                q4[h] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+            return;
+        }
 #pragma unroll
         for (uint32_t i = 0; i < 16; i++) {
             uint32_t w = i < 4 ? a0 : (i < 8 ? a1 : (i < 12 ? a2 : a3));
