@@ -1,0 +1,358 @@
+// bin_kernel.cuh — stages (c)+(d) for jobs with many edges: the binned tile kernel.
+// Included by engine.cu inside namespace ftl (one translation unit: the kernels share Params / EdgeRec / ...).
+#pragma once
+
+// ---------------------------------------------------------------------------
+// (c)+(d) binned tiles: LANES ARE ROWS
+// ---------------------------------------------------------------------------
+// A tile is (job, band of 32 raster rows, window of WC columns).  One warp owns a tile; lane l owns
+// row l of the band for the whole scatter: the warp walks the tile's edge list (bin_edges), every
+// lane evaluates the SAME edge on ITS row in closed form (fig.rs:238-321,557-600) and adds
+// the span's coverage deltas to its own row of a shared-memory tile of wrapping i16 cells — the
+// reference's own cell type (plotter.rs:45).  Lanes never share a cell, so the adds are plain
+// ld/add/st (no shared-memory atomics: the round-1 scatter spent 2.9 wavefronts per atomic on bank
+// conflicts), the edge record is warp-uniform (staged in shared memory, read by broadcast), control
+// flow is uniform (the same edge has nearly the same span length on neighbouring rows), and the
+// touched-group mask and the row total live in lane registers.  An edge crossing the whole band
+// (the common case for tall edges: config 5) takes a branch-free path with no start / end handling.
+//
+// The row is then resolved WC/16 lanes per row (16 cells per lane, packed 16-bit prefix sums), the
+// fill rule applied and the pixels stored / blended exactly as the direct kernel does (emit16).
+//
+// Wide rasters: the running sum of a row crosses windows.  Each (band, window) tile is claimed from
+// a ticket counter in window-major order; a tile publishes row sums (carry-in + its own row totals,
+// known right after the scatter) to its right neighbour through one 32-bit word per row holding
+// {launch epoch, 16-bit sum}: the consumer spins on that word only, so no fence is needed.  A
+// predecessor always has a smaller ticket, hence is running or done: no deadlock, whatever the
+// residency.  Narrow rasters (few windows, many tiles) walk the windows of a band serially with
+// the sums in registers instead.
+constexpr uint32_t BIN_ROWS = 32;
+constexpr uint32_t BIN_LOG2R = 5;
+
+__device__ __forceinline__ uint32_t slds16(uint32_t a) {
+    uint16_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void ssts16(uint32_t a, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" ::"r"(a), "h"((uint16_t)v)); }
+__device__ __forceinline__ void ssts4(uint32_t a, int4 v) {
+    asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
+}
+__device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v)); }
+
+// One edge on one row of the band (the lane's row), cells of [win_lo, win_hi) only.
+//   xb        X at the bottom of band row 0 (closed form of advance_edges, fig.rs:569-573)
+//   r0, r1    first / last row of the edge relative to the band
+//   dxs, dxe  inv_slope * (ONE - fract(y_upper)), inv_slope * ((ONE - fract(y_lower)) & MASK)   (fig.rs:244-249,262-278)
+//   misc      pixel_cov(fract(y_upper)) | pixel_cov(fract(y_lower)) << 9 | negative sign << 18
+// FULL: the edge covers every row of a band whose 32 rows are all drawn (no start / end row, cov = 256).
+template <bool FULL>
+__device__ __forceinline__ void bin_item(int32_t xb, int32_t inv_slope, int32_t step, int32_t r0, int32_t r1, int32_t dxs, int32_t dxe, uint32_t misc,
+                                         int32_t rel_row, bool row_ok, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t rbase, uint32_t rx,
+                                         int32_t &tot, uint32_t &mask) {
+    bool act = FULL || (row_ok && rel_row >= r0 && rel_row <= r1);
+    const fx_t x_bot = (fx_t)((uint32_t)xb + (uint32_t)rel_row * (uint32_t)inv_slope);
+    fx_t x0, x1;
+    int32_t cov;
+    if (FULL) {
+        x0 = fx_sub(x_bot, inv_slope);
+        x1 = x_bot;
+        cov = 256;
+    } else {
+        const bool starting = rel_row == r0, ending = rel_row == r1;
+        x0 = fx_sub(x_bot, starting ? dxs : inv_slope);
+        x1 = ending ? fx_sub(x_bot, dxe) : x_bot;
+        cov = (ending ? (int32_t)((misc >> 9) & 0x1FFu) : 256) - (starting ? (int32_t)(misc & 0x1FFu) : 0);
+        if (cov <= 0) act = false;
+    }
+    const fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
+    const int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
+    const int32_t c0 = min_pix > 0 ? min_pix : 0;
+    int32_t c = c0 > win_lo ? c0 : win_lo;
+    if (min_pix >= W || c >= win_hi) act = false;
+    // first_cov / step_cov (fig.rs:305-321): full_cov = cov / 256 in Fixed = cov << 8, so fx_mul(a, cov << 8) = (a * cov) >> 8
+    const int32_t rr = min_pix == max_pix ? (int32_t)(((uint32_t)(FX_ONE - fx_fract(fx_avg(max_x, min_x))) * (uint32_t)cov) >> 8)
+                                          : (FX_ONE - fx_fract(min_x)) >> 1;
+    const int32_t first = (int32_t)(((uint64_t)(uint32_t)rr * (uint64_t)(uint32_t)step) >> 16);  // step == ONE for a vertical edge: first = rr
+    int32_t xc = first, prev = 0;
+    // a span that starts left of the window (or of the raster): resume inside it (rare: one warp-uniform test)
+    if (__any_sync(0xFFFFFFFFu, act && c != min_pix)) {
+        const int64_t xc64 = (int64_t)first + (int64_t)(c - min_pix) * (int64_t)step;
+        xc = (int32_t)(xc64 < (int64_t)FX_ONE ? xc64 : (int64_t)FX_ONE);
+        if (c > c0) {
+            const int64_t xq = xc64 - (int64_t)step;
+            const int32_t xk = pixel_cov((fx_t)(xq < (int64_t)FX_ONE ? xq : (int64_t)FX_ONE));
+            prev = xk < cov ? xk : cov;
+            if (prev >= cov) act = false;
+        }
+    }
+    if (act) {
+        const int32_t ed = (misc & (1u << 18)) ? -1 : 1;
+        const int32_t prev0 = prev, rel0 = c - win_lo;
+        int32_t rel = rel0;
+        const int32_t end_rel = win_hi - win_lo;
+        for (;;) {  // scan_area (fig.rs:285-302): cell k receives X(k) - X(k-1), X(k) = min(pixel_cov(min(first + k*step, ONE)), cov)
+            int32_t xk = (xc + 128) >> 8;  // pixel_cov of a value in [0, ONE]
+            if (xk > cov) xk = cov;
+            const int32_t d = xk - prev;
+            if (d != 0) {
+                const uint32_t a = rbase + (((uint32_t)rel << 1) ^ rx);
+                ssts16(a, slds16(a) + (uint32_t)(ed * d));
+            }
+            prev = xk;
+            rel++;
+            xc += step;
+            if (xc > FX_ONE) xc = FX_ONE;
+            if (xk >= cov || rel >= end_rel) break;
+        }
+        tot += ed * (prev - prev0);
+        const uint32_t g0 = (uint32_t)rel0 >> 3, g1 = (uint32_t)(rel - 1) >> 3;  // 8-cell groups touched
+        mask |= ((2u << (g1 - g0)) - 1u) << g0;
+    }
+}
+
+// alpha bytes of four consecutive pixels from two words of packed wrapped-i16 sums (lo = pixel 2j, hi = pixel 2j+1)
+// and the sums reaching them (imgbuf.rs:54-66,157-167; fig.rs:637-664)
+template <bool EVEN_ODD>
+__device__ __forceinline__ uint32_t packed_alpha(uint32_t pa, uint32_t pb, int32_t base_a, int32_t base_b) {
+    const uint32_t ba = __byte_perm((uint32_t)base_a, 0u, 0x1010), bb = __byte_perm((uint32_t)base_b, 0u, 0x1010);
+    if (!EVEN_ODD) {
+        const uint32_t lo = __viaddmin_s16x2_relu(pa, ba, 0x00FF00FFu);  // clamp(i16(p + base), 0, 255) per halfword
+        const uint32_t hi = __viaddmin_s16x2_relu(pb, bb, 0x00FF00FFu);
+        return __byte_perm(lo, hi, 0x6420);
+    } else {
+        uint32_t lo = __viaddmin_s16x2(pa, ba, 0x7FFF7FFFu);  // wrapping i16 add of the base, per halfword
+        uint32_t hi = __viaddmin_s16x2(pb, bb, 0x7FFF7FFFu);
+        const uint32_t bl = (lo >> 8) & 0x00010001u, bh = (hi >> 8) & 0x00010001u;
+        lo = ((lo & 0x00FF00FFu) ^ (bl * 0xFFu)) + bl;
+        hi = ((hi & 0x00FF00FFu) ^ (bh * 0xFFu)) + bh;
+        lo = __vimin_s16x2_relu(lo, 0x00FF00FFu);
+        hi = __vimin_s16x2_relu(hi, 0x00FF00FFu);
+        return __byte_perm(lo, hi, 0x6420);
+    }
+}
+
+// SrcOver of one constant alpha over 16 bytes of pixels already in registers (the three cases of fill_const)
+template <int FMT>
+__device__ __forceinline__ void blend_const_u4(uint4 *p, uint4 t, uint32_t a, uint32_t color, uint32_t clr_a) {
+    if (a == 255u && clr_a == 255u) {
+        const uint32_t w = FMT == FTL_RGBA8P ? mul255_x4(color) : mul255_x4((color & 0xFFFFu) * 0x00010001u);
+        *p = make_uint4(w, w, w, w);
+    } else if (a == 0u) {
+        mul255_rmw(p, t);
+    } else {
+        const uint32_t sa1 = 255u - pix::ch8_mul(a, clr_a);
+#pragma unroll 1
+        for (int k = 0; k < 4; k++) {  // rolled: the general blend is large
+            const uint32_t wk = k == 0 ? t.x : (k == 1 ? t.y : (k == 2 ? t.z : t.w));
+            uint32_t o = 0;
+#pragma unroll
+            for (int ch = 0; ch < 4; ch++) {
+                const uint32_t sc = FMT == FTL_RGBA8P ? (color >> (8 * ch)) & 0xFF : (color >> (8 * (ch & 1))) & 0xFF;
+                o |= pix::src_over_ch((wk >> (8 * ch)) & 0xFF, sc, a, sa1) << (8 * ch);
+            }
+            if (k == 0) t.x = o;
+            else if (k == 1) t.y = o;
+            else if (k == 2) t.z = o;
+            else t.w = o;
+        }
+        *p = t;
+    }
+}
+
+// A tile without edges in a read-modify-write format: every row takes the constant alpha of its running sum.
+// Lanes = 4 rows x 8 columns of 16 bytes, eight loads in flight per lane (the blend of a constant span is
+// bound by read latency: alpha 0 changes almost no pixel, so nearly all of it is loads).
+template <int FMT, bool EVEN_ODD>
+__device__ __forceinline__ void bin_const_tile(int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch, uint32_t row_u4, uint32_t color,
+                                               uint32_t clr_a) {
+    const uint32_t lane = threadIdx.x & 31, sub = lane >> 3, l8 = lane & 7;
+#pragma unroll 1
+    for (uint32_t s = 0; s < BIN_ROWS; s += 4) {
+        const uint32_t row = s + sub;
+        const int32_t cr = __shfl_sync(0xFFFFFFFFu, carry, row);
+        if (!((valid_mask >> s) & 0xFu)) continue;
+        const bool ok = (valid_mask >> row) & 1u;
+        const uint32_t a = rule_alpha<EVEN_ODD>(cr);
+        uint4 *p = reinterpret_cast<uint4 *>(dst_win + (size_t)row * pitch);
+#pragma unroll 1
+        for (uint32_t u0 = 0; u0 < row_u4; u0 += 64) {
+            uint4 t[8];
+            const bool opaque = a == 255u && clr_a == 255u;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t u = u0 + l8 + 8u * i;
+                if (ok && u < row_u4 && !opaque) t[i] = p[u];
+            }
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t u = u0 + l8 + 8u * i;
+                if (ok && u < row_u4) blend_const_u4<FMT>(p + u, t[i], a, color, clr_a);
+            }
+        }
+    }
+}
+
+// Resolve the warp's tile: rows of WC cells, WC/16 lanes per row, 32/(WC/16) rows per step.
+//   mask / carry : this LANE's row (lane = row): touched 8-cell groups, running sum reaching the window
+template <int FMT, bool EVEN_ODD, bool ALIGNED, int WC>
+__device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t mask, int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch,
+                                            uint32_t w_rel, uint32_t color) {
+    constexpr uint32_t LPR = WC / 16, RPS = 32 / LPR;
+    const uint32_t lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
+    const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
+    const uint32_t touched = __ballot_sync(0xFFFFFFFFu, mask != 0);
+    if (FMT != FTL_MATTE8 && ALIGNED && touched == 0 && w_rel >= (uint32_t)WC) {
+        constexpr uint32_t U = FMT == FTL_GRAYA8P ? 2u : 4u;  // 16-byte words per 16 pixels
+        bin_const_tile<FMT, EVEN_ODD>(carry, valid_mask, dst_win, pitch, LPR * U, color, clr_a);
+        return;
+    }
+#pragma unroll 1
+    for (uint32_t s = 0; s < BIN_ROWS; s += RPS) {
+        const uint32_t row = s + sub;
+        const uint32_t m = __shfl_sync(0xFFFFFFFFu, mask, row);
+        const int32_t cr = __shfl_sync(0xFFFFFFFFu, carry, row);
+        const uint32_t step_rows = ((RPS == 32 ? 0u : (1u << RPS)) - 1u) << s;
+        if (!(valid_mask & step_rows)) continue;
+        const bool ok = (valid_mask >> row) & 1u;
+        uint8_t *drow = dst_win + (size_t)row * pitch;
+        if (!(touched & step_rows)) {  // edge-free rows: one constant alpha
+            const uint32_t q = rule_alpha<EVEN_ODD>(cr) * 0x01010101u;
+            if (ok) emit16<FMT, ALIGNED>(drow, 16 * l, w_rel, q, q, q, q, color, clr_a);
+            continue;
+        }
+        int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
+        const uint32_t rowaddr = cells + row * (uint32_t)(WC * 2), rxg = row & 7u;
+        if ((m >> (2 * l)) & 1u) {
+            const uint32_t a = rowaddr + (((2 * l) ^ rxg) << 4);
+            v0 = slds4(a);
+            ssts4_zero(a);
+        }
+        if ((m >> (2 * l + 1)) & 1u) {
+            const uint32_t a = rowaddr + (((2 * l + 1) ^ rxg) << 4);
+            v1 = slds4(a);
+            ssts4_zero(a);
+        }
+        // packed prefix inside each word: (lo, hi) -> (lo, lo + hi) mod 2^16
+        const uint32_t p0 = (uint32_t)v0.x * 0x00010001u, p1 = (uint32_t)v0.y * 0x00010001u, p2 = (uint32_t)v0.z * 0x00010001u,
+                       p3 = (uint32_t)v0.w * 0x00010001u, p4 = (uint32_t)v1.x * 0x00010001u, p5 = (uint32_t)v1.y * 0x00010001u,
+                       p6 = (uint32_t)v1.z * 0x00010001u, p7 = (uint32_t)v1.w * 0x00010001u;
+        const int32_t o1 = (int32_t)(p0 >> 16), o2 = o1 + (int32_t)(p1 >> 16), o3 = o2 + (int32_t)(p2 >> 16), o4 = o3 + (int32_t)(p3 >> 16),
+                      o5 = o4 + (int32_t)(p4 >> 16), o6 = o5 + (int32_t)(p5 >> 16), o7 = o6 + (int32_t)(p6 >> 16), tot = o7 + (int32_t)(p7 >> 16);
+        int32_t inc = tot;
+#pragma unroll
+        for (int d = 1; d < (int)LPR; d <<= 1) scan_step<(int)LPR>(inc, d);
+        const int32_t b = cr + inc - tot;
+        const uint32_t a0 = packed_alpha<EVEN_ODD>(p0, p1, b, b + o1);
+        const uint32_t a1 = packed_alpha<EVEN_ODD>(p2, p3, b + o2, b + o3);
+        const uint32_t a2 = packed_alpha<EVEN_ODD>(p4, p5, b + o4, b + o5);
+        const uint32_t a3 = packed_alpha<EVEN_ODD>(p6, p7, b + o6, b + o7);
+        if (ok) emit16<FMT, ALIGNED>(drow, 16 * l, w_rel, a0, a1, a2, a3, color, clr_a);
+    }
+}
+
+template <int FMT, bool ALIGNED, int WC>
+__global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs, const JobState *__restrict__ JS, Params P,
+                                                  const uint32_t *__restrict__ bin_off, const uint32_t *__restrict__ entries,
+                                                  const Counters *__restrict__ C, uint32_t *__restrict__ ticket, uint32_t *__restrict__ look,
+                                                  uint32_t epoch) {
+    if (C->overflow) return;
+    extern __shared__ __align__(16) uint8_t bin_smem[];
+    const uint32_t lane = threadIdx.x;
+    const uint32_t cells = smem_addr(bin_smem), stage = cells + BIN_ROWS * WC * 2;
+    for (uint32_t i = lane; i < BIN_ROWS * WC * 2 / 16; i += 32) ssts4_zero(cells + 16u * i);
+    __syncwarp();
+    const int32_t W = (int32_t)P.W;
+    const uint32_t tiles_per_win = (P.job_end - P.job_begin) * P.b_nbands;
+    const uint32_t n_tasks = P.b_lookback ? tiles_per_win * P.b_nwin : tiles_per_win;
+    const uint32_t rbase = cells + lane * (uint32_t)(WC * 2), rx = (lane & 7u) << 4;
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1u);
+        t = __shfl_sync(0xFFFFFFFFu, t, 0);
+        if (t >= n_tasks) break;
+        uint32_t w_begin = 0, w_end = P.b_nwin, jb = t;
+        if (P.b_lookback) {  // window-major: the left neighbour of a tile always has a smaller ticket
+            w_begin = t / tiles_per_win;
+            jb = t - w_begin * tiles_per_win;
+            w_end = w_begin + 1;
+        }
+        const uint32_t j = P.job_begin + jb / P.b_nbands, band = jb % P.b_nbands;
+        const JobState js = JS[j];
+        if (js.vtx_end - js.vtx_begin <= DIRECT_MAX) continue;  // drawn by raster_tiles from the job's own edge range
+        const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << BIN_LOG2R);
+        const int32_t row = row0 + (int32_t)lane;
+        const bool row_ok = row >= js.first_row && row < (int32_t)P.row_end;  // rows above the figure are untouched (fig.rs:497)
+        const uint32_t valid_mask = __ballot_sync(0xFFFFFFFFu, row_ok);
+        if (valid_mask == 0) continue;
+        const bool band_full = valid_mask == 0xFFFFFFFFu;
+        const unsigned long long raster = jobs[j].raster;
+        const uint32_t rule = jobs[j].rule, color = jobs[j].color;
+        uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(row0 - (int32_t)P.row_begin) * P.pitch;
+        int32_t carry = 0;
+        for (uint32_t w = w_begin; w < w_end; w++) {
+            const uint32_t bin = (j * P.b_nbands + band) * P.b_nwin + w;
+            const uint32_t e0 = bin_off[bin], ne = bin_off[bin + 1] - e0;
+            const int32_t win_lo = (int32_t)(w * (uint32_t)WC), win_hi = min(W, win_lo + WC);
+            int32_t tot = 0;
+            uint32_t mask = 0;
+            // ---- (c) scatter: the warp walks the bin, 32 records staged per round, the next round's gather in flight ----
+            EdgeRec nxt;
+            nxt.flags = 0;
+            if (lane < ne) nxt = E[entries[e0 + lane]];
+            for (uint32_t base = 0; base < ne; base += 32) {
+                const EdgeRec e = nxt;
+                if (base + lane < ne) {
+                    // everything that does not depend on the row, once per (edge, band)
+                    const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
+                    int4 a, b;
+                    a.x = (int32_t)((uint32_t)e.x_bot0 + (uint32_t)(row0 - e.ry0) * (uint32_t)e.inv_slope);
+                    a.y = e.inv_slope;
+                    a.z = e.step_pix > 0 ? e.step_pix : FX_ONE;
+                    a.w = e.ry0 - row0;
+                    b.x = e.ry1 - row0;
+                    b.y = fx_mul(e.inv_slope, FX_ONE - fr0);
+                    b.z = fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK);
+                    b.w = (int32_t)((uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9) | ((e.flags & 2u) << 17));
+                    ssts4(stage + lane * 32u, a);
+                    ssts4(stage + lane * 32u + 16u, b);
+                }
+                if (base + 32 + lane < ne) nxt = E[entries[e0 + base + 32 + lane]];
+                __syncwarp();
+                const uint32_t cnt = min(32u, ne - base);
+#pragma unroll 1
+                for (uint32_t k = 0; k < cnt; k++) {
+                    const int4 a = slds4(stage + k * 32u), b = slds4(stage + k * 32u + 16u);
+                    if (band_full && a.w < 0 && b.x >= (int32_t)BIN_ROWS)
+                        bin_item<true>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, (uint32_t)b.w, (int32_t)lane, true, W, win_lo, win_hi, rbase, rx, tot, mask);
+                    else
+                        bin_item<false>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, (uint32_t)b.w, (int32_t)lane, row_ok, W, win_lo, win_hi, rbase, rx, tot, mask);
+                }
+                __syncwarp();
+            }
+            // ---- the sums reaching this window / leaving it ----
+            if (P.b_lookback) {
+                if (w > 0) {
+                    const uint32_t *src = look + (size_t)(bin - 1) * 32u + lane;
+                    uint32_t v;
+                    do {
+                        v = ld_relaxed(src);
+                    } while (!__all_sync(0xFFFFFFFFu, (v >> 16) == epoch));
+                    carry = (int32_t)(v & 0xFFFFu);
+                }
+                if (w + 1 < P.b_nwin) st_relaxed(look + (size_t)bin * 32u + lane, (epoch << 16) | ((uint32_t)(carry + tot) & 0xFFFFu));
+            }
+            // ---- (d) resolve ----
+            uint8_t *dwin = dst + (size_t)win_lo * P.bpp;
+            if (rule == FTL_EVENODD) bin_resolve<FMT, true, ALIGNED, WC>(cells, mask, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
+            else bin_resolve<FMT, false, ALIGNED, WC>(cells, mask, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
+            __syncwarp();
+            carry += tot;
+        }
+    }
+}

@@ -128,9 +128,6 @@ int ftl_set_join(ftl_plotter *p, int join, float miter_limit) {
 static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
     if (rule != FTL_NONZERO && rule != FTL_EVENODD) return bad("unknown fill rule");
     if (n_ops && !ops) return bad("ops is null");
-    // PenWidth persists on the plotter across calls (plotter.rs:151-153)
-    for (size_t i = 0; i < n_ops; i++)
-        if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
     std::vector<HostJob> jobs(1);
     HostJob &j = jobs[0];
     j.op_begin = 0; j.op_end = (uint32_t)n_ops;
@@ -139,7 +136,12 @@ static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_
     j.rule = rule;
     if (color) memcpy(j.color, color, p->geo.bpp());
     j.raster = p->raster;
-    return p->eng.fill(p->geo, jobs, ops, n_ops);
+    int rc = p->eng.fill(p->geo, jobs, ops, n_ops);
+    if (rc) return rc;  // a rejected call leaves the plotter state alone
+    // PenWidth persists on the plotter across calls (plotter.rs:151-153)
+    for (size_t i = 0; i < n_ops; i++)
+        if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
+    return FTL_OK;
 }
 
 int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
@@ -170,9 +172,11 @@ int ftl_fill_layers(ftl_plotter *p, uint32_t n_layers, const ftl_path_op *ops, c
         if (colors) memcpy(j.color, colors + 4 * (size_t)l, 4);
         j.raster = p->raster;
     }
+    int rc = p->eng.fill_layers(p->geo, jobs, ops, n_ops);
+    if (rc) return rc;
     for (size_t i = 0; i < n_ops; i++)  // PenWidth persists on the plotter (plotter.rs:151-153)
         if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
-    return p->eng.fill_layers(p->geo, jobs, ops, n_ops);
+    return FTL_OK;
     GUARD_END
 }
 
@@ -239,6 +243,8 @@ int ftl_sync(ftl_plotter *p) {
 }
 int ftl_raster_device_ptr(ftl_plotter *p, void **dptr, size_t *nbytes) {
     if (!p || !dptr) return bad("null argument");
+    int rc = p->eng.sync();  // fills issued so far (and any deferred repeat of an overflowed replay) are complete
+    if (rc) return rc;
     *dptr = p->raster;
     if (nbytes) *nbytes = p->geo.bytes();
     return FTL_OK;
@@ -363,6 +369,8 @@ int ftl_batch_sync(ftl_batch *b) {
 }
 int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes) {
     if (!b || !dptr) return bad("null argument");
+    int rc = b->eng.sync();  // fills issued so far (and any deferred repeat of an overflowed replay) are complete
+    if (rc) return rc;
     *dptr = b->rasters;
     if (nbytes) *nbytes = b->geo.bytes() * b->capacity;
     return FTL_OK;

@@ -47,7 +47,7 @@ struct __align__(16) EdgeRec {  // 32 B: one per ring segment whose end points d
     uint32_t job;
     uint32_t flags;     // bit0 valid, bit1 set when the edge runs against the figure direction (sign -1, fig.rs:286)
 };
-constexpr uint32_t DIRECT_MAX = 64;  // jobs with at most this many edge slots skip binning: their tiles scan the job's edges
+constexpr uint32_t DIRECT_MAX = 64;  // jobs with at most this many edge slots skip binning: raster_tiles scans the job's own edges; larger jobs go to raster_bins
 
 struct __align__(8) SumHead {  // scan element over ops: vertex count + position of the last sub-figure head
     uint32_t sum, head;
@@ -70,8 +70,12 @@ struct Params {  // per-call constants, passed by value
     uint32_t n_jobs, n_ops, n_tiles;
     uint32_t win_chunks, warp_words, cta_warps;  // chunks per row window, smem words per warp, warps per CTA
     uint32_t win_rows;                           // rows of a narrow raster (one window per row) a warp holds at once
-    uint32_t n_win, n_bins;                      // windows per row; bins = n_tiles * n_win
+    uint32_t n_win;                              // windows per row of the direct kernel
     uint32_t all_direct;                         // host-proven: every job has <= DIRECT_MAX vertices (no binning needed)
     uint32_t all_tiny;                           // host-proven: every job has <= 8 vertices (every tile can take the analytic rows)
-    uint32_t tile_begin, tile_end;               // tiles this launch of the tile kernel covers
+    uint32_t tile_begin, tile_end;               // tiles this launch of the direct tile kernel covers
+    // binned tiles (raster_bins): bands of 32 rows x windows of b_wc columns
+    uint32_t b_nbands, b_nwin, b_wc, n_bins;     // bins = n_jobs * b_nbands * b_nwin
+    uint32_t b_lookback;                         // 1: one (band, window) tile per ticket, row sums passed through `look`; 0: a ticket walks all windows of a band
+    uint32_t job_begin, job_end;                 // jobs this launch of the binned kernel covers
 };

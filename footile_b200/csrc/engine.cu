@@ -17,7 +17,8 @@
 //   device_types.cuh   records in HBM and per-call Params
 //   scan.cuh           generic 3-phase exclusive scan
 //   front_kernels.cuh  stages (a)+(b)
-//   tile_kernel.cuh    stages (c)+(d): scatter rows, analytic rows, resolve, composite
+//   tile_kernel.cuh    stages (c)+(d) for jobs of at most 64 edges: scatter rows, analytic rows, resolve, composite
+//   bin_kernel.cuh     stages (c)+(d) for larger jobs: (32 rows x window) tiles, lanes = rows, no atomics
 //   pack_kernels.cuh   packed read-back, raster checksums
 //   engine.cu          host side: scratch arena, graph replay, launches, read-back
 //
@@ -72,6 +73,7 @@ static std::atomic<bool> g_profiling{false};
 #include "scan.cuh"
 #include "front_kernels.cuh"
 #include "tile_kernel.cuh"
+#include "bin_kernel.cuh"
 #include "pack_kernels.cuh"
 
 // ---------------------------------------------------------------------------
@@ -130,7 +132,9 @@ struct Engine::Impl {
     cudaStream_t st = nullptr;
     int n_sms = 148;
     size_t max_smem = 0;
-    DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc;
+    DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc, tickets, look;
+    uint32_t look_epoch = 0;              // launch epoch of the look-back words (0: the buffer must be cleared first)
+    std::vector<uint8_t> host_direct;    // per job: provably at most DIRECT_MAX edge slots (line-only, few ops)
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
     PinBuf pin_ring, pin_pack[2], pin_lit[2];
     DevBuf pack_fixed, pack_cnt, pack_lit;
@@ -195,7 +199,7 @@ Engine::~Engine() {
             cudaStreamSynchronize(impl_->st);
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
-                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
             for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1]}) b->release();
@@ -209,19 +213,26 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out);
 static int run_pipeline(Engine::Impl &m, bool exact);
 static int resolve_pending(Engine::Impl &m);
 
-typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *, const Counters *);
-static TileKernel tile_kernel(int fmt, bool aligned, bool general) {
-    if (general) switch (fmt) {
-        case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true, true> : raster_tiles<FTL_MATTE8, false, true>;
-        case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true, true> : raster_tiles<FTL_GRAYA8P, false, true>;
-        default: return aligned ? raster_tiles<FTL_RGBA8P, true, true> : raster_tiles<FTL_RGBA8P, false, true>;
-        }
+typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const Counters *);
+static TileKernel tile_kernel(int fmt, bool aligned) {
     switch (fmt) {
-    case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true, false> : raster_tiles<FTL_MATTE8, false, false>;
-    case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true, false> : raster_tiles<FTL_GRAYA8P, false, false>;
-    default: return aligned ? raster_tiles<FTL_RGBA8P, true, false> : raster_tiles<FTL_RGBA8P, false, false>;
+    case FTL_MATTE8: return aligned ? raster_tiles<FTL_MATTE8, true> : raster_tiles<FTL_MATTE8, false>;
+    case FTL_GRAYA8P: return aligned ? raster_tiles<FTL_GRAYA8P, true> : raster_tiles<FTL_GRAYA8P, false>;
+    default: return aligned ? raster_tiles<FTL_RGBA8P, true> : raster_tiles<FTL_RGBA8P, false>;
     }
 }
+typedef void (*BinKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const uint32_t *, const uint32_t *, const Counters *, uint32_t *,
+                          uint32_t *, uint32_t);
+template <int WC>
+static BinKernel bin_kernel_wc(int fmt, bool aligned) {
+    switch (fmt) {
+    case FTL_MATTE8: return aligned ? raster_bins<FTL_MATTE8, true, WC> : raster_bins<FTL_MATTE8, false, WC>;
+    case FTL_GRAYA8P: return aligned ? raster_bins<FTL_GRAYA8P, true, WC> : raster_bins<FTL_GRAYA8P, false, WC>;
+    default: return aligned ? raster_bins<FTL_RGBA8P, true, WC> : raster_bins<FTL_RGBA8P, false, WC>;
+    }
+}
+static BinKernel bin_kernel(int fmt, bool aligned, uint32_t wc) { return wc == 128 ? bin_kernel_wc<128>(fmt, aligned) : bin_kernel_wc<256>(fmt, aligned); }
+static size_t bin_smem_bytes(uint32_t wc) { return (size_t)BIN_ROWS * wc * 2 + 32 * 32; }
 
 #define ENSURE_INIT()                                                        \
     do {                                                                     \
@@ -263,9 +274,13 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
             CK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
             di.max_smem = (size_t)v;
             for (int f = 0; f < 3; f++)
-                for (int a = 0; a < 4; a++) {
-                    CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
-                    CK(cudaFuncSetAttribute(tile_kernel(f, (a & 1) != 0, (a & 2) != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                for (int a = 0; a < 2; a++) {
+                    CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
+                    CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    for (uint32_t wc : {128u, 256u}) {
+                        CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes(wc)));
+                        CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    }
                 }
             CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
             di.ready = true;
@@ -294,9 +309,11 @@ static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typen
     return FTL_OK;
 }
 
-static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, uint32_t warp_slots, bool all_direct, Params *P) {
+static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, int n_sms, Params *P) {
+    const uint32_t warp_slots = (uint32_t)n_sms * 16u;
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
+    // ---- direct tiles (raster_tiles) ----
     P->chunks = (g.width + CHUNK - 1) / CHUNK;
     P->WP = P->chunks * CHUNK;
     // each warp keeps one row window of up to 4 chunks (2048 px) in shared memory
@@ -308,11 +325,9 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     P->cta_warps = 4;
     if (const char *ev = getenv("FTL_CTA_WARPS")) P->cta_warps = (uint32_t)std::min(4, std::max(1, atoi(ev)));  // tuning knob
 
-    // Band height: 8 rows per warp amortise the per-tile set-up when every tile scans its job's own few
-    // edges; binned jobs do better with 4 (fewer edges per bin to test against each row); fewer rows per
-    // band when one launch would otherwise leave most of the GPU's warp slots empty (a single raster, a
-    // layer of a scene).
-    uint32_t log2R = all_direct ? 3 : 2;
+    // Band height: 8 rows per warp amortise the per-tile set-up; fewer rows per band when one launch
+    // would otherwise leave most of the GPU's warp slots empty (a single raster, a layer of a scene).
+    uint32_t log2R = 3;
     while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
     while (log2R > 0 && (uint64_t)jobs_per_launch * div_up(g.rows(), 1u << log2R) < 2ull * warp_slots) log2R--;
     if (const char *ev = getenv("FTL_LOG2R")) log2R = (uint32_t)std::min(5, std::max(0, atoi(ev)));  // tuning knob
@@ -327,6 +342,16 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
         set_error("row window exceeds shared memory");
         return FTL_ERR_TOO_WIDE;
     }
+    // ---- binned tiles (raster_bins): bands of 32 rows x windows of b_wc columns ----
+    P->b_wc = 256;
+    if (const char *ev = getenv("FTL_BIN_WC")) P->b_wc = atoi(ev) == 128 ? 128u : 256u;  // tuning knob
+    P->b_nbands = div_up(g.rows(), BIN_ROWS);
+    P->b_nwin = div_up(g.width, P->b_wc);
+    // One ticket per (band, window) with the row sums handed to the right neighbour, unless the launch has
+    // plenty of bands anyway (many narrow rasters): then a ticket walks the windows of its band serially.
+    const uint32_t bin_slots = (uint32_t)n_sms * 12u;
+    P->b_lookback = P->b_nwin > 1 && (uint64_t)jobs_per_launch * P->b_nbands < 8ull * bin_slots;
+    if (const char *ev = getenv("FTL_BIN_LOOKBACK")) P->b_lookback = P->b_nwin > 1 && atoi(ev) != 0;  // tuning knob
     return FTL_OK;
 }
 
@@ -371,14 +396,20 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
     P.all_direct = 1;
     P.all_tiny = 1;
-    for (const HostJob &h : jobs) {
+    m.host_direct.assign(jobs.size(), 1);
+    for (size_t jx = 0; jx < jobs.size(); jx++) {
+        const HostJob &h = jobs[jx];
         if (h.op_end - h.op_begin > 8u) P.all_tiny = 0;
-        if (h.op_end - h.op_begin > DIRECT_MAX) P.all_direct = 0;
-        for (uint32_t i = h.op_begin; i < h.op_end && P.all_direct; i++)
-            if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) P.all_direct = 0;
-        if (!P.all_direct) break;
+        bool direct = h.op_end - h.op_begin <= DIRECT_MAX;
+        for (uint32_t i = h.op_begin; i < h.op_end && direct; i++)
+            if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) direct = false;
+        if (!direct) {
+            m.host_direct[jx] = 0;
+            P.all_direct = 0;
+            if (!layered) break;  // only layered launches look at the per-job flags
+        }
     }
-    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), (uint32_t)m.n_sms * 16u, P.all_direct != 0, &P);
+    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), m.n_sms, &P);
     if (rc) return rc;
     P.n_jobs = (uint32_t)jobs.size();
     P.n_ops = (uint32_t)n_ops;
@@ -388,17 +419,18 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         return FTL_ERR_INVALID;
     }
     P.n_tiles = (uint32_t)nt;
-    if (nt * P.n_win >= 0x7FFFFFFFull) {
+    const uint64_t nb = P.all_direct ? 0ull : (uint64_t)P.n_jobs * P.b_nbands * P.b_nwin;
+    if (nb >= 0x7FFFFFFFull) {
         set_error("too many tiles for one call");
         return FTL_ERR_INVALID;
     }
-    P.n_bins = (uint32_t)(nt * P.n_win);
+    P.n_bins = (uint32_t)nb;
     // stage + upload ops and job descriptors
     size_t ops_bytes = n_ops * sizeof(ftl_path_op), jobs_bytes = jobs.size() * sizeof(JobDesc);
+    // the previous call's async copies out of the pinned staging must be done before it is overwritten or freed
+    CK(cudaStreamSynchronize(m.st));
     if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
     if ((rc = m.pin_jobs.ensure(jobs_bytes))) return rc;
-    // the previous call's async copies out of the pinned staging must be done before it is overwritten
-    CK(cudaStreamSynchronize(m.st));
     if (ops_bytes) memcpy(m.pin_ops.p, ops, ops_bytes);
     JobDesc *jd = (JobDesc *)m.pin_jobs.p;
     for (size_t j = 0; j < jobs.size(); j++) {
@@ -458,7 +490,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     if ((rc = m.jstate.ensure((size_t)P.n_jobs * sizeof(JobState), st))) return rc;
     if ((rc = m.cnt.ensure((size_t)(P.n_ops + 1) * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure(((size_t)P.n_ops + 1) * sizeof(SumHead), st))) return rc;
-    if ((rc = m.tcount.ensure((size_t)P.n_bins * sizeof(uint32_t), st))) return rc;
+    if ((rc = m.tcount.ensure(((size_t)P.n_bins + 1) * sizeof(uint32_t), st))) return rc;
     if ((rc = m.toff.ensure(((size_t)P.n_bins + 1) * sizeof(uint32_t), st))) return rc;
     if ((rc = m.partials.ensure((size_t)div_up(P.n_ops + 1, SCAN_BLOCK) * sizeof(SumHead), st))) return rc;
     if ((rc = m.tpart.ensure((size_t)div_up(P.n_bins + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return rc;
@@ -491,6 +523,10 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 CK(cudaMemcpyAsync(m.pin_small.p, &((SumHead *)m.off.p)[P.n_ops].sum, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
                 CK(cudaStreamSynchronize(st));
                 uint32_t nv = *(uint32_t *)m.pin_small.p;
+                if (nv >= 0x7FFFFFFFu) {
+                    set_error("too many vertices for one call (2^31 - 1 after flattening)");
+                    return FTL_ERR_INVALID;
+                }
                 size_t want = nv ? nv : 1;
                 if ((r2 = m.vtx.ensure(want * sizeof(Vtx), st))) return r2;
                 if ((r2 = m.edges.ensure(want * sizeof(EdgeRec), st))) return r2;
@@ -543,7 +579,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct};
+                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands};
         if (!m.graph || key != m.graph_key) {
             m.drop_graph();
             cudaGraph_t g = nullptr;
@@ -569,7 +605,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     // ---- (c)+(d) tiles ----
     int occ = 1;
     const bool aligned = P.W % (16u / P.bpp) == 0;  // rows start on 16-byte boundaries
-    TileKernel tk = tile_kernel((int)P.fmt, aligned, !P.all_direct);
+    TileKernel tk = tile_kernel((int)P.fmt, aligned);
     const int tile_threads = (int)P.cta_warps * 32;
     CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, tk, tile_threads, m.smem_bytes));
     if (occ < 1) occ = 1;
@@ -579,14 +615,38 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     // (tools/occ_probe.py).  Everything that reads or scatters wants all the warps it can get.
     if (P.fmt == FTL_MATTE8 && P.all_direct && P.all_tiny && aligned && (P.W & 15u) == 0) occ = std::min(occ, P.W >= 6144u ? 2 : (P.W >= 3072u ? 3 : 5));
     if (const char *ev = getenv("FTL_OCC")) occ = std::max(1, std::min(16, atoi(ev)));  // tuning knob
+    // binned jobs: one-warp CTAs of raster_bins, as many as fit
+    BinKernel bk = bin_kernel((int)P.fmt, aligned, P.b_wc);
+    const int bin_smem = (int)bin_smem_bytes(P.b_wc);
+    int bocc = 1;
+    if (!P.all_direct) {
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&bocc, bk, 32, bin_smem));
+        if (bocc < 1) bocc = 1;
+        if (const char *ev = getenv("FTL_BIN_OCC")) bocc = std::max(1, std::min(32, atoi(ev)));  // tuning knob
+    }
     // Independent rasters: one launch over all tiles.  Layers of one raster: one launch per job, in
     // order, each over that job's tiles (the stages before ran once for all layers).
     const uint32_t n_launches = m.layered ? P.n_jobs : 1u;
+    uint32_t *d_tickets = nullptr, *d_look = nullptr;
+    if (!P.all_direct) {
+        if ((rc = m.tickets.ensure((size_t)n_launches * sizeof(uint32_t), st))) return rc;
+        d_tickets = (uint32_t *)m.tickets.p;
+        CK(cudaMemsetAsync(d_tickets, 0, (size_t)n_launches * sizeof(uint32_t), st));
+        if (P.b_lookback) {
+            const size_t look_bytes = (size_t)P.n_bins * 32 * sizeof(uint32_t);
+            const void *before = m.look.p;
+            if ((rc = m.look.ensure(look_bytes, st))) return rc;
+            if (m.look.p != before || m.look_epoch + n_launches >= 0xFFFFu) m.look_epoch = 0;
+            if (m.look_epoch == 0) CK(cudaMemsetAsync(m.look.p, 0, m.look.cap, st));
+            d_look = (uint32_t *)m.look.p;
+        }
+    }
     for (uint32_t l = 0; l < n_launches; l++) {
         Params PL = P;
         PL.tile_begin = m.layered ? l * P.n_bands : 0u;
         PL.tile_end = m.layered ? (l + 1) * P.n_bands : P.n_tiles;
-        uint32_t grid = std::min<uint32_t>(div_up(PL.tile_end - PL.tile_begin, P.cta_warps), (uint32_t)(m.n_sms * occ));
+        PL.job_begin = m.layered ? l : 0u;
+        PL.job_end = m.layered ? l + 1 : P.n_jobs;
         ProfSpan span{};
         const bool prof = g_profiling.load();
         if (prof) {
@@ -594,8 +654,18 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
             CK(cudaEventCreate(&span.b));
             CK(cudaEventRecord(span.a, st));
         }
-        tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, PL, (const uint32_t *)m.toff.p,
-                                                     (const uint32_t *)m.entries.p, d_cnt); LAUNCHED();
+        // jobs of at most DIRECT_MAX edge slots (skipped when the host knows this layer is a binned job... it cannot: curves may flatten to few edges)
+        {
+            uint32_t grid = std::min<uint32_t>(div_up(PL.tile_end - PL.tile_begin, P.cta_warps), (uint32_t)(m.n_sms * occ));
+            tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, PL, d_cnt); LAUNCHED();
+        }
+        // larger jobs (skipped when the host has proven there are none in this launch)
+        if (!P.all_direct && !(m.layered && m.host_direct[l])) {
+            const uint64_t tasks = (uint64_t)(PL.job_end - PL.job_begin) * P.b_nbands * (P.b_lookback ? P.b_nwin : 1u);
+            uint32_t grid = (uint32_t)std::min<uint64_t>(tasks, (uint64_t)m.n_sms * bocc);
+            bk<<<grid, 32, bin_smem, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, PL, (const uint32_t *)m.toff.p, (const uint32_t *)m.entries.p, d_cnt,
+                                          d_tickets + l, d_look, P.b_lookback ? ++m.look_epoch : 0u); LAUNCHED();
+        }
         if (prof) {
             CK(cudaEventRecord(span.b, st));
             std::lock_guard<std::mutex> lock(g_spans_mu);
@@ -846,6 +916,12 @@ int Engine::free_raster(void *dptr) {
 }
 int Engine::memset_async(void *dptr, int value, size_t bytes) {
     ENSURE_INIT();
+    {
+        // a speculative replay that overflowed its scratch buffers drew nothing and is repeated by
+        // resolve_pending(): that repeat must land BEFORE the clear, not after it
+        int rc = resolve_pending(*impl_);
+        if (rc) return rc;
+    }
     CK(cudaMemsetAsync(dptr, value, bytes, impl_->st));
     return FTL_OK;
 }

@@ -356,25 +356,25 @@ __global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, con
     }
 }
 
-// Band range of an edge inside this device's rows; returns false if none.
+// Band range (bands of 32 rows, raster_bins) of an edge inside this device's rows; returns false if none.
 __device__ __forceinline__ bool edge_bands(const EdgeRec &e, const Params &P, uint32_t *b0, uint32_t *b1) {
     int32_t lo = e.ry0, hi = e.ry1;  // ry0 >= first_row >= 0 by construction
     if (lo < (int32_t)P.row_begin) lo = (int32_t)P.row_begin;
     if (hi > (int32_t)P.row_end - 1) hi = (int32_t)P.row_end - 1;
     if (lo > hi) return false;
-    *b0 = (uint32_t)(lo - (int32_t)P.row_begin) >> P.log2R;
-    *b1 = (uint32_t)(hi - (int32_t)P.row_begin) >> P.log2R;
+    *b0 = (uint32_t)(lo - (int32_t)P.row_begin) >> 5;
+    *b1 = (uint32_t)(hi - (int32_t)P.row_begin) >> 5;
     return true;
 }
 
-// Conservative range of row windows an edge can write to on the rows [ra, rb] of one band (both
+// Conservative range of column windows an edge can write to on the rows [ra, rb] of one band (both
 // inside the edge's own rows).  The span of a row is linear in the row, so the extremes are at the
-// two end rows, evaluated as edge_row_setup does; the scatter loop can run at most |dx/dy| + 2 cells
+// two end rows, evaluated as the scatter does; the scatter loop can run at most |dx/dy| + 2 cells
 // past the leftmost one.  Anything that would wrap 32-bit arithmetic falls back to "all windows".
 __device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32_t rb, const Params &P, uint32_t *w0, uint32_t *w1) {
     *w0 = 0;
-    *w1 = P.n_win - 1;
-    if (P.n_win == 1) return;
+    *w1 = P.b_nwin - 1;
+    if (P.b_nwin == 1) return;
     int64_t lo = INT64_MAX, hi = INT64_MIN;
     const int64_t slope = e.inv_slope;
     for (int t = 0; t < 2; t++) {
@@ -390,32 +390,31 @@ __device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32
     const int64_t wmax = (int64_t)P.W - 1;
     lo_pix = lo_pix < 0 ? 0 : (lo_pix > wmax ? wmax : lo_pix);
     hi_pix = hi_pix < 0 ? 0 : (hi_pix > wmax ? wmax : hi_pix);
-    const uint32_t win_cells = P.win_chunks * 512u;
-    *w0 = (uint32_t)lo_pix / win_cells;
-    *w1 = (uint32_t)hi_pix / win_cells;
+    *w0 = (uint32_t)lo_pix / P.b_wc;
+    *w1 = (uint32_t)hi_pix / P.b_wc;
 }
 
-// Counting sort of edges by (job, row band, row window): pass FILL=false counts, pass FILL=true
+// Counting sort of edges by (job, band of 32 rows, column window): pass FILL=false counts, pass FILL=true
 // writes edge ids at the scanned offsets.  Short edges are handled by their own thread; an edge
 // crossing many bands is spread over the warp.  Jobs with at most DIRECT_MAX edge slots are not
 // binned at all.
 template <bool FILL>
-__device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t tile, uint32_t band, const Params &P, uint32_t *tile_count,
-                                        const uint32_t *tile_off, uint32_t *entries) {
-    const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << P.log2R);
-    const int32_t ra = max(e.ry0, row0), rb = min(min(e.ry1, row0 + (int32_t)P.R - 1), (int32_t)P.row_end - 1);
+__device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t tile, uint32_t band, const Params &P, uint32_t *bin_count,
+                                        const uint32_t *bin_off, uint32_t *entries) {
+    const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << 5);
+    const int32_t ra = max(e.ry0, row0), rb = min(min(e.ry1, row0 + 31), (int32_t)P.row_end - 1);
     uint32_t w0, w1;
     edge_windows(e, ra, rb, P, &w0, &w1);
     for (uint32_t w = w0; w <= w1; w++) {
-        const uint32_t bin = tile * P.n_win + w;
-        const uint32_t slot = atomicAdd(&tile_count[bin], 1u);
-        if (FILL) entries[tile_off[bin] + slot] = k;
+        const uint32_t bin = tile * P.b_nwin + w;
+        const uint32_t slot = atomicAdd(&bin_count[bin], 1u);
+        if (FILL) entries[bin_off[bin] + slot] = k;
     }
 }
 template <bool FILL>
 __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
-                                                 const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ tile_count,
-                                                 const uint32_t *__restrict__ tile_off, uint32_t *__restrict__ entries) {
+                                                 const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ bin_count,
+                                                 const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ entries) {
     if (FILL && C->overflow) return;
     const uint32_t nv = C->nv;
     const uint32_t lane = threadIdx.x & 31;
@@ -432,12 +431,12 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
                 const JobState &js = JS[e.job];
                 if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
                     nb = b1 - b0 + 1;
-                    tbase = e.job * P.n_bands;
+                    tbase = e.job * P.b_nbands;
                 }
             }
         }
         if (nb > 0 && nb <= 4)
-            for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k, tbase + b, b, P, tile_count, tile_off, entries);
+            for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k, tbase + b, b, P, bin_count, bin_off, entries);
         uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
         while (tall) {
             int src = __ffs(tall) - 1;
@@ -445,7 +444,7 @@ __global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, 
             uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src);
             uint32_t stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
             const EdgeRec es = E[k0 + src];
-            for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + src, stb + sb0 + b, sb0 + b, P, tile_count, tile_off, entries);
+            for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);
         }
     }
 }

@@ -14,7 +14,13 @@ struct AddU32 {
 struct SumHeadOp {
     typedef SumHead T;
     static __device__ __forceinline__ T identity() { return {0u, NONE32}; }
-    static __device__ __forceinline__ T combine(T a, T b) { return {a.sum + b.sum, b.head != NONE32 ? a.sum + b.head : a.head}; }
+    // the vertex total saturates instead of wrapping: more than 2^32 - 1 vertices then read as "does not fit" (cap_v
+    // is at most 0x7FFFFFFF), never as a small wrapped count that would pass the capacity guard
+    static __device__ __forceinline__ T combine(T a, T b) {
+        uint32_t s = a.sum + b.sum;
+        if (s < a.sum) s = 0xFFFFFFFFu;
+        return {s, b.head != NONE32 ? a.sum + b.head : a.head};
+    }
     static __device__ __forceinline__ T shfl_up(T v, int d) {
         return {__shfl_up_sync(0xFFFFFFFFu, v.sum, d), __shfl_up_sync(0xFFFFFFFFu, v.head, d)};
     }

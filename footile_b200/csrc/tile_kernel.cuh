@@ -598,17 +598,16 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// The tile kernel.  Every WARP owns a private shared-memory row window
-// (`win_chunks` chunks of 512 cells + their masks) and walks the rows of a
-// (job, band) tile on its own: its lanes scatter the coverage of the edges
-// crossing the row, then the row is resolved and written, window after
-// window, with the running sum carried across windows.  Warps never wait for
-// each other, and the small window keeps many warps resident per SM, which is
-// what hides the latency of the serial scatter -> scan -> store chain.
-template <int FMT, bool ALIGNED, bool GENERAL>
+// The direct tile kernel: jobs with at most DIRECT_MAX edge slots (polygons, stars, most layers of a scene).
+// Every WARP owns a private shared-memory row window (`win_chunks` chunks of 512 cells + their masks) and
+// walks the rows of a (job, band) tile on its own: its lanes scatter the coverage of the job's edges
+// crossing the row, then the row is resolved and written, window after window, with the running sum
+// carried across windows.  Warps never wait for each other, and the small window keeps many warps
+// resident per SM, which is what hides the latency of the serial scatter -> scan -> store chain.
+// Jobs with more edges are drawn by raster_bins (bin_kernel.cuh).
+template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
-                                                       const JobState *__restrict__ JS, Params P, const uint32_t *__restrict__ tile_off,
-                                                       const uint32_t *__restrict__ entries, const Counters *__restrict__ C) {
+                                                       const JobState *__restrict__ JS, Params P, const Counters *__restrict__ C) {
     if (C->overflow) return;
     extern __shared__ __align__(16) int32_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
@@ -619,8 +618,7 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
     const uint32_t bpp = P.bpp;
     const uint32_t n_warps = gridDim.x * warps_per_cta;
     // analytic rows need full 16-pixel groups on 16-byte boundaries (and group indices below 0xFFFF)
-    constexpr bool ANALYTIC = ALIGNED && !GENERAL;
-    const bool analytic_ok = ANALYTIC && (P.W & 15u) == 0 && (P.W >> 4) < 0xFFFFu;
+    const bool analytic_ok = ALIGNED && (P.W & 15u) == 0 && (P.W >> 4) < 0xFFFFu;
     uint32_t j = (P.tile_begin + blockIdx.x * warps_per_cta + warp) / P.n_bands, j_next = 0;
     for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps, j = j_next) {
         const uint32_t band = tile - j * P.n_bands;
@@ -638,28 +636,22 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
         if (row_hi > (int32_t)P.row_end) row_hi = (int32_t)P.row_end;
         if (row0 < js.first_row) row0 = js.first_row;  // rows above the figure are untouched (fig.rs:497)
         if (row0 >= row_hi) continue;
+        const uint32_t ne = js.vtx_end - js.vtx_begin, e0 = js.vtx_begin;
+        if (ne > DIRECT_MAX) continue;  // a binned job: raster_bins draws it
         const unsigned long long raster = jobs[j].raster;
         const uint32_t rule = jobs[j].rule, color = jobs[j].color;
-        const uint32_t n_slots = js.vtx_end - js.vtx_begin;
-        // Edge list of the tile: the job's own edges (direct: at most DIRECT_MAX slots; the only case
-        // when GENERAL is false), or the (tile, window) bins.  With a single list for all windows the
-        // first 32 edges stay in registers for all rows of the tile.
-        const bool direct = !GENERAL || n_slots <= DIRECT_MAX;
-        const bool one_list = !GENERAL || direct || P.n_win == 1;
-        uint32_t e0 = direct ? js.vtx_begin : tile_off[tile * P.n_win];
-        uint32_t ne = direct ? n_slots : tile_off[tile * P.n_win + 1] - e0;
         // Row groups: with few edges the 32 lanes are (row, edge) pairs of 4 (or 2) consecutive rows, so
         // the per-(edge,row) set-up of several rows costs one pass; each row then scatters with its own lanes.
-        const uint32_t gl = !one_list ? 5u : (ne <= 8 ? 3u : (ne <= 16 ? 4u : 5u));
+        const uint32_t gl = ne <= 8 ? 3u : (ne <= 16 ? 4u : 5u);
         const uint32_t my_e = lane & ((1u << gl) - 1u), my_r = lane >> gl;
         // Narrow rasters (one window per row) with lanes = edges: the window holds `win_rows` rows, every
         // lane scatters all the rows of its edges in one pass, then the rows are resolved one by one.
-        const bool multi = gl == 5u && one_list && P.win_rows > 1u;
+        const bool multi = gl == 5u && P.win_rows > 1u;
         const int32_t rows_per_pass = multi ? (int32_t)P.win_rows : (int32_t)(32u >> gl);
         const uint32_t row_bytes = 4u * P.win_chunks * CHUNK, rmask_bytes = 4u * P.win_chunks;
         EdgeRec mine;
         mine.flags = 0;
-        if (one_list && my_e < ne) mine = E[direct ? e0 + my_e : entries[e0 + my_e]];
+        if (my_e < ne) mine = E[e0 + my_e];
         uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(row0 - (int32_t)P.row_begin) * P.pitch;
         const uint32_t win_bytes = (uint32_t)win_cells * bpp;
         for (int32_t ry_base = row0; ry_base < row_hi; ry_base += rows_per_pass) {
@@ -679,24 +671,17 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
                 const int32_t ry = ry_base + rr;
                 const uint32_t rcells = multi ? cells + (uint32_t)rr * row_bytes : cells, rmask = multi ? mask + (uint32_t)rr * rmask_bytes : mask;
                 int32_t carry = 0;
-                uint32_t bin = tile * P.n_win;
                 uint8_t *dwin = dst;
-                for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, bin++, dwin += win_bytes) {
+                for (int32_t win_lo = 0; win_lo < W; win_lo += win_cells, dwin += win_bytes) {
                     const int32_t win_hi = min(W, win_lo + win_cells);
                     // ---- (c) scatter: one lane per edge crossing this row (multi: all rows of the pass at once) ----
                     if (!multi || rr == 0) {
                         uint32_t first = 32;
                         if (multi) first = 0;
-                        else if (one_list) {
-                            if ((int32_t)my_r == rr) edge_row_scatter(st, win_lo, win_hi, cells, mask);
-                        } else {  // wide raster with many edges: each window has its own bin
-                            e0 = tile_off[bin];
-                            ne = tile_off[bin + 1] - e0;
-                            first = 0;
-                        }
+                        else if ((int32_t)my_r == rr) edge_row_scatter(st, win_lo, win_hi, cells, mask);
                         const int32_t ra = multi ? ry_base : ry, rb = multi ? ry_last : ry;
                         for (uint32_t i = lane + first; i < ne; i += 32) {
-                            const EdgeRec e = (multi && i < 32) ? mine : E[direct ? e0 + i : entries[e0 + i]];
+                            const EdgeRec e = (multi && i < 32) ? mine : E[e0 + i];
                             if (!(e.flags & 1u)) continue;
                             const int32_t r1 = min(e.ry1, rb);
                             for (int32_t r = max(e.ry0, ra); r <= r1; r++) {

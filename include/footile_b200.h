@@ -16,6 +16,15 @@
  *     `&mut self` on every drawing call); distinct handles are independent;
  *   - there is NO CPU fallback: without a CUDA device every compute entry
  *     point fails with FTL_ERR_NO_DEVICE.
+ *
+ * Deliberate deviations from the reference (all towards "draw what was asked"):
+ *   - vertex ids are 32-bit: the reference stores them in a u16 (src/vid.rs:20-24) and
+ *     Fig::add_point silently drops every point once 65 535 are stored (src/fig.rs:430); fills here
+ *     render all points (up to 2^31 - 1 per call).  The stroker keeps the reference's cap per
+ *     stroke (src/stroker.rs:63).  Inputs that stay below 65 535 flattened points per fill - every
+ *     example and benchmark of the reference - are unaffected;
+ *   - curve subdivision is capped at depth 16 (the reference recurses without bound, README.md:32-33);
+ *   - NaN/Inf coordinates are rejected with FTL_ERR_NONFINITE instead of recursing forever.
  */
 #ifndef FOOTILE_B200_H
 #define FOOTILE_B200_H

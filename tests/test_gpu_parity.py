@@ -363,7 +363,7 @@ def test_config3_stroke_scenes_small(join):  # examples/*.rs at their own size
         assert g.raster().pixels.any(), name
 
 
-@pytest.mark.parametrize("join", [JoinStyle.Round, JoinStyle.Miter(4.0)])
+@pytest.mark.parametrize("join", [JoinStyle.Round, JoinStyle.Miter(4.0), JoinStyle.Bevel])
 def test_config3_strokes_4k_rgba(join):  # 3840x2160 Rgba8p over (64,128,64,255), scenes x30
     w, h = 3840, 2160
     base = Raster.with_color(w, h, Format.Rgba8p, (64, 128, 64, 255)).pixels
@@ -372,6 +372,35 @@ def test_config3_strokes_4k_rgba(join):  # 3840x2160 Rgba8
         g.stroke(path, (255, 255, 0, 255))
         o.stroke(path, (255, 255, 0, 255))
     assert_same(g, o)
+
+
+def _round_rs(join):
+    """examples/round.rs:9-17 with the given join: 100x100 Matte8, pen width 40, (10,60) -> (60,60) -> (60,10)."""
+    path = scenes.stroke_scenes(1.0)["round"]
+    g, o = both(100, 100, Format.Matte8, join=join)
+    g.stroke(path, (255,))
+    o.stroke(path, (255,))
+    assert_same(g, o, str(join))
+    return g.raster().pixels
+
+
+def test_stroke_join_semantics_outer_corner():
+    """A guard on the recalled pointy semantics (right(), angle_rel, intersection: SURVEY App. B): with the
+    wrong sign of right() GPU and oracle would still agree, but the join would land on the INNER corner.
+    The path turns at (60,60); the outer corner is towards (80,80), the inner one towards (40,40)
+    (stroker.rs:301-309 round_point, 380-396 miter / bevel)."""
+    rnd = _round_rs(JoinStyle.Round)
+    # round join: a disc of radius 20 about (60,60) - (73,73) is 18.4 away (inside), (78,78) 25.5 away (outside)
+    assert rnd[73, 73] == 255 and rnd[78, 78] == 0
+    assert rnd[66, 76] == 255 and rnd[76, 66] == 255  # inside the disc (17.7 from the corner), outside the bevel chord x + y = 140
+    mit = _round_rs(JoinStyle.Miter(4.0))
+    assert mit[78, 78] == 255 and mit[73, 73] == 255   # the miter tip reaches (80,80)
+    bev = _round_rs(JoinStyle.Bevel)
+    assert bev[73, 73] == 0 and bev[68, 68] == 255     # the bevel is the chord (60,80)-(80,60): x + y = 140
+    for img in (rnd, mit, bev):
+        assert img[45, 45] == 255 and img[35, 35] == 0  # inner corner: inside both strokes at (45,45), nothing at (35,35)
+        assert img[70, 20] == 255 and img[20, 70] == 255 and img[5, 5] == 0  # the two straight runs (rows = y, columns = x)
+        assert img[60, 85] == 0 and img[85, 60] == 0    # butt ends are not extended past the outer edges (x = 80, y = 80)
 
 
 # ---- config 4: batch of random curve paths -------------------------------------
@@ -477,6 +506,58 @@ def test_config5_many_subfigures_and_bands():
             assert np.array_equal(gb.raster().pixels, exp[r0:r1]), (rule, k)
 
 
+_C5 = {}
+
+
+def _config5_full(rule):
+    """BASELINE.json configs[4] at FULL size: one 32768x32768 Matte8 raster, 160 000 closed 64-gons (10.24 M
+    edges) in ONE fill (fig.rs:480-502).  Cached per rule: (ops, device raster as a host array, fill info)."""
+    if rule not in _C5:
+        size = 32768
+        if "ops" not in _C5:
+            _C5["ops"] = scenes.random_polygons(0, 160000, vertices=64, size=size, extent=2048)
+        g = Plotter.with_clear(size, size, Format.Matte8)
+        g.fill(rule, _C5["ops"], (255,))
+        _C5[rule] = (g.raster().pixels, g.debug_last_fill())
+        del g
+    return _C5["ops"], _C5[rule][0], _C5[rule][1]
+
+
+@pytest.mark.parametrize("rule", [FillRule.EvenOdd, FillRule.NonZero])
+def test_config5_full_size_stripes_vs_oracle(rule):
+    """Seeded 16-row stripes of the full-size fill against the order-free oracle (u32 vertex ids): every stripe
+    walks all 10.24 M edges on the CPU, so 8 stripes per rule is what a few seconds allow."""
+    size, rows = 32768, 16
+    ops, full, info = _config5_full(rule)
+    rng = np.random.default_rng(5 + int(rule))
+    starts = [0, size - rows] + [int(r) for r in rng.integers(0, size - rows, 6)]
+    o = oracle.Plotter(size, size, oracle.MATTE8, vid_cap=1 << 30, orderfree=True)
+    for r0 in starts:
+        o.set_rows(r0, r0 + rows)
+        o.fill(int(rule), ops, (255,))
+        assert o.last_info() == info
+        exp = o.raster()[r0: r0 + rows]
+        got = full[r0: r0 + rows]
+        assert np.array_equal(exp, got), "rule %s rows %d..%d: %d bytes differ" % (rule, r0, r0 + rows, int((exp != got).sum()))
+    # size-independent properties of the whole raster: a dense scene covers most pixels, and both rules agree
+    # wherever the NonZero matte is empty
+    assert np.count_nonzero(full[::64]) > 0.5 * full[::64].size
+
+
+def test_config5_full_size_row_bands_equal_unsplit():
+    """The multi-GPU layout of config 5: 4 row bands on their own handles reproduce the unsplit raster."""
+    size = 32768
+    ops, full, info = _config5_full(FillRule.EvenOdd)
+    for k in range(4):
+        r0, r1 = k * size // 4, (k + 1) * size // 4
+        gb = Plotter.with_clear(size, size, Format.Matte8, rows=(r0, r1))
+        gb.fill(FillRule.EvenOdd, ops, (255,))
+        assert gb.debug_last_fill() == info
+        assert np.array_equal(gb.raster().pixels, full[r0:r1]), k
+        del gb
+    _C5.clear()
+
+
 def test_sequential_oracle_agrees_on_many_subfigures():
     size = 512
     ops = scenes.random_polygons(7, 40, vertices=16, size=size, extent=128)
@@ -519,6 +600,32 @@ def test_speculative_capacity_overflow_is_recovered():
         g.fill(FillRule.NonZero, ops, clr)  # non-idempotent blend: a repeated or dropped pass would show
         o.fill(oracle.NONZERO, ops, clr)
     assert_same(g, o)
+
+
+def test_clear_after_an_overflowed_replay_stays_clear():
+    """a speculative replay that overflowed draws nothing and is repeated later; a clear issued in
+    between must come AFTER that repeat.  small fill (sizes the buffers) -> big fill (overflows) -> clear -> read."""
+    rng = np.random.default_rng(3)
+    small = poly([(10, 10), (50, 12), (30, 60)])
+    big = random_path(rng, 256, 60)
+    b = Batch(256, 256, Format.Matte8, 1)
+    one = np.array([0], dtype=np.uint64)
+    b.fill(small, np.array([0, len(small)], dtype=np.uint64))
+    b.fill(big, np.array([0, len(big)], dtype=np.uint64))
+    b.clear()
+    assert not b.read().any()
+    # and a loop of clear(); run() on an overflowing job set leaves exactly one fill in the raster
+    b2 = Batch(256, 256, Format.Rgba8p, 1)
+    clr = np.array([[10, 90, 10, 128]], dtype=np.uint8)
+    b2.fill(small, np.array([0, len(small)], dtype=np.uint64), colors=clr)
+    b2.upload(big, np.array([0, len(big)], dtype=np.uint64), colors=clr)
+    for _ in range(3):
+        b2.clear()
+        b2.run()
+    o = oracle.Plotter(256, 256, oracle.RGBA8P)
+    o.fill(oracle.NONZERO, big, (10, 90, 10, 128))
+    assert np.array_equal(b2.read()[0], o.raster())
+    del one
 
 
 def test_many_async_replays_then_read():

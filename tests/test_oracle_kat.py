@@ -284,3 +284,25 @@ def test_debug_edges_of_a_triangle():
     assert int(shallow[2]) == one // 9 and int(shallow[0]) == 9 * one and int(shallow[3]) == 0 and int(shallow[4]) == one
     assert int(vertical[2]) == 0 and int(vertical[0]) == 0 and int(vertical[3]) == 0 and int(vertical[4]) == one
     assert int(shallow[5]) == -int(vertical[5])  # the two sides wind opposite ways
+
+
+def test_oracle_stroke_join_semantics_outer_corner():
+    """The recalled pointy semantics (right(), angle_rel, Line::intersection: SURVEY App. B) cannot be checked
+    against the crate, but they can be checked against GEOMETRY: examples/round.rs turns at (60,60) with the outer
+    corner towards (80,80).  A flipped right() would put the join on the inner corner (stroker.rs:301-309,380-396)."""
+    from footile_b200 import scenes
+    path = scenes.stroke_scenes(1.0)["round"]
+    imgs = {}
+    for name, kind, limit in (("round", oracle.ROUND, 0.0), ("miter", oracle.MITER, 4.0), ("bevel", oracle.BEVEL, 0.0)):
+        o = oracle.Plotter(100, 100, oracle.MATTE8)
+        o.set_join(kind, limit)
+        o.stroke(path, (255,))
+        imgs[name] = o.raster()
+    assert imgs["round"][73, 73] == 255 and imgs["round"][78, 78] == 0
+    assert imgs["round"][66, 76] == 255 and imgs["round"][76, 66] == 255
+    assert imgs["miter"][78, 78] == 255 and imgs["miter"][73, 73] == 255
+    assert imgs["bevel"][73, 73] == 0 and imgs["bevel"][68, 68] == 255
+    for img in imgs.values():
+        assert img[45, 45] == 255 and img[35, 35] == 0
+        assert img[70, 20] == 255 and img[20, 70] == 255 and img[5, 5] == 0
+        assert img[60, 85] == 0 and img[85, 60] == 0
