@@ -18,7 +18,7 @@ SYMBOLS = [
     "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
     "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
-    "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream",
+    "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream", "ftl_fill_upload", "ftl_fill_replay",
     "ftl_launch_count", "ftl_set_profiling", "ftl_tile_kernel_time",
     "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
 ]
@@ -75,6 +75,8 @@ def lib():
         "ftl_batch_device_ptr": (i32, [vp, vp, vp]),
         "ftl_batch_upload": (i32, [vp, u32, vp, vp, vp, vp, vp]),
         "ftl_batch_run": (i32, [vp]),
+        "ftl_fill_upload": (i32, [vp, i32, vp, sz, vp]),
+        "ftl_fill_replay": (i32, [vp]),
         "ftl_batch_stream": (i32, [vp, vp]),
         "ftl_stream": (i32, [vp, vp]),
         "ftl_launch_count": (C.c_uint64, []),

@@ -3,20 +3,32 @@
 #pragma once
 
 // ---------------------------------------------------------------------------
-// (c)+(d) binned tiles: LANES ARE ROWS
+// (c)+(d) binned tiles
 // ---------------------------------------------------------------------------
-// A tile is (job, band of 32 raster rows, window of WC columns).  One warp owns a tile; lane l owns
-// row l of the band for the whole scatter: the warp walks the tile's edge list (bin_edges), every
-// lane evaluates the SAME edge on ITS row in closed form (fig.rs:238-321,557-600) and adds
-// the span's coverage deltas to its own row of a shared-memory tile of wrapping i16 cells — the
-// reference's own cell type (plotter.rs:45).  Lanes never share a cell, so the adds are plain
-// ld/add/st (no shared-memory atomics: the round-1 scatter spent 2.9 wavefronts per atomic on bank
-// conflicts), the edge record is warp-uniform (staged in shared memory, read by broadcast), control
-// flow is uniform (the same edge has nearly the same span length on neighbouring rows), and the
-// touched-group mask and the row total live in lane registers.  An edge crossing the whole band
-// (the common case for tall edges: config 5) takes a branch-free path with no start / end handling.
+// A tile is (job, band of 32 raster rows, window of WC columns).  One warp owns a tile and a private
+// shared-memory image of it: 32 rows of WC wrapping i16 cells — the reference's own cell type
+// (plotter.rs:45) — two cells per 32-bit word, the low one stored with a bias of 0x8000 (see below).
+// The warp walks the tile's edge list (bin_edges) 32 entries per round and scatters each round in one
+// of two ways:
 //
-// The row is then resolved WC/16 lanes per row (16 cells per lane, packed 16-bit prefix sums), the
+//   T  LANES ARE ROWS (tall edges, dense tiles).  Every lane evaluates the SAME edge on ITS row of the
+//      band in closed form (fig.rs:238-321,557-600) and adds the span's coverage deltas to
+//      its own row with plain 16-bit ld/add/st: lanes never share a cell, so there are no atomics
+//      (the round-1 scatter spent 2.9 wavefronts per shared atomic on bank conflicts), the edge record
+//      is warp-uniform (staged in shared memory, read by broadcast), control flow is uniform (an edge
+//      has nearly the same span length on neighbouring rows) and the row totals live in lane
+//      registers.  An edge crossing the whole band takes a path with no start / end handling.
+//   S  LANES ARE (EDGE, ROW) ITEMS (short edges, sparse tiles: curves flattened to segments a few rows
+//      tall would leave most row-lanes idle).  A prefix sum over the rows each staged edge has inside
+//      the band numbers the round's items; every lane takes an item, finds its edge by a 5-step
+//      search of the prefix and evaluates that row.  Lanes can meet in a cell, so deltas are added with ONE
+//      32-bit red.shared per cell to the word holding the cell pair: delta for the low cell,
+//      delta << 16 for the high one.  A 32-bit add carries from the low cell into the high one when
+//      the low half crosses 0 / 65536; the bias keeps the low half at 0x8000 + (sum so far), so no
+//      add can carry while |sum of the deltas of one cell| < 32768.  A cell receives at most 256 per
+//      edge of the tile, hence S is used only in tiles of fewer than 128 edges: exact, not "almost".
+//
+// The rows are then resolved WC/16 lanes per row (16 cells per lane, packed 16-bit prefix sums), the
 // fill rule applied and the pixels stored / blended exactly as the direct kernel does (emit16).
 //
 // Wide rasters: the running sum of a row crosses windows.  Each (band, window) tile is claimed from
@@ -28,6 +40,20 @@
 // the sums in registers instead.
 constexpr uint32_t BIN_ROWS = 32;
 constexpr uint32_t BIN_LOG2R = 5;
+constexpr uint32_t BIN_ROW_PAD = 16;       // bytes between rows beyond WC * 2: neighbouring rows start 4 banks apart
+constexpr uint32_t BIN_BIAS = 0x00008000u; // resting value of a cell-pair word
+constexpr uint32_t BIN_PACKED_MAX = 128;   // tiles with fewer edges may add deltas as packed 32-bit words
+
+template <int WC>
+struct BinTile {
+    static constexpr uint32_t ROW_BYTES = WC * 2 + BIN_ROW_PAD;
+    static constexpr uint32_t CELL_BYTES = BIN_ROWS * ROW_BYTES;
+    static constexpr uint32_t STAGE = CELL_BYTES;             // 32 staged edge records of 32 bytes
+    static constexpr uint32_t TOT = STAGE + 32 * 32;          // 32 row totals (S rounds)
+    static constexpr uint32_t PREFIX = TOT + 32 * 4;          // inclusive prefix of the items per staged edge (S rounds)
+    static constexpr uint32_t FLAGS = PREFIX + 32 * 4;        // touched-row mask (S rounds)
+    static constexpr uint32_t BYTES = FLAGS + 16;
+};
 
 __device__ __forceinline__ uint32_t slds16(uint32_t a) {
     uint16_t v;
@@ -38,6 +64,9 @@ __device__ __forceinline__ void ssts16(uint32_t a, uint32_t v) { asm volatile("s
 __device__ __forceinline__ void ssts4(uint32_t a, int4 v) {
     asm volatile("st.shared.v4.s32 [%0], {%1, %2, %3, %4};" ::"r"(a), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w));
 }
+__device__ __forceinline__ void ssts4_bias(uint32_t a) {
+    asm volatile("st.shared.v4.u32 [%0], {%1, %1, %1, %1};" ::"r"(a), "r"(BIN_BIAS));
+}
 __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
     uint32_t v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p));
@@ -45,26 +74,23 @@ __device__ __forceinline__ uint32_t ld_relaxed(const uint32_t *p) {
 }
 __device__ __forceinline__ void st_relaxed(uint32_t *p, uint32_t v) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v)); }
 
-// One edge on one row of the band (the lane's row), cells of [win_lo, win_hi) only.
-//   xb        X at the bottom of band row 0 (closed form of advance_edges, fig.rs:569-573)
-//   r0, r1    first / last row of the edge relative to the band
+// One edge on one row, cells of [win_lo, win_hi) only: the span of the row and the coverage of its first cell.
+//   x_bot     X at the bottom of the row (closed form of advance_edges, fig.rs:569-573)
 //   dxs, dxe  inv_slope * (ONE - fract(y_upper)), inv_slope * ((ONE - fract(y_lower)) & MASK)   (fig.rs:244-249,262-278)
 //   misc      pixel_cov(fract(y_upper)) | pixel_cov(fract(y_lower)) << 9 | negative sign << 18
-// FULL: the edge covers every row of a band whose 32 rows are all drawn (no start / end row, cov = 256).
-template <bool FULL>
-__device__ __forceinline__ void bin_item(int32_t xb, int32_t inv_slope, int32_t step, int32_t r0, int32_t r1, int32_t dxs, int32_t dxe, uint32_t misc,
-                                         int32_t rel_row, bool row_ok, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t rbase, uint32_t rx,
-                                         int32_t &tot, uint32_t &mask) {
-    bool act = FULL || (row_ok && rel_row >= r0 && rel_row <= r1);
-    const fx_t x_bot = (fx_t)((uint32_t)xb + (uint32_t)rel_row * (uint32_t)inv_slope);
+// Returns false when the row receives nothing inside the window.  On success: cells [c, ...) receive
+// X(k) - X(k-1) with X(k) = min(pixel_cov(min(xc + k*step, ONE)), cov) and X(-1) = prev (fig.rs:285-321).
+// PLAIN: neither the first nor the last row of the edge (cov = 256).  VOTE: all lanes are here (lanes = rows).
+template <bool PLAIN, bool VOTE>
+__device__ __forceinline__ bool bin_span(fx_t x_bot, int32_t inv_slope, int32_t step, bool starting, bool ending, int32_t dxs, int32_t dxe, uint32_t misc,
+                                         bool act, int32_t W, int32_t win_lo, int32_t win_hi, int32_t &c, int32_t &xc, int32_t &prev, int32_t &cov,
+                                         bool &resumed) {
     fx_t x0, x1;
-    int32_t cov;
-    if (FULL) {
+    if (PLAIN) {
         x0 = fx_sub(x_bot, inv_slope);
         x1 = x_bot;
         cov = 256;
     } else {
-        const bool starting = rel_row == r0, ending = rel_row == r1;
         x0 = fx_sub(x_bot, starting ? dxs : inv_slope);
         x1 = ending ? fx_sub(x_bot, dxe) : x_bot;
         cov = (ending ? (int32_t)((misc >> 9) & 0x1FFu) : 256) - (starting ? (int32_t)(misc & 0x1FFu) : 0);
@@ -73,15 +99,18 @@ __device__ __forceinline__ void bin_item(int32_t xb, int32_t inv_slope, int32_t 
     const fx_t min_x = fx_min(x0, x1), max_x = fx_max(x0, x1);
     const int32_t min_pix = fx_to_i32(min_x), max_pix = fx_to_i32(max_x);
     const int32_t c0 = min_pix > 0 ? min_pix : 0;
-    int32_t c = c0 > win_lo ? c0 : win_lo;
+    c = c0 > win_lo ? c0 : win_lo;
     if (min_pix >= W || c >= win_hi) act = false;
     // first_cov / step_cov (fig.rs:305-321): full_cov = cov / 256 in Fixed = cov << 8, so fx_mul(a, cov << 8) = (a * cov) >> 8
     const int32_t rr = min_pix == max_pix ? (int32_t)(((uint32_t)(FX_ONE - fx_fract(fx_avg(max_x, min_x))) * (uint32_t)cov) >> 8)
                                           : (FX_ONE - fx_fract(min_x)) >> 1;
     const int32_t first = (int32_t)(((uint64_t)(uint32_t)rr * (uint64_t)(uint32_t)step) >> 16);  // step == ONE for a vertical edge: first = rr
-    int32_t xc = first, prev = 0;
-    // a span that starts left of the window (or of the raster): resume inside it (rare: one warp-uniform test)
-    if (__any_sync(0xFFFFFFFFu, act && c != min_pix)) {
+    xc = first;
+    prev = 0;
+    // a span that starts left of the window (or of the raster): resume inside it (rare)
+    const bool resume = act && c != min_pix;
+    resumed = VOTE ? __any_sync(0xFFFFFFFFu, resume) : resume;
+    if (resumed) {
         const int64_t xc64 = (int64_t)first + (int64_t)(c - min_pix) * (int64_t)step;
         xc = (int32_t)(xc64 < (int64_t)FX_ONE ? xc64 : (int64_t)FX_ONE);
         if (c > c0) {
@@ -91,29 +120,72 @@ __device__ __forceinline__ void bin_item(int32_t xb, int32_t inv_slope, int32_t 
             if (prev >= cov) act = false;
         }
     }
+    return act;
+}
+
+// T: the lane's row of one staged edge, plain 16-bit read-modify-write of the lane's own cells.
+//   xb  X at the bottom of band row 0;  r0, r1  first / last row of the edge relative to the band;  ed  +1 / -1 (fig.rs:286)
+template <bool FULL>
+__device__ __forceinline__ void bin_item_rows(int32_t xb, int32_t inv_slope, int32_t step, int32_t r0, int32_t r1, int32_t dxs, int32_t dxe, uint32_t misc,
+                                              int32_t ed, int32_t rel_row, bool row_ok, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t rbase, int32_t &tot) {
+    const fx_t x_bot = (fx_t)((uint32_t)xb + (uint32_t)rel_row * (uint32_t)inv_slope);
+    int32_t c, xc, prev, cov;
+    bool resumed;
+    const bool act = bin_span<FULL, true>(x_bot, inv_slope, step, rel_row == r0, rel_row == r1, dxs, dxe, misc,
+                                          FULL || (row_ok && rel_row >= r0 && rel_row <= r1), W, win_lo, win_hi, c, xc, prev, cov, resumed);
+    uint32_t a = rbase + ((uint32_t)(c - win_lo) << 1);
+    const uint32_t a_end = rbase + ((uint32_t)(win_hi - win_lo) << 1);
+    if (step == FX_ONE && !resumed) {
+        // |dx/dy| <= 1 (warp-uniform): the span covers at most two cells, X(0) = pixel_cov(first) and X(1) = cov - no loop
+        if (act) {
+            int32_t x0 = (xc + 128) >> 8;
+            if (x0 > cov) x0 = cov;
+            ssts16(a, slds16(a) + (uint32_t)(ed * x0));
+            const bool two = x0 < cov && a + 2 < a_end;
+            if (two) ssts16(a + 2, slds16(a + 2) + (uint32_t)(ed * (cov - x0)));
+            tot += ed * (two ? cov : x0);
+        }
+        return;
+    }
     if (act) {
-        const int32_t ed = (misc & (1u << 18)) ? -1 : 1;
-        const int32_t prev0 = prev, rel0 = c - win_lo;
-        int32_t rel = rel0;
-        const int32_t end_rel = win_hi - win_lo;
-        for (;;) {  // scan_area (fig.rs:285-302): cell k receives X(k) - X(k-1), X(k) = min(pixel_cov(min(first + k*step, ONE)), cov)
-            int32_t xk = (xc + 128) >> 8;  // pixel_cov of a value in [0, ONE]
+        const int32_t prev0 = prev;
+        int32_t xr = xc + 128;  // pixel_cov of a value in [0, ONE] is (x + 128) >> 8
+        for (;;) {
+            int32_t xk = xr >> 8;
             if (xk > cov) xk = cov;
-            const int32_t d = xk - prev;
-            if (d != 0) {
-                const uint32_t a = rbase + (((uint32_t)rel << 1) ^ rx);
-                ssts16(a, slds16(a) + (uint32_t)(ed * d));
-            }
+            ssts16(a, slds16(a) + (uint32_t)(ed * (xk - prev)));
             prev = xk;
-            rel++;
-            xc += step;
-            if (xc > FX_ONE) xc = FX_ONE;
-            if (xk >= cov || rel >= end_rel) break;
+            a += 2;
+            xr = min(xr + step, FX_ONE + 128);
+            if (xk >= cov || a >= a_end) break;
         }
         tot += ed * (prev - prev0);
-        const uint32_t g0 = (uint32_t)rel0 >> 3, g1 = (uint32_t)(rel - 1) >> 3;  // 8-cell groups touched
-        mask |= ((2u << (g1 - g0)) - 1u) << g0;
     }
+}
+
+// S: one (edge, row) item of a staged edge, packed 32-bit adds (see the file header for why they are exact here).
+template <int WC>
+__device__ __forceinline__ void bin_item_packed(int32_t xb, int32_t inv_slope, int32_t step, int32_t r0, int32_t r1, int32_t dxs, int32_t dxe, uint32_t misc,
+                                                int32_t ed, int32_t rel_row, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t cells, uint32_t totbase) {
+    const fx_t x_bot = (fx_t)((uint32_t)xb + (uint32_t)rel_row * (uint32_t)inv_slope);
+    int32_t c, xc, prev, cov;
+    bool resumed;
+    if (!bin_span<false, false>(x_bot, inv_slope, step, rel_row == r0, rel_row == r1, dxs, dxe, misc, true, W, win_lo, win_hi, c, xc, prev, cov, resumed)) return;
+    const int32_t prev0 = prev;
+    const uint32_t rbase = cells + (uint32_t)rel_row * BinTile<WC>::ROW_BYTES;
+    int32_t rel = c - win_lo;
+    const int32_t end_rel = win_hi - win_lo;
+    int32_t xr = xc + 128;
+    for (;;) {
+        int32_t xk = xr >> 8;
+        if (xk > cov) xk = cov;
+        sred_add(rbase + (((uint32_t)rel >> 1) << 2), (ed * (xk - prev)) << ((rel & 1) << 4));
+        prev = xk;
+        rel++;
+        xr = min(xr + step, FX_ONE + 128);
+        if (xk >= cov || rel >= end_rel) break;
+    }
+    sred_add(totbase + 4u * (uint32_t)rel_row, ed * (prev - prev0));
 }
 
 // alpha bytes of four consecutive pixels from two words of packed wrapped-i16 sums (lo = pixel 2j, hi = pixel 2j+1)
@@ -187,6 +259,7 @@ __device__ __forceinline__ void bin_const_tile(int32_t carry, uint32_t valid_mas
 #pragma unroll
             for (int i = 0; i < 8; i++) {
                 const uint32_t u = u0 + l8 + 8u * i;
+                t[i] = make_uint4(0u, 0u, 0u, 0u);
                 if (ok && u < row_u4 && !opaque) t[i] = p[u];
             }
 #pragma unroll
@@ -199,14 +272,13 @@ __device__ __forceinline__ void bin_const_tile(int32_t carry, uint32_t valid_mas
 }
 
 // Resolve the warp's tile: rows of WC cells, WC/16 lanes per row, 32/(WC/16) rows per step.
-//   mask / carry : this LANE's row (lane = row): touched 8-cell groups, running sum reaching the window
+//   touched : rows that received deltas;   carry : this LANE's row (lane = row): running sum reaching the window
 template <int FMT, bool EVEN_ODD, bool ALIGNED, int WC>
-__device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t mask, int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch,
+__device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t touched, int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch,
                                             uint32_t w_rel, uint32_t color) {
     constexpr uint32_t LPR = WC / 16, RPS = 32 / LPR;
     const uint32_t lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
     const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
-    const uint32_t touched = __ballot_sync(0xFFFFFFFFu, mask != 0);
     if (FMT != FTL_MATTE8 && ALIGNED && touched == 0 && w_rel >= (uint32_t)WC) {
         constexpr uint32_t U = FMT == FTL_GRAYA8P ? 2u : 4u;  // 16-byte words per 16 pixels
         bin_const_tile<FMT, EVEN_ODD>(carry, valid_mask, dst_win, pitch, LPR * U, color, clr_a);
@@ -215,9 +287,8 @@ __device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t mask, int32
 #pragma unroll 1
     for (uint32_t s = 0; s < BIN_ROWS; s += RPS) {
         const uint32_t row = s + sub;
-        const uint32_t m = __shfl_sync(0xFFFFFFFFu, mask, row);
         const int32_t cr = __shfl_sync(0xFFFFFFFFu, carry, row);
-        const uint32_t step_rows = ((RPS == 32 ? 0u : (1u << RPS)) - 1u) << s;
+        const uint32_t step_rows = ((1u << RPS) - 1u) << s;
         if (!(valid_mask & step_rows)) continue;
         const bool ok = (valid_mask >> row) & 1u;
         uint8_t *drow = dst_win + (size_t)row * pitch;
@@ -226,17 +297,17 @@ __device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t mask, int32
             if (ok) emit16<FMT, ALIGNED>(drow, 16 * l, w_rel, q, q, q, q, color, clr_a);
             continue;
         }
-        int4 v0 = make_int4(0, 0, 0, 0), v1 = v0;
-        const uint32_t rowaddr = cells + row * (uint32_t)(WC * 2), rxg = row & 7u;
-        if ((m >> (2 * l)) & 1u) {
-            const uint32_t a = rowaddr + (((2 * l) ^ rxg) << 4);
+        // every lane reads its 16 cells, touched row or not (an untouched row holds the resting value): a per-lane
+        // branch here leaves the half-warps diverged for the rest of the step and every instruction issues twice
+        int4 v0, v1;
+        {
+            const uint32_t a = cells + row * BinTile<WC>::ROW_BYTES + 32u * l;
             v0 = slds4(a);
-            ssts4_zero(a);
-        }
-        if ((m >> (2 * l + 1)) & 1u) {
-            const uint32_t a = rowaddr + (((2 * l + 1) ^ rxg) << 4);
-            v1 = slds4(a);
-            ssts4_zero(a);
+            v1 = slds4(a + 16u);
+            ssts4_bias(a);
+            ssts4_bias(a + 16u);
+            v0.x ^= BIN_BIAS; v0.y ^= BIN_BIAS; v0.z ^= BIN_BIAS; v0.w ^= BIN_BIAS;
+            v1.x ^= BIN_BIAS; v1.y ^= BIN_BIAS; v1.z ^= BIN_BIAS; v1.w ^= BIN_BIAS;
         }
         // packed prefix inside each word: (lo, hi) -> (lo, lo + hi) mod 2^16
         const uint32_t p0 = (uint32_t)v0.x * 0x00010001u, p1 = (uint32_t)v0.y * 0x00010001u, p2 = (uint32_t)v0.z * 0x00010001u,
@@ -261,16 +332,22 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
                                                   const uint32_t *__restrict__ bin_off, const uint32_t *__restrict__ entries,
                                                   const Counters *__restrict__ C, uint32_t *__restrict__ ticket, uint32_t *__restrict__ look,
                                                   uint32_t epoch) {
-    if (C->overflow) return;
+    if (C->overflow || C->n_big == 0) return;
+    typedef BinTile<WC> T;
     extern __shared__ __align__(16) uint8_t bin_smem[];
     const uint32_t lane = threadIdx.x;
-    const uint32_t cells = smem_addr(bin_smem), stage = cells + BIN_ROWS * WC * 2;
-    for (uint32_t i = lane; i < BIN_ROWS * WC * 2 / 16; i += 32) ssts4_zero(cells + 16u * i);
+    uint32_t cells = smem_addr(bin_smem);
+    asm volatile("" : "+r"(cells));  // opaque: keep the shared-window base in a register instead of rebuilding it at every access
+    const uint32_t stage = cells + T::STAGE, totbase = cells + T::TOT, prefix = cells + T::PREFIX, flags = cells + T::FLAGS;
+    uint32_t sp = stage;
+    for (uint32_t i = lane; i < T::CELL_BYTES / 16; i += 32) ssts4_bias(cells + 16u * i);
+    ssts(totbase + 4u * lane, 0u);
+    if (lane == 0) ssts(flags, 0u);
     __syncwarp();
     const int32_t W = (int32_t)P.W;
     const uint32_t tiles_per_win = (P.job_end - P.job_begin) * P.b_nbands;
     const uint32_t n_tasks = P.b_lookback ? tiles_per_win * P.b_nwin : tiles_per_win;
-    const uint32_t rbase = cells + lane * (uint32_t)(WC * 2), rx = (lane & 7u) << 4;
+    const uint32_t rbase = cells + lane * T::ROW_BYTES;
     for (;;) {
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(ticket, 1u);
@@ -291,6 +368,7 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
         const uint32_t valid_mask = __ballot_sync(0xFFFFFFFFu, row_ok);
         if (valid_mask == 0) continue;
         const bool band_full = valid_mask == 0xFFFFFFFFu;
+        const int32_t v_lo = __ffs((int)valid_mask) - 1, v_hi = 31 - __clz((int)valid_mask);  // the drawn rows are one contiguous range
         const unsigned long long raster = jobs[j].raster;
         const uint32_t rule = jobs[j].rule, color = jobs[j].color;
         uint8_t *dst = reinterpret_cast<uint8_t *>(raster) + (size_t)(row0 - (int32_t)P.row_begin) * P.pitch;
@@ -300,57 +378,98 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
             const uint32_t e0 = bin_off[bin], ne = bin_off[bin + 1] - e0;
             const int32_t win_lo = (int32_t)(w * (uint32_t)WC), win_hi = min(W, win_lo + WC);
             int32_t tot = 0;
-            uint32_t mask = 0;
-            // ---- (c) scatter: the warp walks the bin, 32 records staged per round, the next round's gather in flight ----
+            bool row_touched = false, any_s = false;
+            // ---- (c) scatter: the warp walks the bin, 32 records per round, the next round's gather in flight ----
             EdgeRec nxt;
             nxt.flags = 0;
+            nxt.ry0 = 0;
+            nxt.ry1 = -1;
             if (lane < ne) nxt = E[entries[e0 + lane]];
             for (uint32_t base = 0; base < ne; base += 32) {
                 const EdgeRec e = nxt;
-                if (base + lane < ne) {
-                    // everything that does not depend on the row, once per (edge, band)
+                const bool have = base + lane < ne;
+                if (base + 32 + lane < ne) nxt = E[entries[e0 + base + 32 + lane]];
+                // everything that does not depend on the row, once per (edge, band)
+                const int32_t r0 = e.ry0 - row0, r1 = e.ry1 - row0;
+                const int32_t nrows = have ? max(min(r1, v_hi) - max(r0, v_lo) + 1, 0) : 0;
+                if (have) {
                     const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
+                    const bool full = band_full && r0 < 0 && r1 >= (int32_t)BIN_ROWS;
                     int4 a, b;
                     a.x = (int32_t)((uint32_t)e.x_bot0 + (uint32_t)(row0 - e.ry0) * (uint32_t)e.inv_slope);
                     a.y = e.inv_slope;
                     a.z = e.step_pix > 0 ? e.step_pix : FX_ONE;
-                    a.w = e.ry0 - row0;
-                    b.x = e.ry1 - row0;
+                    a.w = (max(r0, -1) + 1) | (min(r1, (int32_t)BIN_ROWS) << 8);  // rows relative to the band, clamped just outside it
+                    b.x = (e.flags & 2u) ? -1 : 1;
                     b.y = fx_mul(e.inv_slope, FX_ONE - fr0);
                     b.z = fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK);
-                    b.w = (int32_t)((uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9) | ((e.flags & 2u) << 17));
+                    b.w = (int32_t)((uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9) | (full ? 1u << 19 : 0u));
                     ssts4(stage + lane * 32u, a);
                     ssts4(stage + lane * 32u + 16u, b);
                 }
-                if (base + 32 + lane < ne) nxt = E[entries[e0 + base + 32 + lane]];
-                __syncwarp();
+                // items (rows inside the band) of this round: short edges go lanes = items, tall ones lanes = rows
+                int32_t incl = nrows;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) scan_step<32>(incl, d);
+                const int32_t n_items = __shfl_sync(0xFFFFFFFFu, incl, 31);
                 const uint32_t cnt = min(32u, ne - base);
+                const bool packed = ne < BIN_PACKED_MAX && (uint32_t)n_items < 12u * cnt;
+                if (packed) ssts(prefix + 4u * lane, (uint32_t)incl);
+                __syncwarp();
+                if (packed) {
+                    if (nrows > 0) sred_or(flags, ((2u << (nrows - 1)) - 1u) << max(r0, v_lo));
+                    any_s = true;
 #pragma unroll 1
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const int4 a = slds4(stage + k * 32u), b = slds4(stage + k * 32u + 16u);
-                    if (band_full && a.w < 0 && b.x >= (int32_t)BIN_ROWS)
-                        bin_item<true>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, (uint32_t)b.w, (int32_t)lane, true, W, win_lo, win_hi, rbase, rx, tot, mask);
-                    else
-                        bin_item<false>(a.x, a.y, a.z, a.w, b.x, b.y, b.z, (uint32_t)b.w, (int32_t)lane, row_ok, W, win_lo, win_hi, rbase, rx, tot, mask);
+                    for (int32_t q = (int32_t)lane; q < n_items; q += 32) {
+                        uint32_t k = 0;  // the staged edge owning item q: first k with incl[k] > q
+#pragma unroll
+                        for (uint32_t h = 16; h > 0; h >>= 1)
+                            if ((int32_t)slds(prefix + 4u * (k + h - 1)) <= q) k += h;
+                        const int32_t before = k ? (int32_t)slds(prefix + 4u * (k - 1)) : 0;
+                        const int4 a = slds4(stage + k * 32u), b = slds4(stage + k * 32u + 16u);
+                        const int32_t er0 = (a.w & 0xFF) - 1, er1 = a.w >> 8;
+                        bin_item_packed<WC>(a.x, a.y, a.z, er0, er1, b.y, b.z, (uint32_t)b.w, b.x, max(er0, v_lo) + (q - before), W, win_lo, win_hi, cells, totbase);
+                    }
+                } else {
+                    row_touched = true;
+#pragma unroll 1
+                    for (uint32_t k = 0; k < cnt; k++, sp += 32u) {
+                        const int4 a = slds4(sp), b = slds4(sp + 16u);
+                        if (b.w & (1 << 19))
+                            bin_item_rows<true>(a.x, a.y, a.z, 0, 0, b.y, b.z, (uint32_t)b.w, b.x, (int32_t)lane, true, W, win_lo, win_hi, rbase, tot);
+                        else
+                            bin_item_rows<false>(a.x, a.y, a.z, (a.w & 0xFF) - 1, a.w >> 8, b.y, b.z, (uint32_t)b.w, b.x, (int32_t)lane, row_ok, W, win_lo, win_hi, rbase, tot);
+                    }
+                    sp = stage;
                 }
                 __syncwarp();
+            }
+            uint32_t touched = __ballot_sync(0xFFFFFFFFu, row_touched && row_ok);
+            if (any_s) {  // totals and touched rows of the lanes = edges rounds
+                __syncwarp();
+                tot += (int32_t)slds(totbase + 4u * lane);
+                touched |= slds(flags);
+                __syncwarp();
+                ssts(totbase + 4u * lane, 0u);
+                if (lane == 0) ssts(flags, 0u);
             }
             // ---- the sums reaching this window / leaving it ----
             if (P.b_lookback) {
                 if (w > 0) {
                     const uint32_t *src = look + (size_t)(bin - 1) * 32u + lane;
-                    uint32_t v;
-                    do {
+                    uint32_t v = ld_relaxed(src);
+                    while (!__all_sync(0xFFFFFFFFu, (v >> 16) == epoch)) {
+                        __nanosleep(64);
                         v = ld_relaxed(src);
-                    } while (!__all_sync(0xFFFFFFFFu, (v >> 16) == epoch));
+                    }
                     carry = (int32_t)(v & 0xFFFFu);
                 }
                 if (w + 1 < P.b_nwin) st_relaxed(look + (size_t)bin * 32u + lane, (epoch << 16) | ((uint32_t)(carry + tot) & 0xFFFFu));
             }
             // ---- (d) resolve ----
             uint8_t *dwin = dst + (size_t)win_lo * P.bpp;
-            if (rule == FTL_EVENODD) bin_resolve<FMT, true, ALIGNED, WC>(cells, mask, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
-            else bin_resolve<FMT, false, ALIGNED, WC>(cells, mask, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
+            if (rule == FTL_EVENODD) bin_resolve<FMT, true, ALIGNED, WC>(cells, touched, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
+            else bin_resolve<FMT, false, ALIGNED, WC>(cells, touched, carry, valid_mask, dwin, P.pitch, (uint32_t)(W - win_lo), color);
             __syncwarp();
             carry += tot;
         }

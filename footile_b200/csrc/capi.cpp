@@ -125,7 +125,7 @@ int ftl_set_join(ftl_plotter *p, int join, float miter_limit) {
     return FTL_OK;
 }
 
-static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
+static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color, bool upload_only = false) {
     if (rule != FTL_NONZERO && rule != FTL_EVENODD) return bad("unknown fill rule");
     if (n_ops && !ops) return bad("ops is null");
     std::vector<HostJob> jobs(1);
@@ -136,7 +136,7 @@ static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_
     j.rule = rule;
     if (color) memcpy(j.color, color, p->geo.bpp());
     j.raster = p->raster;
-    int rc = p->eng.fill(p->geo, jobs, ops, n_ops);
+    int rc = upload_only ? p->eng.upload(p->geo, jobs, ops, n_ops) : p->eng.fill(p->geo, jobs, ops, n_ops);
     if (rc) return rc;  // a rejected call leaves the plotter state alone
     // PenWidth persists on the plotter across calls (plotter.rs:151-153)
     for (size_t i = 0; i < n_ops; i++)
@@ -148,6 +148,19 @@ int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, con
     GUARD_BEGIN
     if (!p) return bad("null plotter");
     return plot_fill(p, rule, ops, n_ops, color);
+    GUARD_END
+}
+
+int ftl_fill_upload(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    return plot_fill(p, rule, ops, n_ops, color, true);
+    GUARD_END
+}
+int ftl_fill_replay(ftl_plotter *p) {
+    GUARD_BEGIN
+    if (!p) return bad("null plotter");
+    return p->eng.replay();
     GUARD_END
 }
 

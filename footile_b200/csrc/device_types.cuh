@@ -60,7 +60,8 @@ struct Counters {
     uint32_t overflow;   // a speculatively sized scratch buffer was too small: nothing was drawn, the host re-runs
     uint32_t need_v;     // vertices the call needed when it overflowed
     uint32_t need_e;     // bin entries the call needed when it overflowed
-    uint32_t pad[2];
+    uint32_t n_big;      // jobs with more than DIRECT_MAX edge slots (drawn by raster_bins)
+    uint32_t pad;
 };
 
 struct Params {  // per-call constants, passed by value
@@ -78,4 +79,5 @@ struct Params {  // per-call constants, passed by value
     uint32_t b_nbands, b_nwin, b_wc, n_bins;     // bins = n_jobs * b_nbands * b_nwin
     uint32_t b_lookback;                         // 1: one (band, window) tile per ticket, row sums passed through `look`; 0: a ticket walks all windows of a band
     uint32_t job_begin, job_end;                 // jobs this launch of the binned kernel covers
+    uint32_t cull;                               // 1: flatten only the sub-figures that can reach rows [row_begin, row_end) or hold the top vertex
 };

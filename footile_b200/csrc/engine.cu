@@ -133,6 +133,7 @@ struct Engine::Impl {
     int n_sms = 148;
     size_t max_smem = 0;
     DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc, tickets, look;
+    DevBuf cull_mark, cull_head, cull_part, cull_lo, cull_hi, cull_job;  // row-band culling (front_kernels.cuh)
     uint32_t look_epoch = 0;              // launch epoch of the look-back words (0: the buffer must be cleared first)
     std::vector<uint8_t> host_direct;    // per job: provably at most DIRECT_MAX edge slots (line-only, few ops)
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
@@ -199,7 +200,8 @@ Engine::~Engine() {
             cudaStreamSynchronize(impl_->st);
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
-                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.cull_mark, &m.cull_head, &m.cull_part, &m.cull_lo,
+                              &m.cull_hi, &m.cull_job, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
             for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1]}) b->release();
@@ -232,7 +234,7 @@ static BinKernel bin_kernel_wc(int fmt, bool aligned) {
     }
 }
 static BinKernel bin_kernel(int fmt, bool aligned, uint32_t wc) { return wc == 128 ? bin_kernel_wc<128>(fmt, aligned) : bin_kernel_wc<256>(fmt, aligned); }
-static size_t bin_smem_bytes(uint32_t wc) { return (size_t)BIN_ROWS * wc * 2 + 32 * 32; }
+static size_t bin_smem_bytes(uint32_t wc) { return wc == 128 ? BinTile<128>::BYTES : BinTile<256>::BYTES; }
 
 #define ENSURE_INIT()                                                        \
     do {                                                                     \
@@ -309,7 +311,7 @@ static int run_scan(cudaStream_t st, const typename Op::T *in, uint32_t n, typen
     return FTL_OK;
 }
 
-static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, int n_sms, Params *P) {
+static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_launch, int n_sms, bool all_direct, Params *P) {
     const uint32_t warp_slots = (uint32_t)n_sms * 16u;
     P->W = g.width; P->H = g.height; P->row_begin = g.row_begin; P->row_end = g.row_end;
     P->fmt = (uint32_t)g.format; P->bpp = g.bpp(); P->pitch = (uint32_t)g.pitch();
@@ -325,9 +327,10 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     P->cta_warps = 4;
     if (const char *ev = getenv("FTL_CTA_WARPS")) P->cta_warps = (uint32_t)std::min(4, std::max(1, atoi(ev)));  // tuning knob
 
-    // Band height: 8 rows per warp amortise the per-tile set-up; fewer rows per band when one launch
-    // would otherwise leave most of the GPU's warp slots empty (a single raster, a layer of a scene).
-    uint32_t log2R = 3;
+    // Band height: 8 rows per warp amortise the per-tile set-up when every job is provably a polygon of a few
+    // edges; jobs of up to 64 edges do better with 4 (one scatter pass per tile); fewer rows per band when one
+    // launch would otherwise leave most of the GPU's warp slots empty (a single raster, a layer of a scene).
+    uint32_t log2R = all_direct ? 3 : 2;
     while (log2R > 0 && (1u << log2R) >= 2 * g.rows()) log2R--;
     while (log2R > 0 && (uint64_t)jobs_per_launch * div_up(g.rows(), 1u << log2R) < 2ull * warp_slots) log2R--;
     if (const char *ev = getenv("FTL_LOG2R")) log2R = (uint32_t)std::min(5, std::max(0, atoi(ev)));  // tuning knob
@@ -343,8 +346,8 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
         return FTL_ERR_TOO_WIDE;
     }
     // ---- binned tiles (raster_bins): bands of 32 rows x windows of b_wc columns ----
-    P->b_wc = 256;
-    if (const char *ev = getenv("FTL_BIN_WC")) P->b_wc = atoi(ev) == 128 ? 128u : 256u;  // tuning knob
+    P->b_wc = 128;  // 8.8 KB per warp: 21 resident warps per SM (256 columns: 12 warps, 20-30 % slower on every workload measured)
+    if (const char *ev = getenv("FTL_BIN_WC")) P->b_wc = atoi(ev) == 256 ? 256u : 128u;  // tuning knob
     P->b_nbands = div_up(g.rows(), BIN_ROWS);
     P->b_nwin = div_up(g.width, P->b_wc);
     // One ticket per (band, window) with the row sums handed to the right neighbour, unless the launch has
@@ -373,6 +376,41 @@ static int validate_ops(const ftl_path_op *ops, size_t n) {
     return FTL_OK;
 }
 
+// Validate ops[0, n) and copy them into the pinned staging buffer in one pass over the caller's memory; large
+// arrays (config 5 sends 291 MB per fill) are split over host threads.  Returns the first failure in op order.
+static int stage_ops(ftl_path_op *dst, const ftl_path_op *ops, size_t n) {
+    auto one = [](ftl_path_op *d, const ftl_path_op *o, size_t cnt, int *status) {
+        int st = FTL_OK;
+        for (size_t i = 0; i < cnt && st == FTL_OK; i++) {
+            const ftl_path_op op = o[i];
+            if (op.tag > FTL_OP_PENWIDTH) st = FTL_ERR_INVALID;
+            const int nv = op.tag == FTL_OP_CLOSE ? 0 : (op.tag == FTL_OP_QUAD ? 4 : (op.tag == FTL_OP_CUBIC ? 6 : (op.tag == FTL_OP_PENWIDTH ? 1 : 2)));
+            for (int k = 0; k < nv; k++)
+                if (!(op.v[k] - op.v[k] == 0.0f) && st == FTL_OK) st = FTL_ERR_NONFINITE;
+            d[i] = op;
+        }
+        *status = st;
+    };
+    unsigned nt = n < (1u << 16) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<int> status(nt, FTL_OK);
+    if (nt == 1) one(dst, ops, n, &status[0]);
+    else {
+        const size_t per = (n + nt - 1) / nt;
+        std::vector<std::thread> th;
+        for (unsigned t = 0; t < nt; t++) {
+            const size_t b = std::min(n, t * per), e = std::min(n, b + per);
+            th.emplace_back(one, dst + b, ops + b, e - b, &status[t]);
+        }
+        for (std::thread &t : th) t.join();
+    }
+    for (int st : status)
+        if (st != FTL_OK) {
+            set_error(st == FTL_ERR_INVALID ? "unknown path op tag" : "non-finite coordinate in path op");
+            return st;
+        }
+    return FTL_OK;
+}
+
 int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered) {
     ENSURE_INIT();
     Impl &m = *impl_;
@@ -390,8 +428,7 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         set_error("too many ops/jobs for one call");
         return FTL_ERR_INVALID;
     }
-    int rc = validate_ops(ops, n_ops);
-    if (rc) return rc;
+    int rc = FTL_OK;
     Params P{};
     // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
     P.all_direct = 1;
@@ -409,10 +446,12 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
             if (!layered) break;  // only layered launches look at the per-job flags
         }
     }
-    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), m.n_sms, &P);
+    rc = choose_tiling(g, m.max_smem, layered ? 1u : (uint32_t)jobs.size(), m.n_sms, P.all_direct != 0, &P);
     if (rc) return rc;
     P.n_jobs = (uint32_t)jobs.size();
     P.n_ops = (uint32_t)n_ops;
+    P.cull = (g.row_begin > 0 || g.row_end < g.height) && n_ops >= 4096;
+    if (const char *ev = getenv("FTL_CULL")) P.cull = atoi(ev) != 0 && n_ops > 0;  // tuning / test knob
     uint64_t nt = (uint64_t)P.n_jobs * P.n_bands;
     if (nt >= 0x7FFFFFFFull) {
         set_error("too many tiles for one call");
@@ -431,7 +470,20 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     CK(cudaStreamSynchronize(m.st));
     if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
     if ((rc = m.pin_jobs.ensure(jobs_bytes))) return rc;
-    if (ops_bytes) memcpy(m.pin_ops.p, ops, ops_bytes);
+    if ((rc = m.ops.ensure(ops_bytes ? ops_bytes : 1, m.st))) return rc;
+    if ((rc = m.jobs.ensure(jobs_bytes, m.st))) return rc;
+    // validate + stage + copy in pieces: the DMA of one piece runs while the host threads stage the next
+    {
+        const size_t PIECE = 1u << 20;  // ops per piece (28 MB)
+        for (size_t at = 0; at < n_ops; at += PIECE) {
+            const size_t cnt = std::min(PIECE, n_ops - at);
+            if ((rc = stage_ops((ftl_path_op *)m.pin_ops.p + at, ops + at, cnt))) {
+                cudaStreamSynchronize(m.st);
+                return rc;
+            }
+            CK(cudaMemcpyAsync((ftl_path_op *)m.ops.p + at, (const ftl_path_op *)m.pin_ops.p + at, cnt * sizeof(ftl_path_op), cudaMemcpyHostToDevice, m.st));
+        }
+    }
     JobDesc *jd = (JobDesc *)m.pin_jobs.p;
     for (size_t j = 0; j < jobs.size(); j++) {
         const HostJob &h = jobs[j];
@@ -450,9 +502,6 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         d.raster = (unsigned long long)(uintptr_t)h.raster;
         jd[j] = d;
     }
-    if ((rc = m.ops.ensure(ops_bytes ? ops_bytes : 1, m.st))) return rc;
-    if ((rc = m.jobs.ensure(jobs_bytes, m.st))) return rc;
-    if (ops_bytes) CK(cudaMemcpyAsync(m.ops.p, m.pin_ops.p, ops_bytes, cudaMemcpyHostToDevice, m.st));
     CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
     m.P = P;
     m.smem_bytes = (int)((size_t)P.warp_words * 4 * P.cta_warps);
@@ -508,11 +557,32 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     const uint32_t fb = std::min<uint32_t>(div_up(P.n_ops ? P.n_ops : 1, 128), (uint32_t)m.n_sms * 16);
 
     // ---- stages (a) and (b), as a replayable sequence ----
+    // A handle that owns a row band of a raster flattens only the sub-figures that can reach its rows (or hold the
+    // figure's top-left vertex): three light passes over the ops make the rest of the front end proportional to the band.
+    const bool cull_on = P.cull != 0;
+    CullBufs cull{nullptr, nullptr, nullptr, nullptr};
+    if (cull_on) {
+        if ((rc = m.cull_mark.ensure(((size_t)P.n_ops + 1) * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.cull_head.ensure(((size_t)P.n_ops + 1) * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.cull_part.ensure((size_t)div_up(P.n_ops + 1, SCAN_BLOCK) * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.cull_lo.ensure((size_t)P.n_ops * sizeof(int32_t), st))) return rc;
+        if ((rc = m.cull_hi.ensure((size_t)P.n_ops * sizeof(int32_t), st))) return rc;
+        if ((rc = m.cull_job.ensure((size_t)P.n_jobs * 2 * sizeof(int32_t), st))) return rc;
+        cull = CullBufs{(const uint32_t *)m.cull_head.p, (const int32_t *)m.cull_lo.p, (const int32_t *)m.cull_hi.p, (const int32_t *)m.cull_job.p};
+    }
     auto front = [&](bool sync_sizes) -> int {
         CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
         uint32_t nv_hint = cap_v;
         if (P.n_ops > 0) {
-            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
+            if (cull_on) {
+                const uint32_t cb = std::min<uint32_t>(div_up(P.n_ops, 256), (uint32_t)m.n_sms * 8);
+                cull_init_jobs<<<div_up(2 * P.n_jobs, 256), 256, 0, st>>>((int32_t *)m.cull_job.p, P.n_jobs); LAUNCHED();
+                cull_op_extents<<<cb, 256, 0, st>>>(d_ops, d_jobs, P, (uint32_t *)m.cull_mark.p, (int32_t *)m.cull_lo.p, (int32_t *)m.cull_hi.p, (int32_t *)m.cull_job.p); LAUNCHED();
+                int r1 = run_scan<MaxU32>(st, (const uint32_t *)m.cull_mark.p, P.n_ops, (uint32_t *)m.cull_head.p, m.cull_part);
+                if (r1) return r1;
+                cull_sub_extents<<<cb, 256, 0, st>>>(d_ops, d_jobs, P, (const uint32_t *)m.cull_head.p, (int32_t *)m.cull_lo.p, (int32_t *)m.cull_hi.p); LAUNCHED();
+            }
+            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, cull); LAUNCHED();
             const bool small_ops = !sync_sizes && P.n_ops <= SCAN_SMALL_MAX;  // one-block scan + the capacity guard in one launch
             int r2 = FTL_OK;
             if (small_ops) {
@@ -535,9 +605,9 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 nv_hint = nv;
             }
             if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
-            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt); LAUNCHED();
+            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull); LAUNCHED();
         }
-        init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs); LAUNCHED();
+        init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt); LAUNCHED();
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
         vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
@@ -579,7 +649,9 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands};
+                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands, P.cull,
+                                     (uint64_t)(uintptr_t)m.cull_mark.p, (uint64_t)(uintptr_t)m.cull_head.p, (uint64_t)(uintptr_t)m.cull_part.p,
+                                     (uint64_t)(uintptr_t)m.cull_lo.p, (uint64_t)(uintptr_t)m.cull_hi.p, (uint64_t)(uintptr_t)m.cull_job.p};
         if (!m.graph || key != m.graph_key) {
             m.drop_graph();
             cudaGraph_t g = nullptr;
@@ -783,7 +855,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
+    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     SumHead tot;
     CK(cudaStreamSynchronize(st));
@@ -791,7 +863,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     uint32_t nv = tot.sum;
     if (nv == 0) return FTL_OK;
     if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
-    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, nullptr); LAUNCHED();
+    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     std::vector<Vtx> v(nv);
     CK(cudaMemcpy(v.data(), m.vtx.p, (size_t)nv * sizeof(Vtx), cudaMemcpyDeviceToHost));
@@ -842,7 +914,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr); LAUNCHED();
+    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     CK(cudaStreamSynchronize(st));
     std::vector<SumHead> off(n_ops + 1);
@@ -851,7 +923,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     for (size_t i = 0; i < n_ops; i++) out->counts[i] = off[i + 1].sum - off[i].sum;
     if (np == 0) return FTL_OK;
     if ((rc = m.wide.ensure((size_t)np * 3 * sizeof(float), st))) return rc;
-    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, nullptr); LAUNCHED();
+    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     out->xyw.resize((size_t)np * 3);
     CK(cudaMemcpy(out->xyw.data(), m.wide.p, (size_t)np * 3 * sizeof(float), cudaMemcpyDeviceToHost));

@@ -163,6 +163,104 @@ __device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<W
     }
 }
 
+// ---------------------------------------------------------------------------
+// row-band culling (one raster split over several GPUs: SURVEY 8e-ii)
+// ---------------------------------------------------------------------------
+// A handle that owns rows [row_begin, row_end) of a raster needs only the sub-figures whose edges can
+// reach those rows - plus every sub-figure that could hold the figure's top-left vertex, because the
+// winding direction and the top row are properties of the WHOLE figure (fig.rs:402-411,493-497).
+// Flattened points are midpoints of control points, so they stay inside the y range of the op's
+// control points (the f32 midpoint and the f32 -> Fixed conversion are both monotone): the extents
+// below are exact bounds, and dropping a sub-figure outside them changes no pixel and no (dir, top_row).
+struct CullBufs {
+    const uint32_t *head;  // per op: 1 + index of the op that starts its sub-figure (inclusive max-scan of the start marks)
+    const int32_t *sub_lo, *sub_hi;  // per start op: Fixed y range of the sub-figure's control points
+    const int32_t *job_bound;        // per job: [2j] min Fixed y over op end points (real vertices), [2j+1] min over all control points
+};
+struct MaxU32 {
+    typedef uint32_t T;
+    static __device__ __forceinline__ T identity() { return 0u; }
+    static __device__ __forceinline__ T combine(T a, T b) { return a > b ? a : b; }
+    static __device__ __forceinline__ T shfl_up(T v, int d) { return __shfl_up_sync(0xFFFFFFFFu, v, d); }
+};
+__global__ void cull_init_jobs(int32_t *job_bound, uint32_t n_jobs) {
+    const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < 2 * n_jobs) job_bound[j] = INT32_MAX;
+}
+// y range (Fixed) of the control points of drawing op i
+__device__ __forceinline__ void op_y_range(const ftl_path_op &op, const float *e, const PenInfo &pi, int32_t *lo, int32_t *hi, int32_t *y_end) {
+    const int n_pts = op.tag == FTL_OP_QUAD ? 2 : (op.tag == FTL_OP_CUBIC ? 3 : 1);
+    float ymin = 0.0f, ymax = 0.0f, ye = 0.0f;
+    for (int k = 0; k < n_pts; k++) {
+        const float y = pointy::transform(e, {op.v[2 * k], op.v[2 * k + 1]}).y;
+        ymin = k == 0 ? y : fminf(ymin, y);
+        ymax = k == 0 ? y : fmaxf(ymax, y);
+        ye = y;
+    }
+    if (n_pts > 1) {  // a curve starts at the pen
+        const float y = pointy::transform(e, pi.pen).y;
+        ymin = fminf(ymin, y);
+        ymax = fmaxf(ymax, y);
+    }
+    *lo = fx_from_f32(ymin);
+    *hi = fx_from_f32(ymax);
+    *y_end = fx_from_f32(ye);
+}
+__global__ void __launch_bounds__(256) cull_op_extents(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
+                                                       uint32_t *__restrict__ headmark, int32_t *__restrict__ sub_lo, int32_t *__restrict__ sub_hi,
+                                                       int32_t *__restrict__ job_bound) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
+        const ftl_path_op op = ops[i];
+        uint32_t mark = 0;
+        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+            const uint32_t j = job_of_op(jobs, P.n_jobs, i);
+            const JobDesc &jd = jobs[j];
+            const PenInfo pi = find_pen(ops, jd.op_begin, i);
+            if (pi.starts_sub || op.tag == FTL_OP_MOVE) {
+                mark = i + 1;
+                sub_lo[i] = INT32_MAX;
+                sub_hi[i] = INT32_MIN;
+            }
+            float e[6];
+#pragma unroll
+            for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+            int32_t lo, hi, ye;
+            op_y_range(op, e, pi, &lo, &hi, &ye);
+            atomicMin(&job_bound[2 * j], ye);
+            atomicMin(&job_bound[2 * j + 1], lo);
+        }
+        headmark[i] = mark;
+    }
+}
+__global__ void __launch_bounds__(256) cull_sub_extents(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
+                                                        const uint32_t *__restrict__ head, int32_t *__restrict__ sub_lo, int32_t *__restrict__ sub_hi) {
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
+        const ftl_path_op op = ops[i];
+        if (op.tag < FTL_OP_MOVE || op.tag > FTL_OP_CUBIC) continue;
+        const uint32_t j = job_of_op(jobs, P.n_jobs, i);
+        const JobDesc &jd = jobs[j];
+        const PenInfo pi = find_pen(ops, jd.op_begin, i);
+        float e[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+        int32_t lo, hi, ye;
+        op_y_range(op, e, pi, &lo, &hi, &ye);
+        const uint32_t h = head[i + 1] - 1u;  // exclusive scan: entry i + 1 covers ops 0 .. i
+        atomicMin(&sub_lo[h], lo);
+        atomicMax(&sub_hi[h], hi);
+    }
+}
+// Does drawing op i belong to a sub-figure this handle must flatten?
+__device__ __forceinline__ bool cull_keep(const CullBufs &cb, const Params &P, uint32_t i, uint32_t j) {
+    const uint32_t h = cb.head[i + 1] - 1u;
+    const int32_t lo = cb.sub_lo[h], hi = cb.sub_hi[h];
+    const int32_t y_vertex = cb.job_bound[2 * j], y_hull = cb.job_bound[2 * j + 1];
+    if (lo <= y_vertex) return true;  // may hold the top-left vertex of the figure
+    // geometry row r lands on raster row r - shift, shift = min(top_row, 0); top_row is between these two
+    const int32_t s_lo = min(fx_to_i32(y_hull), 0), s_hi = min(fx_to_i32(y_vertex), 0);
+    return fx_to_i32(hi) - s_lo >= (int32_t)P.row_begin && fx_to_i32(lo) - s_hi <= (int32_t)P.row_end - 1;
+}
+
 // One thread per PathOp.  Pass 1 (EMIT=false) counts the vertices the op
 // contributes; after the scan, pass 2 (EMIT=true) repeats the identical
 // subdivision and writes them at the scanned offset, so the output order is
@@ -171,7 +269,7 @@ template <bool WIDE, bool EMIT>
 __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                    const float *__restrict__ opw, SumHead *__restrict__ cnt,
                                                    const SumHead *__restrict__ off, Vtx *__restrict__ vout,
-                                                   float *__restrict__ wout, const Counters *__restrict__ C) {
+                                                   float *__restrict__ wout, const Counters *__restrict__ C, CullBufs cull) {
     if (EMIT && C && C->overflow) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
         const ftl_path_op op = ops[i];
@@ -179,7 +277,7 @@ __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict
         uint32_t j = job_of_op(jobs, P.n_jobs, i);
         const JobDesc &jd = jobs[j];
         bool starts = false;
-        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC && (WIDE || !cull.head || cull_keep(cull, P, i, j))) {
             PenInfo pi = find_pen(ops, jd.op_begin, i);
             starts = pi.starts_sub || op.tag == FTL_OP_MOVE;  // Move closes the current sub-figure (plotter.rs:210)
             float e[6];
@@ -238,8 +336,11 @@ __device__ __forceinline__ uint32_t vtx_next_fwd(const Vtx *V, uint32_t nv, uint
     return k + 1;
 }
 
-__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs) {
+__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs, Counters *C) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    const bool big = j < n_jobs && off && off[jobs[j].op_end].sum - off[jobs[j].op_begin].sum > DIRECT_MAX;
+    const uint32_t n_big = __popc(__ballot_sync(0xFFFFFFFFu, big));
+    if ((threadIdx.x & 31u) == 0 && n_big) atomicAdd(&C->n_big, n_big);
     if (j >= n_jobs) return;
     JobState s;
     s.top_key = ~0ull; s.top_vid = NONE32; s.dir = 0; s.top_row = 0; s.first_row = 0x7FFFFFFF; s.shift = 0;

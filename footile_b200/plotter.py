@@ -125,6 +125,17 @@ class Plotter:
         _lib.check(_lib.lib().ftl_fill(self._handle, int(rule), a.ctypes.data if len(a) else None, len(a), c.ctypes.data))
         return self
 
+    def upload(self, rule, ops, clr=None):
+        """Make a fill resident in HBM without drawing it; replay() then draws it with no host traffic."""
+        a = as_ops(ops)
+        c = _color(clr, self._bpp)
+        _lib.check(_lib.lib().ftl_fill_upload(self._handle, int(rule), a.ctypes.data if len(a) else None, len(a), c.ctypes.data))
+        return self
+
+    def replay(self):
+        _lib.check(_lib.lib().ftl_fill_replay(self._handle))
+        return self
+
     def stroke(self, ops, clr=None):
         a = as_ops(ops)
         c = _color(clr, self._bpp)

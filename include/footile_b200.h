@@ -161,6 +161,13 @@ int ftl_batch_upload(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, cons
                      const uint8_t *rules, const float *transforms, const uint8_t *colors);
 int ftl_batch_run(ftl_batch *b);
 
+/* The same for one Plotter: ftl_fill_upload validates the ops and makes the fill resident (transform, tolerance,
+ * rule and colour as set at this call) without drawing; every ftl_fill_replay() then draws it again with no host
+ * traffic at all - Plotter::fill (plotter.rs:339-350) of a path that already lives in HBM.  Config 5 sends 291 MB
+ * of ops per fill otherwise. */
+int ftl_fill_upload(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
+int ftl_fill_replay(ftl_plotter *p);
+
 /* ---- Instrumentation ---------------------------------------------------- */
 /* Number of kernel launches issued by this library since load (all handles). */
 uint64_t ftl_launch_count(void);

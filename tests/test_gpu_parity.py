@@ -539,9 +539,11 @@ def test_config5_full_size_stripes_vs_oracle(rule):
         exp = o.raster()[r0: r0 + rows]
         got = full[r0: r0 + rows]
         assert np.array_equal(exp, got), "rule %s rows %d..%d: %d bytes differ" % (rule, r0, r0 + rows, int((exp != got).sum()))
-    # size-independent properties of the whole raster: a dense scene covers most pixels, and both rules agree
-    # wherever the NonZero matte is empty
-    assert np.count_nonzero(full[::64]) > 0.5 * full[::64].size
+    # size-independent property of the whole raster: hundreds of overlapping self-intersecting polygons make the
+    # winding number a symmetric random walk.  NonZero: negative sums clamp to 0 (imgbuf.rs:54-66), so about half of
+    # the pixels are covered; EvenOdd: ~6.5 edge crossings per pixel leave almost no pixel with zero coverage.
+    frac = np.count_nonzero(full[::64]) / full[::64].size
+    assert (0.4 < frac < 0.6) if rule == FillRule.NonZero else (0.9 < frac < 1.0), frac
 
 
 def test_config5_full_size_row_bands_equal_unsplit():
@@ -552,7 +554,8 @@ def test_config5_full_size_row_bands_equal_unsplit():
         r0, r1 = k * size // 4, (k + 1) * size // 4
         gb = Plotter.with_clear(size, size, Format.Matte8, rows=(r0, r1))
         gb.fill(FillRule.EvenOdd, ops, (255,))
-        assert gb.debug_last_fill() == info
+        binfo = gb.debug_last_fill()  # a band flattens only the sub-figures it needs: n_points differs, (dir, top_row) must not
+        assert (binfo["dir"], binfo["top_row"]) == (info["dir"], info["top_row"])
         assert np.array_equal(gb.raster().pixels, full[r0:r1]), k
         del gb
     _C5.clear()
