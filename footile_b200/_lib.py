@@ -19,7 +19,7 @@ SYMBOLS = [
     "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
     "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream", "ftl_fill_upload", "ftl_fill_replay",
-    "ftl_launch_count", "ftl_set_profiling", "ftl_tile_kernel_time",
+    "ftl_launch_count", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_time_fills",
     "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
 ]
 
@@ -82,6 +82,7 @@ def lib():
         "ftl_launch_count": (C.c_uint64, []),
         "ftl_set_profiling": (i32, [i32]),
         "ftl_tile_kernel_time": (i32, [i32, vp, vp]),
+        "ftl_time_fills": (i32, [vp, i32, vp, sz, vp, u32, i32, vp]),
         "ftl_debug_flatten": (i32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
         "ftl_debug_last_fill": (i32, [vp, vp]),
         "ftl_debug_edges": (i32, [vp, vp, sz, vp]),

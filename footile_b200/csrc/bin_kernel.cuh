@@ -164,15 +164,17 @@ __device__ __forceinline__ void bin_item_rows(int32_t xb, int32_t inv_slope, int
 }
 
 // S: one (edge, row) item of a staged edge, packed 32-bit adds (see the file header for why they are exact here).
-template <int WC>
+// TOT: also add the item's total to the row's word at totbase (tiles that hand row sums to a neighbour window).
+template <bool TOT>
 __device__ __forceinline__ void bin_item_packed(int32_t xb, int32_t inv_slope, int32_t step, int32_t r0, int32_t r1, int32_t dxs, int32_t dxe, uint32_t misc,
-                                                int32_t ed, int32_t rel_row, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t cells, uint32_t totbase) {
+                                                int32_t ed, int32_t rel_row, int32_t W, int32_t win_lo, int32_t win_hi, uint32_t cells, uint32_t row_bytes,
+                                                uint32_t totbase) {
     const fx_t x_bot = (fx_t)((uint32_t)xb + (uint32_t)rel_row * (uint32_t)inv_slope);
     int32_t c, xc, prev, cov;
     bool resumed;
     if (!bin_span<false, false>(x_bot, inv_slope, step, rel_row == r0, rel_row == r1, dxs, dxe, misc, true, W, win_lo, win_hi, c, xc, prev, cov, resumed)) return;
     const int32_t prev0 = prev;
-    const uint32_t rbase = cells + (uint32_t)rel_row * BinTile<WC>::ROW_BYTES;
+    const uint32_t rbase = cells + (uint32_t)rel_row * row_bytes;
     int32_t rel = c - win_lo;
     const int32_t end_rel = win_hi - win_lo;
     int32_t xr = xc + 128;
@@ -185,7 +187,7 @@ __device__ __forceinline__ void bin_item_packed(int32_t xb, int32_t inv_slope, i
         xr = min(xr + step, FX_ONE + 128);
         if (xk >= cov || rel >= end_rel) break;
     }
-    sred_add(totbase + 4u * (uint32_t)rel_row, ed * (prev - prev0));
+    if (TOT) sred_add(totbase + 4u * (uint32_t)rel_row, ed * (prev - prev0));
 }
 
 // alpha bytes of four consecutive pixels from two words of packed wrapped-i16 sums (lo = pixel 2j, hi = pixel 2j+1)
@@ -271,21 +273,25 @@ __device__ __forceinline__ void bin_const_tile(int32_t carry, uint32_t valid_mas
     }
 }
 
-// Resolve the warp's tile: rows of WC cells, WC/16 lanes per row, 32/(WC/16) rows per step.
+// Resolve a tile: rows of WC cells, WC/16 lanes per row, 32/(WC/16) rows per step.
 //   touched : rows that received deltas;   carry : this LANE's row (lane = row): running sum reaching the window
-template <int FMT, bool EVEN_ODD, bool ALIGNED, int WC>
-__device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t touched, int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch,
-                                            uint32_t w_rel, uint32_t color) {
+//   row_bytes : distance between the rows of the tile;   steps s_begin, s_begin + s_stride, ... (rows s .. s + RPS - 1 each)
+//   TOTALS : return the sum of the row's cells (lane = row) for the rows of the steps taken, 0 elsewhere
+template <int FMT, bool EVEN_ODD, bool ALIGNED, int WC, bool TOTALS = false>
+__device__ __forceinline__ int32_t bin_resolve(uint32_t cells, uint32_t touched, int32_t carry, uint32_t valid_mask, uint8_t *dst_win, uint32_t pitch,
+                                               uint32_t w_rel, uint32_t color, uint32_t row_bytes = BinTile<WC>::ROW_BYTES, uint32_t s_begin = 0,
+                                               uint32_t s_stride = 32 / (WC / 16)) {
     constexpr uint32_t LPR = WC / 16, RPS = 32 / LPR;
     const uint32_t lane = threadIdx.x & 31, sub = lane / LPR, l = lane % LPR;
     const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
-    if (FMT != FTL_MATTE8 && ALIGNED && touched == 0 && w_rel >= (uint32_t)WC) {
+    int32_t totals = 0;
+    if (!TOTALS && FMT != FTL_MATTE8 && ALIGNED && touched == 0 && w_rel >= (uint32_t)WC && s_begin == 0 && s_stride == RPS) {
         constexpr uint32_t U = FMT == FTL_GRAYA8P ? 2u : 4u;  // 16-byte words per 16 pixels
         bin_const_tile<FMT, EVEN_ODD>(carry, valid_mask, dst_win, pitch, LPR * U, color, clr_a);
-        return;
+        return 0;
     }
 #pragma unroll 1
-    for (uint32_t s = 0; s < BIN_ROWS; s += RPS) {
+    for (uint32_t s = s_begin; s < BIN_ROWS; s += s_stride) {
         const uint32_t row = s + sub;
         const int32_t cr = __shfl_sync(0xFFFFFFFFu, carry, row);
         const uint32_t step_rows = ((1u << RPS) - 1u) << s;
@@ -301,7 +307,7 @@ __device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t touched, in
         // branch here leaves the half-warps diverged for the rest of the step and every instruction issues twice
         int4 v0, v1;
         {
-            const uint32_t a = cells + row * BinTile<WC>::ROW_BYTES + 32u * l;
+            const uint32_t a = cells + row * row_bytes + 32u * l;
             v0 = slds4(a);
             v1 = slds4(a + 16u);
             ssts4_bias(a);
@@ -319,12 +325,20 @@ __device__ __forceinline__ void bin_resolve(uint32_t cells, uint32_t touched, in
 #pragma unroll
         for (int d = 1; d < (int)LPR; d <<= 1) scan_step<(int)LPR>(inc, d);
         const int32_t b = cr + inc - tot;
+        if (TOTALS) {
+#pragma unroll
+            for (uint32_t q = 0; q < RPS; q++) {
+                const int32_t tq = __shfl_sync(0xFFFFFFFFu, inc, q * LPR + LPR - 1);
+                if (lane == s + q) totals = tq;
+            }
+        }
         const uint32_t a0 = packed_alpha<EVEN_ODD>(p0, p1, b, b + o1);
         const uint32_t a1 = packed_alpha<EVEN_ODD>(p2, p3, b + o2, b + o3);
         const uint32_t a2 = packed_alpha<EVEN_ODD>(p4, p5, b + o4, b + o5);
         const uint32_t a3 = packed_alpha<EVEN_ODD>(p6, p7, b + o6, b + o7);
         if (ok) emit16<FMT, ALIGNED>(drow, 16 * l, w_rel, a0, a1, a2, a3, color, clr_a);
     }
+    return totals;
 }
 
 template <int FMT, bool ALIGNED, int WC>
@@ -428,7 +442,7 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
                         const int32_t before = k ? (int32_t)slds(prefix + 4u * (k - 1)) : 0;
                         const int4 a = slds4(stage + k * 32u), b = slds4(stage + k * 32u + 16u);
                         const int32_t er0 = (a.w & 0xFF) - 1, er1 = a.w >> 8;
-                        bin_item_packed<WC>(a.x, a.y, a.z, er0, er1, b.y, b.z, (uint32_t)b.w, b.x, max(er0, v_lo) + (q - before), W, win_lo, win_hi, cells, totbase);
+                        bin_item_packed<true>(a.x, a.y, a.z, er0, er1, b.y, b.z, (uint32_t)b.w, b.x, max(er0, v_lo) + (q - before), W, win_lo, win_hi, cells, T::ROW_BYTES, totbase);
                     }
                 } else {
                     row_touched = true;

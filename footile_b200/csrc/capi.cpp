@@ -2,6 +2,8 @@
 // Plain pointers and sizes only; never throws across the boundary.
 #include <string.h>
 
+#include <chrono>
+
 #include <new>
 #include <vector>
 
@@ -136,7 +138,7 @@ static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_
     j.rule = rule;
     if (color) memcpy(j.color, color, p->geo.bpp());
     j.raster = p->raster;
-    int rc = upload_only ? p->eng.upload(p->geo, jobs, ops, n_ops) : p->eng.fill(p->geo, jobs, ops, n_ops);
+    int rc = upload_only ? p->eng.upload(p->geo, jobs, ops, n_ops) : p->eng.fill(p->geo, jobs, ops, n_ops, true);
     if (rc) return rc;  // a rejected call leaves the plotter state alone
     // PenWidth persists on the plotter across calls (plotter.rs:151-153)
     for (size_t i = 0; i < n_ops; i++)
@@ -417,6 +419,26 @@ int ftl_set_profiling(int enabled) {
 int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches) {
     Engine::tile_kernel_time(reset != 0, ms, launches);
     return FTL_OK;
+}
+
+// Per-call latency of Plotter::fill through this ABI, timed inside the library so that no binding overhead is counted:
+// `iters` calls of ftl_fill (+ ftl_sync after each one when sync_each != 0, one ftl_sync at the end otherwise).
+int ftl_time_fills(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color, uint32_t iters, int sync_each,
+                   double *us_per_call) {
+    GUARD_BEGIN
+    if (!p || !us_per_call) return bad("null argument");
+    int rc = p->eng.sync();
+    if (rc) return rc;
+    const auto t0 = std::chrono::steady_clock::now();
+    for (uint32_t i = 0; i < iters; i++) {
+        if ((rc = plot_fill(p, rule, ops, n_ops, color))) return rc;
+        if (sync_each && (rc = p->eng.sync())) return rc;
+    }
+    if ((rc = p->eng.sync())) return rc;
+    const auto t1 = std::chrono::steady_clock::now();
+    *us_per_call = iters ? std::chrono::duration<double, std::micro>(t1 - t0).count() / iters : 0.0;
+    return FTL_OK;
+    GUARD_END
 }
 
 // ---- parity probes ----

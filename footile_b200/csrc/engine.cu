@@ -19,6 +19,7 @@
 //   front_kernels.cuh  stages (a)+(b)
 //   tile_kernel.cuh    stages (c)+(d) for jobs of at most 64 edges: scatter rows, analytic rows, resolve, composite
 //   bin_kernel.cuh     stages (c)+(d) for larger jobs: (32 rows x window) tiles, lanes = rows, no atomics
+//   small_kernel.cuh   one small fill (a few ops, a small raster) in one launch: all four stages in a CTA
 //   pack_kernels.cuh   packed read-back, raster checksums
 //   engine.cu          host side: scratch arena, graph replay, launches, read-back
 //
@@ -74,6 +75,7 @@ static std::atomic<bool> g_profiling{false};
 #include "front_kernels.cuh"
 #include "tile_kernel.cuh"
 #include "bin_kernel.cuh"
+#include "small_kernel.cuh"
 #include "pack_kernels.cuh"
 
 // ---------------------------------------------------------------------------
@@ -136,6 +138,19 @@ struct Engine::Impl {
     DevBuf cull_mark, cull_head, cull_part, cull_lo, cull_hi, cull_job;  // row-band culling (front_kernels.cuh)
     uint32_t look_epoch = 0;              // launch epoch of the look-back words (0: the buffer must be cleared first)
     std::vector<uint8_t> host_direct;    // per job: provably at most DIRECT_MAX edge slots (line-only, few ops)
+    // small fills (small_kernel.cuh): one launch each, issued without waiting; a fill that did not fit raises its flag
+    // in mapped host memory and is repeated through the general pipeline at the next blocking call
+    struct SmallSaved {
+        SmallArgs args;
+        Geometry geo;
+    };
+    std::vector<SmallSaved> small_saved;
+    uint32_t small_n = 0;                 // small fills issued since the flags were last checked
+    bool last_small = false;              // the last fill went through small_fill (probes read its records)
+    bool small_tail = false;              // the last operation issued on the stream is a small fill: its completion word tells when the stream is idle
+    uint32_t small_seq = 0;               // sequence number of the last small fill
+    PinBuf small_flags;                   // SMALL_RING overflow flags + the completion word
+    DevBuf small_poison;                  // [0] poison, [1] CTA completion counter
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
     PinBuf pin_ring, pin_pack[2], pin_lit[2];
     DevBuf pack_fixed, pack_cnt, pack_lit;
@@ -157,6 +172,7 @@ struct Engine::Impl {
     }
 };
 constexpr uint32_t RING = 64;
+constexpr uint32_t SMALL_RING = 64;
 
 int Engine::device_count(int *count) {
     int n = 0;
@@ -201,10 +217,10 @@ Engine::~Engine() {
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
                               &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.cull_mark, &m.cull_head, &m.cull_part, &m.cull_lo,
-                              &m.cull_hi, &m.cull_job, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.cull_hi, &m.cull_job, &m.small_poison, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
-            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1]}) b->release();
+            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1], &m.small_flags}) b->release();
             cudaStreamDestroy(impl_->st);
         }
         delete impl_;
@@ -214,6 +230,7 @@ Engine::~Engine() {
 static int engine_init(Engine::Impl *m, int device, void **stream_out);
 static int run_pipeline(Engine::Impl &m, bool exact);
 static int resolve_pending(Engine::Impl &m);
+static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered);
 
 typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const Counters *);
 static TileKernel tile_kernel(int fmt, bool aligned) {
@@ -233,6 +250,15 @@ static BinKernel bin_kernel_wc(int fmt, bool aligned) {
     default: return aligned ? raster_bins<FTL_RGBA8P, true, WC> : raster_bins<FTL_RGBA8P, false, WC>;
     }
 }
+typedef void (*SmallKernel)(const SmallArgs, JobState *, Counters *, EdgeRec *, uint32_t *, uint32_t *, uint32_t *, uint32_t *);
+static SmallKernel small_kernel(int fmt, bool aligned) {
+    switch (fmt) {
+    case FTL_MATTE8: return aligned ? small_fill<FTL_MATTE8, true> : small_fill<FTL_MATTE8, false>;
+    case FTL_GRAYA8P: return aligned ? small_fill<FTL_GRAYA8P, true> : small_fill<FTL_GRAYA8P, false>;
+    default: return aligned ? small_fill<FTL_RGBA8P, true> : small_fill<FTL_RGBA8P, false>;
+    }
+}
+static size_t small_smem_bytes() { return ((sizeof(SmallShared) + 15u) & ~(size_t)15u) + BIN_ROWS * (SMALL_MAX_DIM * 2 + BIN_ROW_PAD); }
 static BinKernel bin_kernel(int fmt, bool aligned, uint32_t wc) { return wc == 128 ? bin_kernel_wc<128>(fmt, aligned) : bin_kernel_wc<256>(fmt, aligned); }
 static size_t bin_smem_bytes(uint32_t wc) { return wc == 128 ? BinTile<128>::BYTES : BinTile<256>::BYTES; }
 
@@ -279,6 +305,7 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
                 for (int a = 0; a < 2; a++) {
                     CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
                     CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+                    CK(cudaFuncSetAttribute(small_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes()));
                     for (uint32_t wc : {128u, 256u}) {
                         CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes(wc)));
                         CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -418,7 +445,13 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
         int rc0 = resolve_pending(m);  // earlier replays refer to the job set that is about to be replaced
         if (rc0) return rc0;
     }
+    return upload_jobs(m, g, jobs, ops, n_ops, layered);
+}
+
+static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered) {
     m.have_jobs = false;  // stays false if anything below fails
+    m.last_small = false;
+    m.small_tail = false;
     m.layered = layered;
     if (jobs.empty() || g.rows() == 0 || g.width == 0) {
         m.have_jobs = false;
@@ -509,7 +542,66 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     return FTL_OK;
 }
 
-int Engine::fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops) {
+// One small fill in one launch (small_kernel.cuh).  Returns -1 when the call is not eligible.
+static int fill_small(Engine::Impl &m, const Geometry &g, const HostJob &h, const ftl_path_op *ops, size_t n_ops) {
+    const char *no_small = getenv("FTL_NO_SMALL");  // read per call: the parity tests draw the same input through both paths
+    if ((no_small && atoi(no_small) != 0) || n_ops == 0 || n_ops > SMALL_MAX_OPS || g.width == 0 || g.width > SMALL_MAX_DIM || g.rows() == 0 || g.rows() > SMALL_MAX_DIM) return -1;
+    if (small_smem_bytes() > m.max_smem) return -1;
+    int rc;
+    if (m.pending && (rc = resolve_pending(m))) return rc;  // an earlier general replay may still have to be repeated: keep the order
+    if (m.small_n >= SMALL_RING && (rc = resolve_pending(m))) return rc;
+    if ((rc = validate_ops(ops, n_ops))) return rc;
+    for (int k = 0; k < 6; k++)
+        if (!(h.e[k] - h.e[k] == 0.0f)) {
+            set_error("non-finite transform");
+            return FTL_ERR_NONFINITE;
+        }
+    cudaStream_t st = m.st;
+    if (!m.small_flags.p) {
+        if ((rc = m.small_flags.ensure((SMALL_RING + 1) * sizeof(uint32_t)))) return rc;
+        memset(m.small_flags.p, 0, (SMALL_RING + 1) * sizeof(uint32_t));
+        if ((rc = m.small_poison.ensure(2 * sizeof(uint32_t), st))) return rc;
+        CK(cudaMemsetAsync(m.small_poison.p, 0, 2 * sizeof(uint32_t), st));
+        m.small_saved.resize(SMALL_RING);
+    }
+    if ((rc = m.counters.ensure(sizeof(Counters), st))) return rc;
+    if ((rc = m.jstate.ensure(sizeof(JobState), st))) return rc;
+    if ((rc = m.edges.ensure((size_t)SMALL_MAX_V * sizeof(EdgeRec), st))) return rc;
+    Engine::Impl::SmallSaved &sv = m.small_saved[m.small_n];
+    SmallArgs &A = sv.args;
+    sv.geo = g;
+    A.job = JobDesc{};
+    A.job.op_begin = 0; A.job.op_end = (uint32_t)n_ops;
+    memcpy(A.job.e, h.e, sizeof(A.job.e));
+    A.job.tol_sq = h.tol_sq;
+    A.job.rule = (uint32_t)h.rule;
+    A.job.color = (uint32_t)h.color[0] | ((uint32_t)h.color[1] << 8) | ((uint32_t)h.color[2] << 16) | ((uint32_t)h.color[3] << 24);
+    A.job.raster = (unsigned long long)(uintptr_t)h.raster;
+    A.n_ops = (uint32_t)n_ops; A.W = g.width; A.H = g.height; A.row_begin = g.row_begin; A.row_end = g.row_end;
+    A.pitch = (uint32_t)g.pitch(); A.bpp = g.bpp(); A.seq = ++m.small_seq;
+    memcpy(A.ops, ops, n_ops * sizeof(ftl_path_op));
+    uint32_t *flags = (uint32_t *)m.small_flags.p;
+    flags[m.small_n] = 0;
+    const bool aligned = g.width % (16u / g.bpp()) == 0;
+    const uint32_t n_bands = div_up(g.rows(), BIN_ROWS);
+    const size_t tile_bytes = (size_t)BIN_ROWS * (div_up(g.width, g.width <= 256u ? 256u : 512u) * (g.width <= 256u ? 256u : 512u) * 2 + BIN_ROW_PAD);
+    small_kernel(g.format, aligned)<<<n_bands, SMALL_WARPS * 32, ((sizeof(SmallShared) + 15u) & ~(size_t)15u) + tile_bytes, st>>>(
+        A, (JobState *)m.jstate.p, (Counters *)m.counters.p, (EdgeRec *)m.edges.p, (uint32_t *)m.small_poison.p, flags + m.small_n,
+        (uint32_t *)m.small_poison.p + 1, flags + SMALL_RING); LAUNCHED();
+    CK(cudaGetLastError());
+    m.small_n++;
+    m.small_tail = true;
+    m.have_jobs = false;
+    m.last_small = true;
+    return FTL_OK;
+}
+
+int Engine::fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool allow_small) {
+    if (allow_small && jobs.size() == 1) {
+        ENSURE_INIT();
+        int rs = fill_small(*impl_, g, jobs[0], ops, n_ops);
+        if (rs != -1) return rs;
+    }
     int rc = upload(g, jobs, ops, n_ops);
     if (rc) return rc;
     return replay();
@@ -528,6 +620,7 @@ int Engine::fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, con
 //                  from device memory and nothing waits for the host; the stages before the tile
 //                  kernel are replayed from a CUDA graph.
 static int run_pipeline(Engine::Impl &m, bool exact) {
+    m.small_tail = false;  // other work follows on the stream: its end is no longer the last small fill's completion word
     const Params P = m.P;
     cudaStream_t st = m.st;
     int rc;
@@ -754,9 +847,32 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
 
 // Check the counters of the replays issued since the last check; repeat, with exact sizes, those
 // that found a scratch buffer too small (they drew nothing).
-static int resolve_pending(Engine::Impl &m) {
-    if (m.pending == 0) return FTL_OK;
+// The last operation on the stream is a small fill: wait for its completion word in mapped host memory (a few hundred
+// nanoseconds after the kernel ends; cudaStreamSynchronize needs several microseconds).  False: the caller must synchronise.
+static bool small_tail_done(Engine::Impl &m) {
+    if (!m.small_tail || !m.small_flags.p) return false;
+    const volatile uint32_t *done = (const volatile uint32_t *)m.small_flags.p + SMALL_RING;
+    for (int spin = 0; spin < 200000; spin++) {
+        if (*done == m.small_seq) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return true;
+        }
+        _mm_pause();
+    }
+    return false;
+}
+static int stream_idle(Engine::Impl &m) {
+    if (small_tail_done(m)) return FTL_OK;
     CK(cudaStreamSynchronize(m.st));
+    return FTL_OK;
+}
+
+static int resolve_pending(Engine::Impl &m) {
+    if (m.pending == 0 && m.small_n == 0) return FTL_OK;
+    {
+        int rc0 = stream_idle(m);
+        if (rc0) return rc0;
+    }
     uint32_t redo = 0;
     const Counters *ring = (const Counters *)m.pin_ring.p;
     for (uint32_t i = 0; i < m.pending; i++) redo += ring[i].overflow ? 1u : 0u;
@@ -764,6 +880,31 @@ static int resolve_pending(Engine::Impl &m) {
     for (uint32_t i = 0; i < redo; i++) {
         int rc = run_pipeline(m, true);
         if (rc) return rc;
+    }
+    // small fills that did not fit their kernel (they, and every small fill after them, drew nothing): repeat them in
+    // order through the general pipeline, then lift the poison
+    const uint32_t n_small = m.small_n;
+    m.small_n = 0;
+    bool any = false;
+    for (uint32_t i = 0; i < n_small; i++) {
+        if (!((const uint32_t *)m.small_flags.p)[i]) continue;
+        any = true;
+        const Engine::Impl::SmallSaved sv = m.small_saved[i];
+        std::vector<HostJob> jobs(1);
+        HostJob &h = jobs[0];
+        h.op_begin = 0; h.op_end = sv.args.n_ops;
+        memcpy(h.e, sv.args.job.e, sizeof(h.e));
+        h.tol_sq = sv.args.job.tol_sq;
+        h.rule = (int)sv.args.job.rule;
+        for (int k = 0; k < 4; k++) h.color[k] = (uint8_t)(sv.args.job.color >> (8 * k));
+        h.raster = (void *)(uintptr_t)sv.args.job.raster;
+        int rc = upload_jobs(m, sv.geo, jobs, sv.args.ops, sv.args.n_ops, false);
+        if (!rc) rc = run_pipeline(m, true);
+        if (rc) return rc;
+    }
+    if (any) {
+        CK(cudaMemsetAsync(m.small_poison.p, 0, sizeof(uint32_t), m.st));
+        CK(cudaStreamSynchronize(m.st));
     }
     return FTL_OK;
 }
@@ -785,7 +926,7 @@ int Engine::last_fill_info(FillInfo *info) {
     ENSURE_INIT();
     Impl &m = *impl_;
     *info = FillInfo();
-    if (!m.have_jobs) return FTL_OK;
+    if (!m.have_jobs && !m.last_small) return FTL_OK;
     {
         int rc = resolve_pending(m);
         if (rc) return rc;
@@ -805,7 +946,7 @@ int Engine::debug_edges(std::vector<int32_t> *out) {
     ENSURE_INIT();
     Impl &m = *impl_;
     out->clear();
-    if (!m.have_jobs) return FTL_OK;
+    if (!m.have_jobs && !m.last_small) return FTL_OK;
     {
         int rc = resolve_pending(m);
         if (rc) return rc;
@@ -839,6 +980,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     if (rc) return rc;
     if ((rc = validate_ops(ops, n_ops))) return rc;
     cudaStream_t st = m.st;
+    m.small_tail = false;
     Params P{};
     P.n_jobs = 1;
     P.n_ops = (uint32_t)n_ops;
@@ -896,6 +1038,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     if (rc) return rc;
     if ((rc = validate_ops(ops, n_ops))) return rc;
     cudaStream_t st = m.st;
+    m.small_tail = false;
     Params P{};
     P.n_jobs = 1;
     P.n_ops = (uint32_t)n_ops;
@@ -942,6 +1085,7 @@ int Engine::accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n
     }
     int rc;
     if ((rc = m.misc.ensure(n * rows * 3, m.st))) return rc;
+    m.small_tail = false;
     int16_t *ds = (int16_t *)m.misc.p;
     uint8_t *dd = (uint8_t *)m.misc.p + n * rows * 2;
     CK(cudaMemcpyAsync(ds, src, n * rows * 2, cudaMemcpyHostToDevice, m.st));
@@ -959,6 +1103,7 @@ int Engine::checksums(const void *rasters, size_t raster_bytes, uint32_t count, 
     int rc;
     if ((rc = resolve_pending(m))) return rc;
     if ((rc = m.misc.ensure((size_t)count * 8, m.st))) return rc;
+    m.small_tail = false;
     fnv_rasters<<<count, 256, 0, m.st>>>((const uint8_t *)rasters, raster_bytes, (uint64_t *)m.misc.p); LAUNCHED();
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(out, m.misc.p, (size_t)count * 8, cudaMemcpyDeviceToHost, m.st));
@@ -970,8 +1115,7 @@ int Engine::sync() {
     ENSURE_INIT();
     int rc = resolve_pending(*impl_);
     if (rc) return rc;
-    CK(cudaStreamSynchronize(impl_->st));
-    return FTL_OK;
+    return stream_idle(*impl_);
 }
 int Engine::alloc_raster(size_t bytes, void **dptr) {
     ENSURE_INIT();
@@ -994,6 +1138,7 @@ int Engine::memset_async(void *dptr, int value, size_t bytes) {
         int rc = resolve_pending(*impl_);
         if (rc) return rc;
     }
+    impl_->small_tail = false;
     CK(cudaMemsetAsync(dptr, value, bytes, impl_->st));
     return FTL_OK;
 }
@@ -1003,6 +1148,7 @@ int Engine::copy_in(void *dptr, const void *src, size_t bytes) {
         int rc = resolve_pending(*impl_);
         if (rc) return rc;
     }
+    impl_->small_tail = false;
     CK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, impl_->st));
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;
@@ -1077,6 +1223,7 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
         if (rc) return rc;
     }
     cudaStream_t st = m.st;
+    m.small_tail = false;
     static const bool raw_only = getenv("FTL_RAW_READ") && atoi(getenv("FTL_RAW_READ")) != 0;
     const size_t PACK_MIN = 4u << 20;
     if (raw_only || bytes < PACK_MIN || (bytes & 1023u) != 0 || ((uintptr_t)dptr & 15u) != 0) {

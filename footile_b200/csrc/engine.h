@@ -57,7 +57,8 @@ public:
 
     // Fill jobs.  If `ops` is null the ops uploaded by the previous call (or by
     // upload()) are reused from HBM.
-    int fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    // allow_small: a single job of a few ops on a small raster may take the one-launch path (small_kernel.cuh).
+    int fill(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool allow_small = false);
     // The jobs are layers drawn in order onto ONE raster (all jobs carry the same raster pointer):
     // flatten / edge prep / binning run once for all layers, the tile kernel once per layer.
     int fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);

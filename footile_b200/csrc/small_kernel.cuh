@@ -26,16 +26,19 @@ constexpr uint32_t SMALL_MAX_OPS = 112;   // 112 * 28 B of ops + the job record 
 constexpr uint32_t SMALL_MAX_V = 1024;    // vertices (= edge slots) per fill
 constexpr uint32_t SMALL_MAX_LEAVES = 64; // points per curve op
 constexpr uint32_t SMALL_MAX_DIM = 1024;  // raster width / owned rows
-constexpr int SMALL_WC = 256;
 constexpr uint32_t SMALL_WARPS = 8;
 
 struct SmallArgs {
     JobDesc job;  // op_begin = 0, op_end = n_ops
-    uint32_t n_ops, W, H, row_begin, row_end, pitch, bpp, pad;
+    uint32_t n_ops, W, H, row_begin, row_end, pitch, bpp, seq;  // seq: written to the host's completion word by the last CTA
     ftl_path_op ops[SMALL_MAX_OPS];
 };
 static_assert(sizeof(SmallArgs) <= 3400, "SmallArgs must fit the kernel argument space with the pointers beside it");
 
+struct SmallNode {  // one node of a subdivision level: four control points and its tag
+    float v[8];
+    uint32_t key;
+};
 struct SmallShared {
     Vtx V[SMALL_MAX_V];
     EdgeRec E[SMALL_MAX_V];
@@ -49,16 +52,19 @@ struct SmallShared {
     float leaf_x[SMALL_WARPS][SMALL_MAX_LEAVES], leaf_y[SMALL_WARPS][SMALL_MAX_LEAVES];
     uint32_t leaf_key[SMALL_WARPS][SMALL_MAX_LEAVES];
     int32_t sorted[SMALL_WARPS][2 * SMALL_MAX_LEAVES];
+    SmallNode nodes[SMALL_WARPS][32];
+    int4 stage[2 * BIN_PACKED_MAX];         // the band's edges, prepared (two int4 each)
+    uint32_t item_end[BIN_PACKED_MAX];      // inclusive prefix of the rows each staged edge has inside the band
     JobState js;
     unsigned long long top_key;
-    uint32_t top_vid, pool_used, nv, n_popped, overflow;
+    uint32_t top_vid, pool_used, nv, n_popped, overflow, n_edges, n_staged, touched;
 };
 
 // One curve op, one warp: level-parallel subdivision.  Returns the number of leaves (points) written in
 // depth-first order to out_xy (Fixed pairs), or 0xFFFFFFFF when a level or the leaf list overflows.
 template <bool CUBIC>
 __device__ __forceinline__ uint32_t small_flatten_curve(pointy::Pt a, pointy::Pt b, pointy::Pt c, pointy::Pt d, float tol_sq, float *lx, float *ly,
-                                                        uint32_t *lkey, int32_t *out_xy) {
+                                                        uint32_t *lkey, SmallNode *nodes, int32_t *out_xy) {
     const uint32_t lane = threadIdx.x & 31, lt = (1u << lane) - 1u;
     bool valid = lane == 0;
     uint32_t key = 0, n_leaf = 0;
@@ -88,18 +94,23 @@ __device__ __forceinline__ uint32_t small_flatten_curve(pointy::Pt a, pointy::Pt
         }
         n_leaf += __popc(leafs);
         if (splits == 0) break;
-        // lane L of the next level is child (L & 1) of the (L >> 1)-th splitting lane
-        const bool child = lane < 2u * __popc(splits);
-        const uint32_t parent = child ? __fns(splits, 0, (lane >> 1) + 1) : 0u;
-        const bool right = lane & 1u;
-#define FTL_CHILD(f) (right ? __shfl_sync(0xFFFFFFFFu, r##f, parent) : __shfl_sync(0xFFFFFFFFu, l##f, parent))
-        const float nax = FTL_CHILD(a.x), nay = FTL_CHILD(a.y), nbx = FTL_CHILD(b.x), nby = FTL_CHILD(b.y);
-        const float ncx = FTL_CHILD(c.x), ncy = FTL_CHILD(c.y), ndx = FTL_CHILD(d.x), ndy = FTL_CHILD(d.y);
-#undef FTL_CHILD
-        const uint32_t pkey = __shfl_sync(0xFFFFFFFFu, key, parent);
-        a = {nax, nay}; b = {nbx, nby}; c = {ncx, ncy}; d = {ndx, ndy};
-        key = pkey | ((right ? 1u : 0u) << (15 - depth));
-        valid = child;
+        // the r-th splitting lane hands its two children to lanes 2r and 2r + 1 of the next level through shared memory
+        if (valid && !flat) {
+            const uint32_t r = __popc(splits & lt);
+            SmallNode &nl = nodes[2 * r], &nr = nodes[2 * r + 1];
+            nl.v[0] = la.x; nl.v[1] = la.y; nl.v[2] = lb.x; nl.v[3] = lb.y; nl.v[4] = lc.x; nl.v[5] = lc.y; nl.v[6] = ld.x; nl.v[7] = ld.y;
+            nr.v[0] = ra.x; nr.v[1] = ra.y; nr.v[2] = rb.x; nr.v[3] = rb.y; nr.v[4] = rc.x; nr.v[5] = rc.y; nr.v[6] = rd.x; nr.v[7] = rd.y;
+            nl.key = key;
+            nr.key = key | (1u << (15 - depth));
+        }
+        __syncwarp();
+        valid = lane < 2u * __popc(splits);
+        if (valid) {
+            const SmallNode &n = nodes[lane];
+            a = {n.v[0], n.v[1]}; b = {n.v[2], n.v[3]}; c = {n.v[4], n.v[5]}; d = {n.v[6], n.v[7]};
+            key = n.key;
+        }
+        __syncwarp();
     }
     __syncwarp();
     // depth-first order = ascending tag: rank every leaf (n_leaf <= 64)
@@ -116,7 +127,8 @@ __device__ __forceinline__ uint32_t small_flatten_curve(pointy::Pt a, pointy::Pt
 
 template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_constant__ SmallArgs A, JobState *__restrict__ js_out, Counters *__restrict__ cnt_out,
-                                                              EdgeRec *__restrict__ edges_out, uint32_t *__restrict__ poison, uint32_t *__restrict__ host_flag) {
+                                                              EdgeRec *__restrict__ edges_out, uint32_t *__restrict__ poison, uint32_t *__restrict__ host_flag,
+                                                              uint32_t *__restrict__ done_count, uint32_t *__restrict__ host_done) {
     extern __shared__ __align__(16) uint8_t small_smem[];
     SmallShared &S = *reinterpret_cast<SmallShared *>(small_smem);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -125,6 +137,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         S.pool_used = 0; S.n_popped = 0;
         S.overflow = *poison;  // an earlier small fill is waiting to be repeated by the host: keep the order, draw nothing
         S.top_key = ~0ull; S.top_vid = NONE32;
+        S.n_edges = 0; S.n_staged = 0; S.touched = 0;
     }
     for (uint32_t i = tid; i <= SMALL_MAX_OPS; i += blockDim.x) { S.op_cnt[i] = 0; S.op_start[i] = 0; S.op_off[i] = 0; }
     __syncthreads();
@@ -148,10 +161,10 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
             __syncwarp();
         } else if (op.tag == FTL_OP_QUAD) {
             const pointy::Pt b = pointy::transform(e, {op.v[0], op.v[1]}), c = pointy::transform(e, {op.v[2], op.v[3]});
-            n = small_flatten_curve<false>(a, b, c, c, A.job.tol_sq, S.leaf_x[warp], S.leaf_y[warp], S.leaf_key[warp], out);
+            n = small_flatten_curve<false>(a, b, c, c, A.job.tol_sq, S.leaf_x[warp], S.leaf_y[warp], S.leaf_key[warp], S.nodes[warp], out);
         } else {
             const pointy::Pt b = pointy::transform(e, {op.v[0], op.v[1]}), c = pointy::transform(e, {op.v[2], op.v[3]}), d = pointy::transform(e, {op.v[4], op.v[5]});
-            n = small_flatten_curve<true>(a, b, c, d, A.job.tol_sq, S.leaf_x[warp], S.leaf_y[warp], S.leaf_key[warp], out);
+            n = small_flatten_curve<true>(a, b, c, d, A.job.tol_sq, S.leaf_x[warp], S.leaf_y[warp], S.leaf_key[warp], S.nodes[warp], out);
         }
         if (n == 0xFFFFFFFFu) {
             if (lane == 0) S.overflow = 1;
@@ -189,14 +202,8 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         if (lane == 0) { S.op_off[i] = base; S.op_cnt[i] = kept; S.op_start[i] = starts ? 1u : 0u; }
     }
     __syncthreads();
-    if (S.overflow) {
-        if (blockIdx.x == 0 && tid == 0) {
-            *poison = 1u;
-            *host_flag = 1u;
-            cnt_out->overflow = 1u;
-        }
-        return;
-    }
+    bool draw = !S.overflow;
+    if (draw) {
     // ---- vertex offsets and sub-figure heads over the ops (n_ops <= 112: one warp, four ops per lane) ----
     if (warp == 0) {
         uint32_t cnt[4], sum = 0;
@@ -296,9 +303,9 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
     }
     __syncthreads();
     const JobState js = S.js;
-    if (js.top_vid == NONE32) return;  // no vertices: nothing is drawn (fig.rs:491)
+    draw = js.top_vid != NONE32;  // no vertices: nothing is drawn (fig.rs:491)
     // ---- edges: one per ring segment (fig.rs:179-210,576-600) ----
-    for (uint32_t k = tid; k < nv; k += blockDim.x) {
+    for (uint32_t k = tid; k < nv && draw; k += blockDim.x) {
         const Vtx v = S.V[k];
         const bool last = vtx_is_last(S.V, nv, k);
         const bool pop = last && vtx_same(v, S.V[v.sub]);
@@ -313,77 +320,123 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
             }
         }
         if (!ed.flags) { ed.x_bot0 = 0; ed.inv_slope = 0; ed.step_pix = 0; ed.ry0 = 0; ed.ry1 = -1; ed.fr = 0; ed.job = 0; }
+        else atomicAdd(&S.n_edges, 1u);
         S.E[k] = ed;
         if (blockIdx.x == 0 && edges_out) edges_out[k] = ed;
     }
     __syncthreads();
+    // the scatter below adds packed 32-bit words: exact while fewer than 128 edges can meet in a cell (bin_kernel.cuh)
+    if (draw && S.n_edges >= BIN_PACKED_MAX) {
+        if (tid == 0) S.overflow = 1;
+        draw = false;
+    }
+    __syncthreads();
 
-    // ---- (c)+(d): every warp draws bands of 32 rows with the lanes-are-rows scatter of bin_kernel.cuh ----
-    typedef BinTile<SMALL_WC> T;
-    uint32_t cells = smem_addr(small_smem) + (uint32_t)((sizeof(SmallShared) + 15u) & ~15u) + warp * T::BYTES;
-    asm volatile("" : "+r"(cells));
-    const uint32_t stage = cells + T::STAGE;
-    for (uint32_t i = lane; i < T::CELL_BYTES / 16; i += 32) ssts4_bias(cells + 16u * i);
-    __syncwarp();
+    // ---- (c)+(d): this CTA draws one band of 32 rows; the tile spans the whole raster width ----
     const int32_t W = (int32_t)A.W;
-    const uint32_t n_bands = (A.row_end - A.row_begin + BIN_ROWS - 1) / BIN_ROWS, n_win = (A.W + SMALL_WC - 1) / SMALL_WC;
-    const uint32_t rbase = cells + lane * T::ROW_BYTES;
-    const uint32_t rule = A.job.rule, color = A.job.color;
-    for (uint32_t band = blockIdx.x * SMALL_WARPS + warp; band < n_bands; band += gridDim.x * SMALL_WARPS) {
-        const int32_t row0 = (int32_t)A.row_begin + (int32_t)(band << BIN_LOG2R);
-        const int32_t row = row0 + (int32_t)lane;
-        const bool row_ok = row >= js.first_row && row < (int32_t)A.row_end;
-        const uint32_t valid_mask = __ballot_sync(0xFFFFFFFFu, row_ok);
-        if (valid_mask == 0) continue;
-        const bool band_full = valid_mask == 0xFFFFFFFFu;
+    const uint32_t seg = A.W <= 256u ? 256u : 512u;                       // columns per resolve pass
+    const uint32_t row_bytes = ((A.W + seg - 1) / seg) * seg * 2u + BIN_ROW_PAD;
+    uint32_t cells = smem_addr(small_smem) + (uint32_t)((sizeof(SmallShared) + 15u) & ~15u);
+    asm volatile("" : "+r"(cells));
+    const int32_t row0 = (int32_t)A.row_begin + (int32_t)(blockIdx.x << BIN_LOG2R);
+    const int32_t row = row0 + (int32_t)lane;
+    const bool row_ok = draw && row >= js.first_row && row < (int32_t)A.row_end;  // rows above the figure are untouched (fig.rs:497)
+    const uint32_t valid_mask = __ballot_sync(0xFFFFFFFFu, row_ok);
+    if (valid_mask != 0) {
+        const int32_t v_lo = __ffs((int)valid_mask) - 1, v_hi = 31 - __clz((int)valid_mask);
+        for (uint32_t i = tid; i < BIN_ROWS * row_bytes / 16; i += blockDim.x) ssts4_bias(cells + 16u * i);
+        // the edges crossing the band, prepared once (compacted in any order: sums do not depend on it)
+        for (uint32_t k = tid; k < nv; k += blockDim.x) {
+            const EdgeRec ed = S.E[k];
+            const int32_t r0 = ed.ry0 - row0, r1 = ed.ry1 - row0;
+            const int32_t nrows = min(r1, v_hi) - max(r0, v_lo) + 1;
+            if (!(ed.flags & 1u) || nrows <= 0) continue;
+            const uint32_t slot = atomicAdd(&S.n_staged, 1u);
+            const fx_t fr0 = (fx_t)(ed.fr & 0xFFFFu), fr1 = (fx_t)(ed.fr >> 16);
+            int4 a, b;
+            a.x = (int32_t)((uint32_t)ed.x_bot0 + (uint32_t)(row0 - ed.ry0) * (uint32_t)ed.inv_slope);
+            a.y = ed.inv_slope;
+            a.z = ed.step_pix > 0 ? ed.step_pix : FX_ONE;
+            a.w = (max(r0, -1) + 1) | (min(r1, (int32_t)BIN_ROWS) << 8);
+            b.x = (ed.flags & 2u) ? -1 : 1;
+            b.y = fx_mul(ed.inv_slope, FX_ONE - fr0);
+            b.z = fx_mul(ed.inv_slope, (FX_ONE - fr1) & FX_MASK);
+            b.w = (int32_t)((uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9));
+            S.stage[2 * slot] = a;
+            S.stage[2 * slot + 1] = b;
+            S.item_end[slot] = (uint32_t)nrows;
+            atomicOr(&S.touched, ((2u << (nrows - 1)) - 1u) << max(r0, v_lo));
+        }
+        __syncthreads();
+        const uint32_t n_staged = S.n_staged;
+        if (warp == 0) {  // inclusive prefix of the item counts (fewer than 128 edges: four per lane)
+            uint32_t c4[4], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = lane * 4 + k;
+                c4[k] = i < n_staged ? S.item_end[i] : 0u;
+                sum += c4[k];
+            }
+            uint32_t inc = sum;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
+                if ((int)lane >= d) inc += o;
+            }
+            uint32_t run = inc - sum;
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t i = lane * 4 + k;
+                run += c4[k];
+                if (i < BIN_PACKED_MAX) S.item_end[i] = run;
+            }
+        }
+        __syncthreads();
+        // (c) scatter: one (edge, row) item per thread and pass
+        const uint32_t n_items = n_staged ? S.item_end[n_staged - 1] : 0u;
+        for (uint32_t q = tid; q < n_items; q += blockDim.x) {
+            uint32_t k = 0;  // first staged edge with item_end > q (entries beyond n_staged repeat the total)
+#pragma unroll
+            for (uint32_t h = 64; h > 0; h >>= 1)
+                if (S.item_end[k + h - 1] <= q) k += h;
+            const uint32_t before = k ? S.item_end[k - 1] : 0u;
+            const int4 a = S.stage[2 * k], b = S.stage[2 * k + 1];
+            const int32_t er0 = (a.w & 0xFF) - 1, er1 = a.w >> 8;
+            bin_item_packed<false>(a.x, a.y, a.z, er0, er1, b.y, b.z, (uint32_t)b.w, b.x, max(er0, v_lo) + (int32_t)(q - before), W, 0, W, cells, row_bytes, 0u);
+        }
+        __syncthreads();
+        // (d) resolve: the rows are dealt to the warps; a row wider than a pass carries its sum from pass to pass
+        const uint32_t touched = S.touched & valid_mask, rule = A.job.rule, color = A.job.color;
         uint8_t *dst = reinterpret_cast<uint8_t *>(A.job.raster) + (size_t)(row0 - (int32_t)A.row_begin) * A.pitch;
         int32_t carry = 0;
-        for (uint32_t w = 0; w < n_win; w++) {
-            const int32_t win_lo = (int32_t)(w * (uint32_t)SMALL_WC), win_hi = min(W, win_lo + SMALL_WC);
-            int32_t tot = 0;
-            bool row_touched = false;
-            for (uint32_t base = 0; base < nv; base += 32) {
-                // stage the edges of this round that cross the band (compacted: the item loop visits only those)
-                const EdgeRec ed = base + lane < nv ? S.E[base + lane] : S.E[0];
-                const int32_t r0 = ed.ry0 - row0, r1 = ed.ry1 - row0;
-                const bool hit = base + lane < nv && (ed.flags & 1u) && r0 < (int32_t)BIN_ROWS && r1 >= 0;
-                const uint32_t hits = __ballot_sync(0xFFFFFFFFu, hit);
-                if (hits == 0) continue;
-                if (hit) {
-                    const uint32_t slot = __popc(hits & ((1u << lane) - 1u));
-                    const fx_t fr0 = (fx_t)(ed.fr & 0xFFFFu), fr1 = (fx_t)(ed.fr >> 16);
-                    const bool full = band_full && r0 < 0 && r1 >= (int32_t)BIN_ROWS;
-                    int4 a, b;
-                    a.x = (int32_t)((uint32_t)ed.x_bot0 + (uint32_t)(row0 - ed.ry0) * (uint32_t)ed.inv_slope);
-                    a.y = ed.inv_slope;
-                    a.z = ed.step_pix > 0 ? ed.step_pix : FX_ONE;
-                    a.w = (max(r0, -1) + 1) | (min(r1, (int32_t)BIN_ROWS) << 8);
-                    b.x = (ed.flags & 2u) ? -1 : 1;
-                    b.y = fx_mul(ed.inv_slope, FX_ONE - fr0);
-                    b.z = fx_mul(ed.inv_slope, (FX_ONE - fr1) & FX_MASK);
-                    b.w = (int32_t)((uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9) | (full ? 1u << 19 : 0u));
-                    ssts4(stage + slot * 32u, a);
-                    ssts4(stage + slot * 32u + 16u, b);
-                }
-                __syncwarp();
-                row_touched = true;
-                const uint32_t cnt = __popc(hits);
-#pragma unroll 1
-                for (uint32_t k = 0; k < cnt; k++) {
-                    const int4 a = slds4(stage + k * 32u), b = slds4(stage + k * 32u + 16u);
-                    if (b.w & (1 << 19))
-                        bin_item_rows<true>(a.x, a.y, a.z, 0, 0, b.y, b.z, (uint32_t)b.w, b.x, (int32_t)lane, true, W, win_lo, win_hi, rbase, tot);
-                    else
-                        bin_item_rows<false>(a.x, a.y, a.z, (a.w & 0xFF) - 1, a.w >> 8, b.y, b.z, (uint32_t)b.w, b.x, (int32_t)lane, row_ok, W, win_lo, win_hi, rbase, tot);
-                }
-                __syncwarp();
+        for (uint32_t x0 = 0; x0 < A.W; x0 += seg) {
+            uint8_t *dwin = dst + (size_t)x0 * A.bpp;
+            const uint32_t c0 = cells + 2u * x0, w_rel = A.W - x0;
+            int32_t tot;
+            if (seg == 256u) {
+                if (rule == FTL_EVENODD) tot = bin_resolve<FMT, true, ALIGNED, 256, true>(c0, touched, carry, valid_mask, dwin, A.pitch, w_rel, color, row_bytes, 2 * warp, 2 * SMALL_WARPS);
+                else tot = bin_resolve<FMT, false, ALIGNED, 256, true>(c0, touched, carry, valid_mask, dwin, A.pitch, w_rel, color, row_bytes, 2 * warp, 2 * SMALL_WARPS);
+            } else {
+                if (rule == FTL_EVENODD) tot = bin_resolve<FMT, true, ALIGNED, 512, true>(c0, touched, carry, valid_mask, dwin, A.pitch, w_rel, color, row_bytes, warp, SMALL_WARPS);
+                else tot = bin_resolve<FMT, false, ALIGNED, 512, true>(c0, touched, carry, valid_mask, dwin, A.pitch, w_rel, color, row_bytes, warp, SMALL_WARPS);
             }
-            const uint32_t touched = __ballot_sync(0xFFFFFFFFu, row_touched && row_ok);
-            uint8_t *dwin = dst + (size_t)win_lo * A.bpp;
-            if (rule == FTL_EVENODD) bin_resolve<FMT, true, ALIGNED, SMALL_WC>(cells, touched, carry, valid_mask, dwin, A.pitch, (uint32_t)(W - win_lo), color);
-            else bin_resolve<FMT, false, ALIGNED, SMALL_WC>(cells, touched, carry, valid_mask, dwin, A.pitch, (uint32_t)(W - win_lo), color);
-            __syncwarp();
             carry += tot;
+        }
+    }
+    }  // if (draw)
+    // ---- completion: the last CTA tells the host (a word in mapped memory, so ftl_sync can watch it instead of the stream) ----
+    __syncthreads();
+    if (tid == 0) {
+        if (S.overflow && blockIdx.x == 0) {
+            *poison = 1u;
+            *host_flag = 1u;
+            cnt_out->overflow = 1u;
+        }
+        __threadfence_system();
+        if (atomicAdd(done_count, 1u) == gridDim.x - 1) {
+            *done_count = 0u;
+            __threadfence_system();
+            *reinterpret_cast<volatile uint32_t *>(host_done) = A.seq;
         }
     }
 }

@@ -179,6 +179,11 @@ uint64_t ftl_launch_count(void);
 int ftl_set_profiling(int enabled);
 int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches);
 
+/* Per-call latency of ftl_fill (benches/fishyb.rs:10-39 times exactly this call), measured inside the library so that
+ * no binding overhead is counted: iters calls, each followed by ftl_sync when sync_each != 0 (otherwise one at the end). */
+int ftl_time_fills(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color, uint32_t iters, int sync_each,
+                   double *us_per_call);
+
 /* ---- Parity probes (used by tests only) --------------------------------- */
 /* Flattened Fixed points of a fill after point intake (fig.rs:428-461):
  * returns the count via *n_points and writes up to cap (x,y) i32 pairs; subs

@@ -819,3 +819,57 @@ def test_property_matte_fill_is_idempotent_and_deterministic_full_batch():
         exp = o.raster()
         assert np.array_equal(b1.read(int(j), 1)[0], exp)
         assert int(s1[j]) == fnv_expected(exp)
+
+
+# ---- the one-launch path for small fills (small_kernel.cuh) against the general pipeline and the oracle ----------
+def _general_path(on):
+    import os
+    if on:
+        os.environ["FTL_NO_SMALL"] = "1"
+    else:
+        os.environ.pop("FTL_NO_SMALL", None)
+
+
+@pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p, Format.Graya8p])
+def test_small_fill_equals_general_pipeline_and_oracle(fmt):
+    rng = np.random.default_rng(2024)
+    for it in range(24):
+        w, h = int(rng.integers(1, 300)), int(rng.integers(1, 300))
+        if it % 6 == 0:
+            w, h = 1024, 37  # four windows per band
+        ops = random_path(rng, max(w, h), int(rng.integers(1, 12)))
+        rule = FillRule.EvenOdd if it & 1 else FillRule.NonZero
+        clr = tuple(int(v) for v in rng.integers(0, 256, 4))
+        init = rng.integers(0, 256, (h, w * {Format.Matte8: 1, Format.Graya8p: 2, Format.Rgba8p: 4}[fmt]), dtype=np.uint8)
+        imgs, infos, edges = [], [], []
+        for general in (False, True):
+            _general_path(general)
+            try:
+                g, o = both(w, h, fmt, init=init, tol=0.3 if it % 3 else 0.05)
+                g.fill(rule, ops, clr)
+                g.fill(rule, ops, clr)  # twice: blends are not idempotent, and the tile must be left clean
+                imgs.append(g.raster().pixels)
+                infos.append(g.debug_last_fill())
+                edges.append(np.sort(g.debug_edges().view([("f%d" % k, "<i4") for k in range(6)]), axis=0))
+            finally:
+                _general_path(False)
+        o.fill(int(rule), ops, clr)
+        o.fill(int(rule), ops, clr)
+        assert infos[0] == infos[1] == o.last_info(), it
+        assert np.array_equal(edges[0], edges[1]), it
+        assert np.array_equal(imgs[0], imgs[1]), it
+        assert np.array_equal(imgs[0], o.raster()), it
+
+
+def test_small_fill_overflow_falls_back_in_order():
+    """A fill that does not fit the one-launch kernel (a curve with more than 64 points) draws nothing there, poisons the
+    small fills issued after it, and all of them are repeated IN ORDER by the general pipeline at the next blocking call."""
+    big = Path2D().absolute().move_to(5, 5).cubic_to(900, 20, 20, 900, 600, 600).close().finish()
+    small = poly([(10, 10), (200, 30), (120, 220)])
+    g, o = both(640, 640, Format.Rgba8p, tol=0.01)
+    seq = [(small, (200, 10, 10, 128)), (big, (10, 200, 10, 128)), (small, (10, 10, 200, 128)), (big, (90, 90, 0, 200)), (small, (0, 50, 50, 77))]
+    for ops, clr in seq:
+        g.fill(FillRule.NonZero, ops, clr)
+        o.fill(oracle.NONZERO, ops, clr)
+    assert_same(g, o)
+    assert g.debug_last_fill() == o.last_info()
