@@ -8,7 +8,7 @@ library or a CUDA device every drawing call raises.
 """
 from .path import FillRule, JoinStyle, OpTag, OP_DTYPE, Path2D, PathOp, as_ops  # noqa: F401
 from .plotter import Batch, Format, Plotter, Raster, debug_accumulate  # noqa: F401
-from ._lib import FootileError, device_count, launch_count, set_profiling, tile_kernel_time  # noqa: F401
+from ._lib import FootileError, device_count, launch_count, set_profiling, tile_kernel_time, transfer_bytes  # noqa: F401
 
 __all__ = ["FillRule", "JoinStyle", "OpTag", "OP_DTYPE", "Path2D", "PathOp", "as_ops", "Batch", "Format", "Plotter", "Raster",
-           "debug_accumulate", "FootileError", "device_count", "launch_count", "set_profiling", "tile_kernel_time"]
+           "debug_accumulate", "FootileError", "device_count", "launch_count", "set_profiling", "tile_kernel_time", "transfer_bytes"]

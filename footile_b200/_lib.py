@@ -16,11 +16,11 @@ SYMBOLS = [
     "ftl_plotter_new", "ftl_plotter_new_band", "ftl_plotter_free", "ftl_width", "ftl_height",
     "ftl_set_tolerance", "ftl_set_transform", "ftl_set_join", "ftl_pen_width",
     "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
-    "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill",
+    "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill", "ftl_batch_set_join", "ftl_batch_stroke",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
     "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream", "ftl_fill_upload", "ftl_fill_replay",
-    "ftl_launch_count", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_time_fills",
-    "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
+    "ftl_launch_count", "ftl_transfer_bytes", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_time_fills",
+    "ftl_debug_small_profile", "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
 ]
 
 
@@ -69,6 +69,8 @@ def lib():
         "ftl_batch_set_tolerance": (i32, [vp, f32]),
         "ftl_batch_clear": (i32, [vp, u32, u32]),
         "ftl_batch_fill": (i32, [vp, u32, vp, vp, vp, vp, vp]),
+        "ftl_batch_set_join": (i32, [vp, i32, f32]),
+        "ftl_batch_stroke": (i32, [vp, u32, vp, vp, vp, vp]),
         "ftl_batch_read": (i32, [vp, u32, u32, vp, sz]),
         "ftl_batch_checksums": (i32, [vp, u32, u32, vp]),
         "ftl_batch_sync": (i32, [vp]),
@@ -80,11 +82,13 @@ def lib():
         "ftl_batch_stream": (i32, [vp, vp]),
         "ftl_stream": (i32, [vp, vp]),
         "ftl_launch_count": (C.c_uint64, []),
+        "ftl_transfer_bytes": (i32, [i32, vp, vp]),
         "ftl_set_profiling": (i32, [i32]),
         "ftl_tile_kernel_time": (i32, [i32, vp, vp]),
         "ftl_time_fills": (i32, [vp, i32, vp, sz, vp, u32, i32, vp]),
         "ftl_debug_flatten": (i32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
         "ftl_debug_last_fill": (i32, [vp, vp]),
+        "ftl_debug_small_profile": (i32, [vp, vp]),
         "ftl_debug_edges": (i32, [vp, vp, sz, vp]),
         "ftl_debug_stroke_ops": (i32, [vp, vp, sz, vp, sz, vp]),
         "ftl_debug_stroke_outline": (i32, [i32, f32, f32, vp, sz, vp, vp, vp, sz, vp]),
@@ -114,6 +118,13 @@ def device_count():
 
 def launch_count():
     return int(lib().ftl_launch_count())
+
+
+def transfer_bytes(reset=False):
+    """(h2d, d2h) bytes the library moved over PCIe since load / the last reset."""
+    a, b = C.c_uint64(0), C.c_uint64(0)
+    check(lib().ftl_transfer_bytes(1 if reset else 0, C.byref(a), C.byref(b)))
+    return int(a.value), int(b.value)
 
 
 def set_profiling(on):

@@ -1,10 +1,13 @@
 // capi.cpp — the C ABI of include/footile_b200.h over ftl::Engine.
 // Plain pointers and sizes only; never throws across the boundary.
+#include <stdlib.h>
 #include <string.h>
 
 #include <chrono>
 
+#include <algorithm>
 #include <new>
+#include <thread>
 #include <vector>
 
 #include "engine.h"
@@ -29,6 +32,8 @@ struct ftl_batch {
     uint32_t capacity = 0;
     void *rasters = nullptr;
     float tol_sq = 0.3f * 0.3f;
+    int join = FTL_JOIN_MITER;
+    float miter_limit = 4.0f;
     explicit ftl_batch(int device) : eng(device) {}
 };
 
@@ -195,11 +200,35 @@ int ftl_fill_layers(ftl_plotter *p, uint32_t n_layers, const ftl_path_op *ops, c
     GUARD_END
 }
 
+// The stroke-side flatten runs on the host unless the path is huge (or FTL_DEVICE_STROKE_FLATTEN=1 asks for the device
+// kernel: the parity tests compare the two): a device round trip costs more than flattening a few thousand ops here.
+static bool stroke_flatten_on_host(size_t n_ops) {
+    const char *ev = getenv("FTL_DEVICE_STROKE_FLATTEN");
+    if (ev && atoi(ev) != 0) return false;
+    return n_ops <= (1u << 16);
+}
+static int check_finite_ops(const ftl_path_op *ops, size_t n_ops) {
+    for (size_t i = 0; i < n_ops; i++) {
+        if (ops[i].tag > FTL_OP_PENWIDTH) return bad("unknown path op tag");
+        const int nv = ops[i].tag == FTL_OP_CLOSE ? 0 : (ops[i].tag == FTL_OP_QUAD ? 4 : (ops[i].tag == FTL_OP_CUBIC ? 6 : (ops[i].tag == FTL_OP_PENWIDTH ? 1 : 2)));
+        for (int k = 0; k < nv; k++)
+            if (!(ops[i].v[k] - ops[i].v[k] == 0.0f)) {
+                set_error("non-finite coordinate in path op");
+                return FTL_ERR_NONFINITE;
+            }
+    }
+    return FTL_OK;
+}
+
 static int stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, std::vector<ftl_path_op> *outline) {
     std::vector<float> opw;
     float final_w = stroke_widths(p->s_width, ops, n_ops, &opw);
     WideFlat flat;
-    int rc = p->eng.flatten_wide(p->e, p->tol_sq, ops, n_ops, opw.data(), &flat);
+    int rc = FTL_OK;
+    if (stroke_flatten_on_host(n_ops)) {
+        if ((rc = check_finite_ops(ops, n_ops))) return rc;
+        flatten_wide_host(p->e, p->tol_sq, ops, n_ops, opw.data(), &flat);
+    } else rc = p->eng.flatten_wide(p->e, p->tol_sq, ops, n_ops, opw.data(), &flat);
     if (rc) return rc;
     p->s_width = final_w;
     StrokeParams sp;
@@ -342,6 +371,67 @@ int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const 
     return b->eng.fill(b->geo, jobs, ops, n_ops);
     GUARD_END
 }
+int ftl_batch_set_join(ftl_batch *b, int join, float miter_limit) {
+    if (!b) return bad("null batch");
+    if (join < FTL_JOIN_MITER || join > FTL_JOIN_ROUND) return bad("unknown join style");
+    b->join = join;
+    b->miter_limit = miter_limit;
+    return FTL_OK;
+}
+
+// n_jobs strokes in one pass: every job is flattened and outlined on host threads (stroker.rs:204-416 is sequential f32
+// arithmetic over libm, a few microseconds per path), the outlines are concatenated and filled NonZero by ONE pass of
+// the device pipeline - with transforms[j] applied a second time, exactly as Plotter::stroke does (plotter.rs:361-364).
+int ftl_batch_stroke(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const float *transforms, const uint8_t *colors) {
+    GUARD_BEGIN
+    if (!b) return bad("null batch");
+    if (n_jobs == 0) return FTL_OK;
+    if (n_jobs > b->capacity) return bad("more jobs than rasters in the batch");
+    if (!op_offsets) return bad("op_offsets is null");
+    const size_t n_ops = (size_t)op_offsets[n_jobs];
+    if (n_ops && !ops) return bad("ops is null");
+    for (uint32_t j = 0; j < n_jobs; j++)
+        if (op_offsets[j + 1] < op_offsets[j] || op_offsets[j + 1] > 0x7FFFFFFFull) return bad("op_offsets must be non-decreasing");
+    int rc = check_finite_ops(ops, n_ops);
+    if (rc) return rc;
+    std::vector<std::vector<ftl_path_op>> outlines(n_jobs);
+    StrokeParams sp;
+    sp.join = b->join; sp.miter_limit = b->miter_limit; sp.tol_sq = b->tol_sq;
+    auto work = [&](uint32_t j0, uint32_t j1) {
+        std::vector<float> opw;
+        WideFlat flat;
+        static const float ident[6] = {1, 0, 0, 0, 1, 0};
+        for (uint32_t j = j0; j < j1; j++) {
+            const ftl_path_op *jo = ops + op_offsets[j];
+            const size_t jn = (size_t)(op_offsets[j + 1] - op_offsets[j]);
+            stroke_widths(1.0f, jo, jn, &opw);  // a new Plotter starts with pen width 1 (plotter.rs:112)
+            flatten_wide_host(transforms ? transforms + 6 * (size_t)j : ident, b->tol_sq, jo, jn, opw.data(), &flat);
+            stroke_outline(sp, jo, jn, flat, &outlines[j]);
+        }
+    };
+    unsigned nt = n_ops < 4096 ? 1u : std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency()));
+    nt = std::min<unsigned>(nt, n_jobs);
+    if (nt <= 1) work(0, n_jobs);
+    else {
+        std::vector<std::thread> th;
+        const uint32_t per = (n_jobs + nt - 1) / nt;
+        for (unsigned t = 0; t < nt; t++) {
+            const uint32_t j0 = std::min(n_jobs, t * per), j1 = std::min(n_jobs, j0 + per);
+            if (j0 < j1) th.emplace_back(work, j0, j1);
+        }
+        for (std::thread &t : th) t.join();
+    }
+    std::vector<uint64_t> offs(n_jobs + 1, 0);
+    for (uint32_t j = 0; j < n_jobs; j++) offs[j + 1] = offs[j] + outlines[j].size();
+    std::vector<ftl_path_op> all((size_t)offs[n_jobs]);
+    for (uint32_t j = 0; j < n_jobs; j++)
+        if (!outlines[j].empty()) memcpy(all.data() + offs[j], outlines[j].data(), outlines[j].size() * sizeof(ftl_path_op));
+    std::vector<HostJob> jobs;
+    if ((rc = batch_jobs(b, n_jobs, offs.data(), nullptr, transforms, colors, &jobs))) return rc;
+    return b->eng.fill(b->geo, jobs, all.data(), all.size());
+    GUARD_END
+}
+
 int ftl_batch_upload(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const uint8_t *rules,
                      const float *transforms, const uint8_t *colors) {
     GUARD_BEGIN
@@ -412,6 +502,10 @@ int ftl_stream(ftl_plotter *p, void **stream) {
 
 // ---- instrumentation ----
 uint64_t ftl_launch_count(void) { return Engine::launch_count(); }
+int ftl_transfer_bytes(int reset, uint64_t *h2d, uint64_t *d2h) {
+    Engine::transfer_bytes(reset != 0, h2d, d2h);
+    return FTL_OK;
+}
 int ftl_set_profiling(int enabled) {
     Engine::set_profiling(enabled != 0);
     return FTL_OK;
@@ -438,6 +532,16 @@ int ftl_time_fills(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_op
     const auto t1 = std::chrono::steady_clock::now();
     *us_per_call = iters ? std::chrono::duration<double, std::micro>(t1 - t0).count() / iters : 0.0;
     return FTL_OK;
+    GUARD_END
+}
+
+int ftl_debug_small_profile(ftl_plotter *p, int64_t stamps[9]) {
+    GUARD_BEGIN
+    if (!p || !stamps) return bad("null argument");
+    long long t[9];
+    int rc = p->eng.small_profile(t);
+    for (int k = 0; k < 9; k++) stamps[k] = t[k];
+    return rc;
     GUARD_END
 }
 

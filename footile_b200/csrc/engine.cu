@@ -67,6 +67,7 @@ const char *last_error() { return g_err.c_str(); }
     } while (0)
 
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_h2d_bytes{0}, g_d2h_bytes{0};  // bytes this library moved over PCIe (rasters and path data; not the few counter words)
 static std::atomic<bool> g_profiling{false};
 #define LAUNCHED() g_launches.fetch_add(1, std::memory_order_relaxed)
 
@@ -186,6 +187,14 @@ int Engine::device_count(int *count) {
     return FTL_OK;
 }
 uint64_t Engine::launch_count() { return g_launches.load(); }
+void Engine::transfer_bytes(bool reset, uint64_t *h2d, uint64_t *d2h) {
+    if (h2d) *h2d = g_h2d_bytes.load();
+    if (d2h) *d2h = g_d2h_bytes.load();
+    if (reset) {
+        g_h2d_bytes.store(0);
+        g_d2h_bytes.store(0);
+    }
+}
 void Engine::set_profiling(bool on) { g_profiling.store(on); }
 void Engine::tile_kernel_time(bool reset, double *ms, uint64_t *launches) {
     std::lock_guard<std::mutex> lock(g_spans_mu);
@@ -250,7 +259,7 @@ static BinKernel bin_kernel_wc(int fmt, bool aligned) {
     default: return aligned ? raster_bins<FTL_RGBA8P, true, WC> : raster_bins<FTL_RGBA8P, false, WC>;
     }
 }
-typedef void (*SmallKernel)(const SmallArgs, JobState *, Counters *, EdgeRec *, uint32_t *, uint32_t *, uint32_t *, uint32_t *);
+typedef void (*SmallKernel)(const SmallArgs, JobState *, Counters *, EdgeRec *, uint32_t *, uint32_t *, uint32_t *, uint32_t *, long long *);
 static SmallKernel small_kernel(int fmt, bool aligned) {
     switch (fmt) {
     case FTL_MATTE8: return aligned ? small_fill<FTL_MATTE8, true> : small_fill<FTL_MATTE8, false>;
@@ -515,6 +524,7 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
                 return rc;
             }
             CK(cudaMemcpyAsync((ftl_path_op *)m.ops.p + at, (const ftl_path_op *)m.pin_ops.p + at, cnt * sizeof(ftl_path_op), cudaMemcpyHostToDevice, m.st));
+            g_h2d_bytes.fetch_add(cnt * sizeof(ftl_path_op), std::memory_order_relaxed);
         }
     }
     JobDesc *jd = (JobDesc *)m.pin_jobs.p;
@@ -536,9 +546,26 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
         jd[j] = d;
     }
     CK(cudaMemcpyAsync(m.jobs.p, m.pin_jobs.p, jobs_bytes, cudaMemcpyHostToDevice, m.st));
+    g_h2d_bytes.fetch_add(jobs_bytes, std::memory_order_relaxed);
     m.P = P;
     m.smem_bytes = (int)((size_t)P.warp_words * 4 * P.cta_warps);
     m.have_jobs = true;
+    return FTL_OK;
+}
+
+// FTL_SMALL_PROF=1: block 0 of every small fill stamps clock64() at its phase boundaries into 16 words behind the poison
+// word pair (read back with Engine::small_profile); a development aid, off by default.
+static long long *small_prof(Engine::Impl &m) {
+    static const bool on = getenv("FTL_SMALL_PROF") && atoi(getenv("FTL_SMALL_PROF")) != 0;
+    return on ? (long long *)((uint32_t *)m.small_poison.p + 2) : nullptr;
+}
+int Engine::small_profile(long long out[9]) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    for (int k = 0; k < 9; k++) out[k] = 0;
+    if (!m.small_poison.p) return FTL_OK;
+    CK(cudaStreamSynchronize(m.st));
+    CK(cudaMemcpy(out, (uint32_t *)m.small_poison.p + 2, 9 * sizeof(long long), cudaMemcpyDeviceToHost));
     return FTL_OK;
 }
 
@@ -560,8 +587,8 @@ static int fill_small(Engine::Impl &m, const Geometry &g, const HostJob &h, cons
     if (!m.small_flags.p) {
         if ((rc = m.small_flags.ensure((SMALL_RING + 1) * sizeof(uint32_t)))) return rc;
         memset(m.small_flags.p, 0, (SMALL_RING + 1) * sizeof(uint32_t));
-        if ((rc = m.small_poison.ensure(2 * sizeof(uint32_t), st))) return rc;
-        CK(cudaMemsetAsync(m.small_poison.p, 0, 2 * sizeof(uint32_t), st));
+        if ((rc = m.small_poison.ensure(2 * sizeof(uint32_t) + 16 * sizeof(long long), st))) return rc;
+        CK(cudaMemsetAsync(m.small_poison.p, 0, 2 * sizeof(uint32_t) + 16 * sizeof(long long), st));
         m.small_saved.resize(SMALL_RING);
     }
     if ((rc = m.counters.ensure(sizeof(Counters), st))) return rc;
@@ -587,8 +614,9 @@ static int fill_small(Engine::Impl &m, const Geometry &g, const HostJob &h, cons
     const size_t tile_bytes = (size_t)BIN_ROWS * (div_up(g.width, g.width <= 256u ? 256u : 512u) * (g.width <= 256u ? 256u : 512u) * 2 + BIN_ROW_PAD);
     small_kernel(g.format, aligned)<<<n_bands, SMALL_WARPS * 32, ((sizeof(SmallShared) + 15u) & ~(size_t)15u) + tile_bytes, st>>>(
         A, (JobState *)m.jstate.p, (Counters *)m.counters.p, (EdgeRec *)m.edges.p, (uint32_t *)m.small_poison.p, flags + m.small_n,
-        (uint32_t *)m.small_poison.p + 1, flags + SMALL_RING); LAUNCHED();
+        (uint32_t *)m.small_poison.p + 1, flags + SMALL_RING, small_prof(m)); LAUNCHED();
     CK(cudaGetLastError());
+    g_h2d_bytes.fetch_add(sizeof(JobDesc) + n_ops * sizeof(ftl_path_op), std::memory_order_relaxed);  // as kernel arguments
     m.small_n++;
     m.small_tail = true;
     m.have_jobs = false;
@@ -1149,6 +1177,7 @@ int Engine::copy_in(void *dptr, const void *src, size_t bytes) {
         if (rc) return rc;
     }
     impl_->small_tail = false;
+    g_h2d_bytes.fetch_add(bytes, std::memory_order_relaxed);
     CK(cudaMemcpyAsync(dptr, src, bytes, cudaMemcpyHostToDevice, impl_->st));
     CK(cudaStreamSynchronize(impl_->st));
     return FTL_OK;
@@ -1227,6 +1256,7 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
     static const bool raw_only = getenv("FTL_RAW_READ") && atoi(getenv("FTL_RAW_READ")) != 0;
     const size_t PACK_MIN = 4u << 20;
     if (raw_only || bytes < PACK_MIN || (bytes & 1023u) != 0 || ((uintptr_t)dptr & 15u) != 0) {
+        g_d2h_bytes.fetch_add(bytes, std::memory_order_relaxed);
         CK(cudaMemcpyAsync(dst, dptr, bytes, cudaMemcpyDeviceToHost, st));
         CK(cudaStreamSynchronize(st));
         return FTL_OK;
@@ -1263,6 +1293,7 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
             pack_classify<<<grid, 256, 0, st>>>((const uint4 *)src, n_blocks, d_code, d_bm, (uint32_t *)m.pack_cnt.p); LAUNCHED();
             if ((r = run_scan<AddU32>(st, (const uint32_t *)m.pack_cnt.p, (uint32_t)units, d_off, m.tpart))) return r;
             CK(cudaMemcpyAsync(pin_fix.p, d_code, fixed, cudaMemcpyDeviceToHost, st));
+            g_d2h_bytes.fetch_add(fixed, std::memory_order_relaxed);
             CK(cudaStreamSynchronize(st));
             const uint32_t *h_off = (const uint32_t *)((const uint8_t *)pin_fix.p + code_bytes + bm_bytes);
             const size_t n_lit = h_off[units];
@@ -1273,6 +1304,7 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
                 pack_literals<<<grid, 256, 0, st>>>((const uint4 *)src, n_blocks, d_bm, d_off, (uint4 *)m.pack_lit.p); LAUNCHED();
                 CK(cudaGetLastError());
                 CK(cudaMemcpyAsync(pin_lit.p, m.pack_lit.p, n_lit * 32, cudaMemcpyDeviceToHost, st));
+                g_d2h_bytes.fetch_add(n_lit * 32, std::memory_order_relaxed);
                 CK(cudaStreamSynchronize(st));
             }
             return FTL_OK;
@@ -1280,6 +1312,7 @@ int Engine::copy_out(void *dst, const void *dptr, size_t bytes) {
         int r = stage();  // overlaps the expansion of the previous piece
         if (worker.joinable()) worker.join();
         if (r == -1) {  // plain copy of this piece
+            g_d2h_bytes.fetch_add(len, std::memory_order_relaxed);
             cudaError_t e1 = cudaMemcpyAsync(out, src, len, cudaMemcpyDeviceToHost, st);
             cudaError_t e2 = cudaStreamSynchronize(st);
             if (e1 != cudaSuccess || e2 != cudaSuccess) {

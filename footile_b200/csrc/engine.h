@@ -81,6 +81,7 @@ public:
     int checksums(const void *rasters, size_t raster_bytes, uint32_t count, uint64_t *out);
 
     int sync();
+    int small_profile(long long out[9]);  // clock64() stamps of the last small fill's phases (FTL_SMALL_PROF=1)
     int alloc_raster(size_t bytes, void **dptr);
     int free_raster(void *dptr);
     int memset_async(void *dptr, int value, size_t bytes);
@@ -89,6 +90,7 @@ public:
 
     static int device_count(int *count);
     static uint64_t launch_count();
+    static void transfer_bytes(bool reset, uint64_t *h2d, uint64_t *d2h);
     static void set_profiling(bool on);
     static void tile_kernel_time(bool reset, double *ms, uint64_t *launches);
 
@@ -112,6 +114,8 @@ struct StrokeParams {
 };
 void stroke_outline(const StrokeParams &sp, const ftl_path_op *ops, size_t n_ops, const WideFlat &flat,
                     std::vector<ftl_path_op> *out);
+// The stroke-side flatten on the host (same bits as Engine::flatten_wide; stroker.cpp).
+void flatten_wide_host(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, const float *opw, WideFlat *out);
 // Per-op (pen_w, s_width) from the PenWidth ops; returns the final s_width
 // (plotter.rs:128-130,151-153,233-236,293-298).
 float stroke_widths(float s_width, const ftl_path_op *ops, size_t n_ops, std::vector<float> *opw);

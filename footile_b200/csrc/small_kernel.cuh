@@ -128,14 +128,19 @@ __device__ __forceinline__ uint32_t small_flatten_curve(pointy::Pt a, pointy::Pt
 template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_constant__ SmallArgs A, JobState *__restrict__ js_out, Counters *__restrict__ cnt_out,
                                                               EdgeRec *__restrict__ edges_out, uint32_t *__restrict__ poison, uint32_t *__restrict__ host_flag,
-                                                              uint32_t *__restrict__ done_count, uint32_t *__restrict__ host_done) {
+                                                              uint32_t *__restrict__ done_count, uint32_t *__restrict__ host_done, long long *__restrict__ prof) {
     extern __shared__ __align__(16) uint8_t small_smem[];
+#define FTL_STAMP(k) do { if (prof && blockIdx.x == gridDim.x / 2 && threadIdx.x == 0) prof[k] = clock64(); } while (0)
+    FTL_STAMP(0);
     SmallShared &S = *reinterpret_cast<SmallShared *>(small_smem);
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t n_ops = A.n_ops;
+    // an earlier small fill may be waiting to be repeated by the host: then this one keeps the order and draws nothing.
+    // The load is issued now and consumed after the flatten stage, off the critical path.
+    const uint32_t poisoned = tid == 0 ? *reinterpret_cast<const volatile uint32_t *>(poison) : 0u;
     if (tid == 0) {
         S.pool_used = 0; S.n_popped = 0;
-        S.overflow = *poison;  // an earlier small fill is waiting to be repeated by the host: keep the order, draw nothing
+        S.overflow = 0;
         S.top_key = ~0ull; S.top_vid = NONE32;
         S.n_edges = 0; S.n_staged = 0; S.touched = 0;
     }
@@ -201,55 +206,22 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         }
         if (lane == 0) { S.op_off[i] = base; S.op_cnt[i] = kept; S.op_start[i] = starts ? 1u : 0u; }
     }
+    if (tid == 0 && poisoned) S.overflow = 1;
     __syncthreads();
+    FTL_STAMP(1);  // flatten done
     bool draw = !S.overflow;
     if (draw) {
-    // ---- vertex offsets and sub-figure heads over the ops (n_ops <= 112: one warp, four ops per lane) ----
-    if (warp == 0) {
-        uint32_t cnt[4], sum = 0;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t i = lane * 4 + k;
-            cnt[k] = i < n_ops ? S.op_cnt[i] : 0u;
-            sum += cnt[k];
+    // ---- vertex offsets and sub-figure heads over the ops: n_ops <= 112, so every op's thread just adds up the
+    // counts before it (broadcast shared-memory reads, no shuffle chains, no extra barrier) ----
+    if (tid <= n_ops) {
+        uint32_t voff = 0, head = NONE32;
+        for (uint32_t k = 0; k < tid; k++) {
+            if (S.op_start[k]) head = voff;
+            voff += S.op_cnt[k];
         }
-        uint32_t inc = sum;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, inc, d);
-            if ((int)lane >= d) inc += o;
-        }
-        uint32_t run = inc - sum;
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t i = lane * 4 + k;
-            if (i <= n_ops && i <= SMALL_MAX_OPS) S.op_voff[i] = run;
-            run += cnt[k];
-        }
-        if (lane == 31) S.nv = inc;
-        __syncwarp();
-        // head of the sub-figure of every op: the latest starting op at or before it
-        uint32_t head = NONE32, hs[4];
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t i = lane * 4 + k;
-            if (i < n_ops && S.op_start[i]) head = S.op_voff[i];
-            hs[k] = head;
-        }
-        // carry the last head of the lanes below (a max-scan does it: heads grow with the op index, NONE32 = none)
-        uint32_t hin = head == NONE32 ? 0u : head + 1u;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const uint32_t o = __shfl_up_sync(0xFFFFFFFFu, hin, d);
-            if ((int)lane >= d) hin = max(hin, o);
-        }
-        const uint32_t below = __shfl_up_sync(0xFFFFFFFFu, hin, 1);
-        const uint32_t carry_head = lane == 0 ? NONE32 : (below == 0 ? NONE32 : below - 1u);
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const uint32_t i = lane * 4 + k;
-            if (i < n_ops) S.op_sub[i] = hs[k] != NONE32 ? hs[k] : carry_head;
-        }
+        S.op_voff[tid] = voff;
+        S.op_sub[tid] = head;  // first vertex of the latest sub-figure started before this op
+        if (tid == n_ops) S.nv = voff;
     }
     __syncthreads();
     const uint32_t nv = S.nv;
@@ -260,6 +232,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         for (uint32_t t = lane; t < cnt; t += 32) S.V[voff + t] = {S.pool[2 * (off + t)], S.pool[2 * (off + t) + 1], sub, 0u};
     }
     __syncthreads();
+    FTL_STAMP(2);  // vertices in place
     // ---- (b) top-left vertex (fig.rs:493-494), closing rule (fig.rs:373-383) ----
     for (uint32_t k = tid; k < nv; k += blockDim.x) {
         const Vtx v = S.V[k];
@@ -302,6 +275,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         }
     }
     __syncthreads();
+    FTL_STAMP(3);  // top vertex, direction
     const JobState js = S.js;
     draw = js.top_vid != NONE32;  // no vertices: nothing is drawn (fig.rs:491)
     // ---- edges: one per ring segment (fig.rs:179-210,576-600) ----
@@ -332,6 +306,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
     }
     __syncthreads();
 
+    FTL_STAMP(4);  // edges
     // ---- (c)+(d): this CTA draws one band of 32 rows; the tile spans the whole raster width ----
     const int32_t W = (int32_t)A.W;
     const uint32_t seg = A.W <= 256u ? 256u : 512u;                       // columns per resolve pass
@@ -392,6 +367,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
             }
         }
         __syncthreads();
+        FTL_STAMP(5);  // tile cleared, edges staged, prefix
         // (c) scatter: one (edge, row) item per thread and pass
         const uint32_t n_items = n_staged ? S.item_end[n_staged - 1] : 0u;
         for (uint32_t q = tid; q < n_items; q += blockDim.x) {
@@ -405,6 +381,7 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
             bin_item_packed<false>(a.x, a.y, a.z, er0, er1, b.y, b.z, (uint32_t)b.w, b.x, max(er0, v_lo) + (int32_t)(q - before), W, 0, W, cells, row_bytes, 0u);
         }
         __syncthreads();
+        FTL_STAMP(6);  // scatter
         // (d) resolve: the rows are dealt to the warps; a row wider than a pass carries its sum from pass to pass
         const uint32_t touched = S.touched & valid_mask, rule = A.job.rule, color = A.job.color;
         uint8_t *dst = reinterpret_cast<uint8_t *>(A.job.raster) + (size_t)(row0 - (int32_t)A.row_begin) * A.pitch;
@@ -424,19 +401,22 @@ __global__ void __launch_bounds__(SMALL_WARPS * 32) small_fill(const __grid_cons
         }
     }
     }  // if (draw)
+    FTL_STAMP(7);  // resolve
     // ---- completion: the last CTA tells the host (a word in mapped memory, so ftl_sync can watch it instead of the stream) ----
     __syncthreads();
     if (tid == 0) {
-        if (S.overflow && blockIdx.x == 0) {
-            *poison = 1u;
-            *host_flag = 1u;
-            cnt_out->overflow = 1u;
-        }
-        __threadfence_system();
+        __threadfence();  // this CTA's pixels are visible device-wide before it counts itself done
         if (atomicAdd(done_count, 1u) == gridDim.x - 1) {
             *done_count = 0u;
-            __threadfence_system();
+            if (S.overflow) {  // every CTA reaches the same verdict: the last one reports it
+                *poison = 1u;
+                cnt_out->overflow = 1u;
+                *reinterpret_cast<volatile uint32_t *>(host_flag) = 1u;
+                __threadfence_system();  // the flag reaches the host before the completion word
+            }
             *reinterpret_cast<volatile uint32_t *>(host_done) = A.seq;
         }
     }
+    FTL_STAMP(8);
+#undef FTL_STAMP
 }

@@ -164,6 +164,74 @@ struct Outline {
 
 }  // namespace
 
+// Stroke-side flattening on the host: the same op sequence as the device kernel flatten_ops<WIDE = true>
+// (front_kernels.cuh; plotter.rs:175-332 with WidePt, geom.rs:14-35) - IEEE f32 adds, multiplies and divisions by two,
+// never contracted (-ffp-contract=off here, -fmad=false there), so both produce the same bits.  A stroke of a few
+// thousand ops is flattened faster here than one device round trip takes.
+namespace {
+struct WFlat {
+    const float *e;
+    float tol_sq;
+    WideFlat *out;
+    uint32_t n;
+    void put(Wide q) {
+        out->xyw.push_back(q.p.x);
+        out->xyw.push_back(q.p.y);
+        out->xyw.push_back(q.w);
+        n++;
+    }
+    static Wide mid(Wide a, Wide b) { return {pointy::midpoint(a.p, b.p), (a.w + b.w) / 2.0f}; }  // WidePt::midpoint (geom.rs:31-35)
+    void quad(Wide a, Wide b, Wide c, int depth) {  // plotter.rs:248-265
+        Wide ab = mid(a, b), bc = mid(b, c), ab_bc = mid(ab, bc), ac = mid(a, c);
+        if (pointy::distance_sq(ab_bc.p, ac.p) <= tol_sq || depth >= 16) put(c);
+        else {
+            quad(a, ab, ab_bc, depth + 1);
+            quad(ab_bc, bc, c, depth + 1);
+        }
+    }
+    void cubic(Wide a, Wide b, Wide c, Wide d, int depth) {  // plotter.rs:311-332
+        Wide ab = mid(a, b), bc = mid(b, c), cd = mid(c, d), ab_bc = mid(ab, bc), bc_cd = mid(bc, cd), pe = mid(ab_bc, bc_cd), ad = mid(a, d);
+        if (pointy::distance_sq(pe.p, ad.p) <= tol_sq || depth >= 16) put(d);
+        else {
+            cubic(a, ab, ab_bc, pe, depth + 1);
+            cubic(pe, bc_cd, cd, d, depth + 1);
+        }
+    }
+};
+}  // namespace
+
+void flatten_wide_host(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, const float *opw, WideFlat *out) {
+    out->counts.assign(n_ops, 0);
+    out->xyw.clear();
+    WFlat f{e, tol_sq, out, 0};
+    Pt pen = {0.0f, 0.0f};  // Plotter::reset / close move the pen to the origin (plotter.rs:128-130,200-203)
+    for (size_t i = 0; i < n_ops; i++) {
+        const ftl_path_op &op = ops[i];
+        f.n = 0;
+        if (op.tag == FTL_OP_CLOSE) pen = {0.0f, 0.0f};
+        else if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+            const float w_pen = opw[2 * i], w_now = opw[2 * i + 1];
+            const Wide a = {pointy::transform(e, pen), w_pen};
+            if (op.tag == FTL_OP_MOVE || op.tag == FTL_OP_LINE) {
+                f.put({pointy::transform(e, {op.v[0], op.v[1]}), w_now});
+                pen = {op.v[0], op.v[1]};
+            } else if (op.tag == FTL_OP_QUAD) {
+                const Wide b = {pointy::transform(e, {op.v[0], op.v[1]}), (w_pen + w_now) / 2.0f};
+                const Wide c = {pointy::transform(e, {op.v[2], op.v[3]}), w_now};
+                f.quad(a, b, c, 0);
+                pen = {op.v[2], op.v[3]};
+            } else {  // float_lerp(a, b, t) = b + (a - b) * t (geom.rs:14-16)
+                const Wide b = {pointy::transform(e, {op.v[0], op.v[1]}), w_now + (w_pen - w_now) * (1.0f / 3.0f)};
+                const Wide c = {pointy::transform(e, {op.v[2], op.v[3]}), w_now + (w_pen - w_now) * (2.0f / 3.0f)};
+                const Wide d = {pointy::transform(e, {op.v[4], op.v[5]}), w_now};
+                f.cubic(a, b, c, d, 0);
+                pen = {op.v[4], op.v[5]};
+            }
+        }
+        out->counts[i] = f.n;
+    }
+}
+
 float stroke_widths(float s_width, const ftl_path_op *ops, size_t n_ops, std::vector<float> *opw) {
     opw->assign(2 * n_ops, 0.0f);
     float pen_w = s_width;  // Plotter::reset (plotter.rs:128-130)

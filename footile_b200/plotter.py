@@ -176,6 +176,12 @@ class Plotter:
                                               rules.ctypes.data if len(layers) else None, colors.ctypes.data if len(layers) else None))
         return self
 
+    def stream(self):
+        """The cudaStream_t (as int) every call on this plotter is issued on."""
+        st = C.c_void_p()
+        _lib.check(_lib.lib().ftl_stream(self._handle, C.byref(st)))
+        return st.value or 0
+
     def sync(self):
         _lib.check(_lib.lib().ftl_sync(self._handle))
         return self
@@ -302,6 +308,16 @@ class Batch:
 
     def upload(self, ops, offsets, rules=None, transforms=None, colors=None):
         _lib.check(_lib.lib().ftl_batch_upload(self._handle, *self._args(ops, offsets, rules, transforms, colors)))
+        return self
+
+    def set_join(self, js):
+        _lib.check(_lib.lib().ftl_batch_set_join(self._handle, js.kind, js.limit))
+        return self
+
+    def stroke(self, ops, offsets, transforms=None, colors=None):
+        """Stroke path j into raster j (every job like a new Plotter: pen width 1, this batch's join and tolerance)."""
+        n, po, pf, _, pt, pc = self._args(ops, offsets, None, transforms, colors)
+        _lib.check(_lib.lib().ftl_batch_stroke(self._handle, n, po, pf, pt, pc))
         return self
 
     def run(self):

@@ -143,6 +143,13 @@ int ftl_batch_set_tolerance(ftl_batch *b, float t);
 int ftl_batch_clear(ftl_batch *b, uint32_t first, uint32_t count);
 int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets,
                    const uint8_t *rules, const float *transforms, const uint8_t *colors);
+/* Plotter::set_join for every stroke of the batch (plotter.rs:158-161). */
+int ftl_batch_set_join(ftl_batch *b, int join, float miter_limit);
+/* n_jobs independent `Plotter::new(raster_j).set_transform(..).stroke(ops_j, color_j)` calls (plotter.rs:356-365) in one
+ * pass: the outlines are made on host threads (the stroker is sequential f32 arithmetic over libm: stroker.rs:204-416)
+ * and filled NonZero by one pass of the device pipeline.  Every job starts with pen width 1 like a new Plotter. */
+int ftl_batch_stroke(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const float *transforms,
+                     const uint8_t *colors);
 /* Copy rasters [first, first+count) to host (blocking). */
 int ftl_batch_read(ftl_batch *b, uint32_t first, uint32_t count, void *dst, size_t nbytes);
 /* 64-bit FNV-1a of each raster's bytes, computed on the device (blocking). */
@@ -171,6 +178,9 @@ int ftl_fill_replay(ftl_plotter *p);
 /* ---- Instrumentation ---------------------------------------------------- */
 /* Number of kernel launches issued by this library since load (all handles). */
 uint64_t ftl_launch_count(void);
+/* Bytes of path data and pixels this library has moved over PCIe since load / the last reset (all handles): what
+ * really crosses the wire - the packed read-back of ftl_read_raster / ftl_batch_read moves far less than the raster. */
+int ftl_transfer_bytes(int reset, uint64_t *h2d, uint64_t *d2h);
 /* Device time (ms) and launch count of the raster-tile kernel (scatter + row
  * scan + fill rule + store/blend) accumulated since the last call with
  * reset != 0.  Measured with CUDA events on the handle's stream when
@@ -196,6 +206,9 @@ int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]);
  * particular order: 6 int32 per edge = x_bot, inv_slope, step_pix, y_upper, y_lower (Fixed 16.16), sign (+1/-1).
  * Writes min(*n_edges, cap) records. */
 int ftl_debug_edges(ftl_plotter *p, int32_t *rec, size_t cap, size_t *n_edges);
+/* Development aid: with FTL_SMALL_PROF=1 in the environment, the SM clock (clock64) at the nine phase boundaries of the
+ * last one-launch small fill: start, flatten, vertices, top vertex, edges, staged, scatter, resolve, end. */
+int ftl_debug_small_profile(ftl_plotter *p, int64_t stamps[9]);
 /* The outline ops Plotter::stroke hands to fill (stroker.rs:239-247). */
 int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
                          size_t *n_out);

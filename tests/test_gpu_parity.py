@@ -873,3 +873,42 @@ def test_small_fill_overflow_falls_back_in_order():
         o.fill(oracle.NONZERO, ops, clr)
     assert_same(g, o)
     assert g.debug_last_fill() == o.last_info()
+
+
+# ---- strokes: host-side flatten == device flatten; batched strokes == one Plotter per stroke ------------------
+def test_stroke_flatten_host_equals_device_kernel():
+    import os
+    rng = np.random.default_rng(99)
+    for it in range(12):
+        path = random_path(rng, 300, int(rng.integers(2, 14)), closed_prob=0.5)
+        width = PathOp.PenWidth(float(rng.uniform(0.5, 12.0)))
+        ops = np.concatenate([np.array([width], dtype=OP_DTYPE), path, np.array([PathOp.PenWidth(3.0)], dtype=OP_DTYPE), path[: len(path) // 2]])
+        join = [JoinStyle.Miter(4.0), JoinStyle.Bevel, JoinStyle.Round][it % 3]
+        g, o = both(320, 320, Format.Matte8, join=join, tol=0.3 if it & 1 else 0.05)
+        host = g.debug_stroke_ops(ops)
+        os.environ["FTL_DEVICE_STROKE_FLATTEN"] = "1"
+        try:
+            dev = g.debug_stroke_ops(ops)
+        finally:
+            os.environ.pop("FTL_DEVICE_STROKE_FLATTEN", None)
+        ref = o.debug_stroke_ops(ops)
+        assert len(host) == len(dev) == len(ref) and host.tobytes() == dev.tobytes() == ref.tobytes(), it
+
+
+@pytest.mark.parametrize("join", [JoinStyle.Round, JoinStyle.Miter(4.0)])
+def test_batch_stroke_equals_one_plotter_per_stroke(join):
+    paths = list(scenes.stroke_scenes(2.0).values()) + [scenes.fishy_bench(), scenes.fishy_example()[0]]
+    n = len(paths)
+    ops, offs = Batch.pack(paths)
+    tr = np.tile(np.array([1, 0, 0, 0, 1, 0], dtype=np.float32), (n, 1))
+    tr[-2] = [1.5, 0, 3, 0, 1.5, 2]  # the double transform of Plotter::stroke shows with a non-identity transform
+    colors = np.tile(np.array([200, 120, 40, 255], dtype=np.uint8), (n, 1))
+    b = Batch(256, 256, Format.Rgba8p, n).set_join(join)
+    b.stroke(ops, offs, transforms=tr, colors=colors)
+    got = b.read()
+    for j, path in enumerate(paths):
+        o = oracle.Plotter(256, 256, oracle.RGBA8P)
+        o.set_join(join.kind, join.limit)
+        o.set_transform(tr[j])
+        o.stroke(path, (200, 120, 40, 255))
+        assert np.array_equal(got[j], o.raster()), j

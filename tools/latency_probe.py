@@ -27,3 +27,15 @@ for mode in ("small", "general"):
     out["%s_fishy_fill_128_rgba8p" % mode] = {"us_sync_each": g.time_fills(FillRule.NonZero, fish, (127, 96, 96, 255), iters=2000, sync_each=True),
                                               "us_back_to_back": g.time_fills(FillRule.NonZero, fish, (127, 96, 96, 255), iters=2000, sync_each=False)}
 print(json.dumps(out))
+if os.environ.get("FTL_SMALL_PROF") == "1":
+    import ctypes as C
+    import numpy as np
+    from footile_b200 import _lib
+    os.environ.pop("FTL_NO_SMALL", None)
+    for size in (16, 256):
+        g = Plotter(Raster(size, size, Format.Matte8)).set_transform([2, 0, 0, 0, 2, 0])
+        for _ in range(5):
+            g.fill(FillRule.NonZero, path, (255,)).sync()
+        st = np.zeros(9, dtype=np.int64)
+        _lib.check(_lib.lib().ftl_debug_small_profile(g._handle, st.ctypes.data))
+        print("phases(cycles) fill_%d" % size, list(np.diff(st)), "total", int(st[8] - st[0]), file=sys.stderr)
