@@ -201,20 +201,6 @@ def oracle_pixels(wl, sample):
     return px
 
 
-def product_pixels(wl, sample, device):
-    """The same count in our arm, from the product's own probe (ftl_debug_last_fill): the top row of a fill does not
-    depend on the raster size, so a tiny plotter answers it."""
-    import footile_b200 as fb
-    px = []
-    W, H = wl.get("w", wl["size"]), wl.get("h", wl["size"])
-    p = fb.Plotter(fb.Raster(8, 8, fb.Format.Matte8), device=device)
-    for j in sample:
-        p.set_transform(wl["tr"][j] if wl["tr"] is not None else [1, 0, 0, 0, 1, 0])
-        p.fill(int(wl["rules"][j]), wl["ops"][int(wl["offs"][j]): int(wl["offs"][j + 1])], (255,))
-        px.append(W * max(0, H - max(p.debug_last_fill()["top_row"], 0)))
-    return px
-
-
 def cpu_run(wl, jobs, threads):
     """Seconds the oracle needs for `jobs` (indices) on `threads` C++ threads (rasters pre-allocated, timed in C++)."""
     import oracle
@@ -466,8 +452,6 @@ def run_batch(D, args, name, batch, fmt, steps, warmup, full=True):
     b = Batch(W, H, Format.Graya8p if graya else (Format.Rgba8p if rgba else Format.Matte8), batch, device=D.local_rank)
     colors = np.tile(np.array(rmw_color, dtype=np.uint8), (batch, 1)) if rgba else None
     stream = torch.cuda.ExternalStream(b.stream(), device=D.local_rank)
-    px_fill = product_pixels(wl, range(batch) if name == "batch512" else range(min(batch, 2)), D.local_rank)
-    px_step = float(sum(px_fill)) if len(px_fill) == batch else float(px_fill[0]) * batch  # heptagram: every fill has the same top row
     raster_bytes = W * H * bpp
     if name == "strokes4k":  # config 3 draws over an opaque (64,128,64,255) raster (examples/stroke2.rs:20-21)
         rect = fb.Path2D().absolute().move_to(0, 0).line_to(W, 0).line_to(W, H).line_to(0, H).close().finish()
@@ -480,6 +464,9 @@ def run_batch(D, args, name, batch, fmt, steps, warmup, full=True):
     for _ in range(warmup):
         b.run()
     D.barrier(b)
+    # pixels per step by the reference's dense-row convention, from the product's own probe (top row of every job)
+    tops = b.top_rows(0, batch).astype(np.int64)
+    px_step = float(np.sum(np.where(tops == np.iinfo(np.int32).max, 0, W * np.maximum(0, H - np.maximum(tops, 0)))))
     sampler = ClockSampler(D.local_rank).start()
     fb.set_profiling(True)
     fb.tile_kernel_time(reset=True)

@@ -15,12 +15,13 @@ SYMBOLS = [
     "ftl_abi_version", "ftl_last_error", "ftl_device_count",
     "ftl_plotter_new", "ftl_plotter_new_band", "ftl_plotter_free", "ftl_width", "ftl_height",
     "ftl_set_tolerance", "ftl_set_transform", "ftl_set_join", "ftl_pen_width",
-    "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
+    "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_read_raster_srgb", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
     "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill", "ftl_batch_set_join", "ftl_batch_stroke",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
     "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream", "ftl_fill_upload", "ftl_fill_replay",
+    "ftl_ctx_new", "ftl_ctx_free", "ftl_ctx_size", "ftl_shard_range", "ftl_band_rows", "ftl_ctx_fill_batch", "ftl_ctx_fill_bands",
     "ftl_launch_count", "ftl_transfer_bytes", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_time_fills",
-    "ftl_debug_small_profile", "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
+    "ftl_debug_area", "ftl_debug_small_profile", "ftl_batch_debug_top_rows", "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
 ]
 
 
@@ -61,6 +62,7 @@ def lib():
         "ftl_fill_layers": (i32, [vp, u32, vp, vp, vp, vp]),
         "ftl_stroke_outline": (i32, [vp, vp, sz, vp, sz, vp]),
         "ftl_read_raster": (i32, [vp, vp, sz]),
+        "ftl_read_raster_srgb": (i32, [vp, vp, sz]),
         "ftl_write_raster": (i32, [vp, vp, sz]),
         "ftl_sync": (i32, [vp]),
         "ftl_raster_device_ptr": (i32, [vp, vp, vp]),
@@ -81,6 +83,13 @@ def lib():
         "ftl_fill_replay": (i32, [vp]),
         "ftl_batch_stream": (i32, [vp, vp]),
         "ftl_stream": (i32, [vp, vp]),
+        "ftl_ctx_new": (i32, [i32, vp, vp]),
+        "ftl_ctx_free": (i32, [vp]),
+        "ftl_ctx_size": (i32, [vp]),
+        "ftl_shard_range": (i32, [u32, u32, u32, vp, vp]),
+        "ftl_band_rows": (i32, [u32, u32, u32, u32, vp, vp]),
+        "ftl_ctx_fill_batch": (i32, [vp, u32, u32, i32, f32, u32, vp, vp, vp, vp, vp, vp, sz]),
+        "ftl_ctx_fill_bands": (i32, [vp, u32, u32, i32, i32, vp, sz, vp, f32, vp, vp, vp, sz]),
         "ftl_launch_count": (C.c_uint64, []),
         "ftl_transfer_bytes": (i32, [i32, vp, vp]),
         "ftl_set_profiling": (i32, [i32]),
@@ -88,7 +97,9 @@ def lib():
         "ftl_time_fills": (i32, [vp, i32, vp, sz, vp, u32, i32, vp]),
         "ftl_debug_flatten": (i32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
         "ftl_debug_last_fill": (i32, [vp, vp]),
+        "ftl_debug_area": (i32, [vp, i32, vp, sz]),
         "ftl_debug_small_profile": (i32, [vp, vp]),
+        "ftl_batch_debug_top_rows": (i32, [vp, u32, u32, vp]),
         "ftl_debug_edges": (i32, [vp, vp, sz, vp]),
         "ftl_debug_stroke_ops": (i32, [vp, vp, sz, vp, sz, vp]),
         "ftl_debug_stroke_outline": (i32, [i32, f32, f32, vp, sz, vp, vp, vp, sz, vp]),

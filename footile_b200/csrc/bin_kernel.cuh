@@ -312,10 +312,10 @@ __device__ __forceinline__ int32_t bin_resolve(uint32_t cells, uint32_t touched,
             v1 = slds4(a + 16u);
             ssts4_bias(a);
             ssts4_bias(a + 16u);
-            v0.x ^= BIN_BIAS; v0.y ^= BIN_BIAS; v0.z ^= BIN_BIAS; v0.w ^= BIN_BIAS;
-            v1.x ^= BIN_BIAS; v1.y ^= BIN_BIAS; v1.z ^= BIN_BIAS; v1.w ^= BIN_BIAS;
         }
-        // packed prefix inside each word: (lo, hi) -> (lo, lo + hi) mod 2^16
+        // packed prefix inside each word: (lo, hi) -> (lo, lo + hi) mod 2^16.  The resting bias 0x8000 of the low cell is not
+        // removed here: it rides into both halves of p_j (+0x8000 each) and into the running offsets (+0x8000 per word), and is
+        // taken out again for free in the constants added to the bases below (kBiasEven / kBiasOdd).
         const uint32_t p0 = (uint32_t)v0.x * 0x00010001u, p1 = (uint32_t)v0.y * 0x00010001u, p2 = (uint32_t)v0.z * 0x00010001u,
                        p3 = (uint32_t)v0.w * 0x00010001u, p4 = (uint32_t)v1.x * 0x00010001u, p5 = (uint32_t)v1.y * 0x00010001u,
                        p6 = (uint32_t)v1.z * 0x00010001u, p7 = (uint32_t)v1.w * 0x00010001u;
@@ -332,10 +332,13 @@ __device__ __forceinline__ int32_t bin_resolve(uint32_t cells, uint32_t touched,
                 if (lane == s + q) totals = tq;
             }
         }
-        const uint32_t a0 = packed_alpha<EVEN_ODD>(p0, p1, b, b + o1);
-        const uint32_t a1 = packed_alpha<EVEN_ODD>(p2, p3, b + o2, b + o3);
-        const uint32_t a2 = packed_alpha<EVEN_ODD>(p4, p5, b + o4, b + o5);
-        const uint32_t a3 = packed_alpha<EVEN_ODD>(p6, p7, b + o6, b + o7);
+        // word j carries (j + 1) * 0x8000 of bias in both halves (its own + j words before it): mod 2^16 that is 0x8000 for
+        // even j and 0 for odd j; tot carries 8 * 0x8000 = 0, so the scan and the row totals need no correction
+        constexpr int32_t kBiasEven = -0x8000, kBiasOdd = 0;
+        const uint32_t a0 = packed_alpha<EVEN_ODD>(p0, p1, b + kBiasEven, b + o1 + kBiasOdd);
+        const uint32_t a1 = packed_alpha<EVEN_ODD>(p2, p3, b + o2 + kBiasEven, b + o3 + kBiasOdd);
+        const uint32_t a2 = packed_alpha<EVEN_ODD>(p4, p5, b + o4 + kBiasEven, b + o5 + kBiasOdd);
+        const uint32_t a3 = packed_alpha<EVEN_ODD>(p6, p7, b + o6 + kBiasEven, b + o7 + kBiasOdd);
         if (ok) emit16<FMT, ALIGNED>(drow, 16 * l, w_rel, a0, a1, a2, a3, color, clr_a);
     }
     return totals;
@@ -487,5 +490,36 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
             __syncwarp();
             carry += tot;
         }
+    }
+}
+
+// Parity probe of stage (c) alone: the signed-area deltas one raster row receives from the edges of a job, before any
+// prefix sum (what Edge::scan_area adds into the i16 area buffer, fig.rs:285-302).  One thread per edge, the same
+// closed-form span as the scatter (bin_span), global atomics into an i32 row that the host truncates to the reference's i16.
+__global__ void __launch_bounds__(256) area_row_probe(const EdgeRec *__restrict__ E, uint32_t e_begin, uint32_t e_end, int32_t row, int32_t W,
+                                                      int32_t *__restrict__ area) {
+    const uint32_t k = e_begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= e_end) return;
+    const EdgeRec e = E[k];
+    if (!(e.flags & 1u) || row < e.ry0 || row > e.ry1) return;
+    const fx_t fr0 = (fx_t)(e.fr & 0xFFFFu), fr1 = (fx_t)(e.fr >> 16);
+    const int32_t step = e.step_pix > 0 ? e.step_pix : FX_ONE;
+    const fx_t x_bot = (fx_t)((uint32_t)e.x_bot0 + (uint32_t)(row - e.ry0) * (uint32_t)e.inv_slope);
+    const uint32_t misc = (uint32_t)pixel_cov(fr0) | ((uint32_t)pixel_cov(fr1) << 9);
+    int32_t c, xc, prev, cov;
+    bool resumed;
+    if (!bin_span<false, false>(x_bot, e.inv_slope, step, row == e.ry0, row == e.ry1, fx_mul(e.inv_slope, FX_ONE - fr0),
+                                fx_mul(e.inv_slope, (FX_ONE - fr1) & FX_MASK), misc, true, W, 0, W, c, xc, prev, cov, resumed))
+        return;
+    const int32_t ed = (e.flags & 2u) ? -1 : 1;
+    int32_t xr = xc + 128;
+    for (;;) {
+        int32_t xk = xr >> 8;
+        if (xk > cov) xk = cov;
+        atomicAdd(&area[c], ed * (xk - prev));
+        prev = xk;
+        c++;
+        xr = min(xr + step, FX_ONE + 128);
+        if (xk >= cov || c >= W) break;
     }
 }

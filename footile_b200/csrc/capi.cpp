@@ -271,6 +271,14 @@ int ftl_read_raster(ftl_plotter *p, void *dst, size_t nbytes) {
     return p->eng.copy_out(dst, p->raster, nbytes);
     GUARD_END
 }
+int ftl_read_raster_srgb(ftl_plotter *p, void *dst, size_t nbytes) {
+    GUARD_BEGIN
+    if (!p || (!dst && nbytes)) return bad("null argument");
+    if (nbytes != p->geo.bytes()) return bad("nbytes does not match rows*width*bpp");
+    if (!nbytes) return p->eng.sync();
+    return p->eng.copy_out_srgb(dst, p->raster, nbytes, p->geo.format);
+    GUARD_END
+}
 int ftl_write_raster(ftl_plotter *p, const void *src, size_t nbytes) {
     GUARD_BEGIN
     if (!p || (!src && nbytes)) return bad("null argument");
@@ -535,6 +543,13 @@ int ftl_time_fills(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_op
     GUARD_END
 }
 
+int ftl_batch_debug_top_rows(ftl_batch *b, uint32_t first, uint32_t count, int32_t *top_rows) {
+    GUARD_BEGIN
+    if (!b || (!top_rows && count)) return bad("null argument");
+    if (!count) return FTL_OK;
+    return b->eng.job_top_rows(first, count, top_rows);
+    GUARD_END
+}
 int ftl_debug_small_profile(ftl_plotter *p, int64_t stamps[9]) {
     GUARD_BEGIN
     if (!p || !stamps) return bad("null argument");
@@ -570,6 +585,17 @@ int ftl_debug_edges(ftl_plotter *p, int32_t *rec, size_t cap, size_t *n_edges) {
     if (rc) return rc;
     *n_edges = v.size() / 6;
     memcpy(rec, v.data(), std::min(v.size(), cap * 6) * sizeof(int32_t));
+    return FTL_OK;
+    GUARD_END
+}
+int ftl_debug_area(ftl_plotter *p, int32_t row, int16_t *area, size_t width) {
+    GUARD_BEGIN
+    if (!p || (!area && width)) return bad("null argument");
+    if (width != p->geo.width) return bad("width does not match the raster");
+    std::vector<int16_t> a;
+    int rc = p->eng.debug_area(row, (uint32_t)width, &a);
+    if (rc) return rc;
+    if (width) memcpy(area, a.data(), width * sizeof(int16_t));
     return FTL_OK;
     GUARD_END
 }

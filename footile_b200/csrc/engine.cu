@@ -30,6 +30,7 @@
 // Build flags: -fmad=false (Rust never fuses a*b+c), no fast-math.
 #include <cuda_runtime.h>
 #include <emmintrin.h>
+#include <math.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -152,6 +153,7 @@ struct Engine::Impl {
     uint32_t small_seq = 0;               // sequence number of the last small fill
     PinBuf small_flags;                   // SMALL_RING overflow flags + the completion word
     DevBuf small_poison;                  // [0] poison, [1] CTA completion counter
+    DevBuf srgb_tmp;                      // converted copy of a raster on its way to the host
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
     PinBuf pin_ring, pin_pack[2], pin_lit[2];
     DevBuf pack_fixed, pack_cnt, pack_lit;
@@ -226,7 +228,7 @@ Engine::~Engine() {
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
                               &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.cull_mark, &m.cull_head, &m.cull_part, &m.cull_lo,
-                              &m.cull_hi, &m.cull_job, &m.small_poison, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.cull_hi, &m.cull_job, &m.small_poison, &m.srgb_tmp, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
             for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1], &m.small_flags}) b->release();
@@ -970,6 +972,47 @@ int Engine::last_fill_info(FillInfo *info) {
     return FTL_OK;
 }
 
+int Engine::job_top_rows(uint32_t first, uint32_t count, int32_t *out) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (!m.have_jobs || (uint64_t)first + count > m.P.n_jobs) {
+        set_error("no resident job set covers that range");
+        return FTL_ERR_INVALID;
+    }
+    int rc = resolve_pending(m);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(m.st));
+    std::vector<JobState> js(count);
+    CK(cudaMemcpy(js.data(), (const JobState *)m.jstate.p + first, (size_t)count * sizeof(JobState), cudaMemcpyDeviceToHost));
+    for (uint32_t j = 0; j < count; j++) out[j] = js[j].top_vid == NONE32 ? INT32_MAX : js[j].top_row;  // INT32_MAX: the job drew nothing
+    return FTL_OK;
+}
+
+int Engine::debug_area(int32_t row, uint32_t width, std::vector<int16_t> *out) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    out->assign(width, 0);
+    if ((!m.have_jobs && !m.last_small) || width == 0) return FTL_OK;
+    int rc = resolve_pending(m);
+    if (rc) return rc;
+    JobState js;
+    CK(cudaStreamSynchronize(m.st));
+    CK(cudaMemcpy(&js, m.jstate.p, sizeof(js), cudaMemcpyDeviceToHost));
+    const uint32_t n = js.vtx_end - js.vtx_begin;
+    if (n == 0 || js.top_vid == NONE32) return FTL_OK;
+    if ((rc = m.misc.ensure((size_t)width * sizeof(int32_t), m.st))) return rc;
+    m.small_tail = false;
+    CK(cudaMemsetAsync(m.misc.p, 0, (size_t)width * sizeof(int32_t), m.st));
+    // `row` is a raster row, like the rows of the edge records (geometry row - shift)
+    area_row_probe<<<div_up(n, 256), 256, 0, m.st>>>((const EdgeRec *)m.edges.p, js.vtx_begin, js.vtx_end, row, (int32_t)width, (int32_t *)m.misc.p); LAUNCHED();
+    CK(cudaGetLastError());
+    std::vector<int32_t> a(width);
+    CK(cudaMemcpyAsync(a.data(), m.misc.p, (size_t)width * sizeof(int32_t), cudaMemcpyDeviceToHost, m.st));
+    CK(cudaStreamSynchronize(m.st));
+    for (uint32_t i = 0; i < width; i++) (*out)[i] = (int16_t)a[i];  // the reference's cells are wrapping i16 (plotter.rs:45)
+    return FTL_OK;
+}
+
 int Engine::debug_edges(std::vector<int32_t> *out) {
     ENSURE_INIT();
     Impl &m = *impl_;
@@ -1137,6 +1180,49 @@ int Engine::checksums(const void *rasters, size_t raster_bytes, uint32_t count, 
     CK(cudaMemcpyAsync(out, m.misc.p, (size_t)count * 8, cudaMemcpyDeviceToHost, m.st));
     CK(cudaStreamSynchronize(m.st));
     return FTL_OK;
+}
+
+// Linear -> sRGB encode table of an 8-bit channel: round(255 * srgb(i / 255)) (pix builds the same table at compile time).
+static void srgb_table(uint8_t t[256]) {
+    for (int i = 0; i < 256; i++) {
+        const double u = i / 255.0;
+        const double e = u <= 0.0031308 ? 12.92 * u : 1.055 * pow(u, 1.0 / 2.4) - 0.055;
+        t[i] = (uint8_t)std::min(255.0, std::max(0.0, floor(e * 255.0 + 0.5)));
+    }
+}
+void Engine::srgb_encode_table(uint8_t t[256]) { srgb_table(t); }
+
+// The owned rows converted for output (examples/fishy.rs:33): Rgba8p -> SRgba8, Graya8p -> SGraya8, Matte8 -> SGray8.
+int Engine::copy_out_srgb(void *dst, const void *dptr, size_t bytes, int format) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    if (format == FTL_MATTE8) return copy_out(dst, dptr, bytes);  // a reinterpretation, byte for byte (png/mod.rs:22-27)
+    int rc = resolve_pending(m);
+    if (rc) return rc;
+    if ((bytes & 15u) != 0 || ((uintptr_t)dptr & 15u) != 0) {
+        set_error("sRGB read-back needs a raster whose size is a multiple of 16 bytes");
+        return FTL_ERR_INVALID;
+    }
+    static std::mutex mu;
+    static bool table_ready[64] = {};
+    {
+        std::lock_guard<std::mutex> lock(mu);
+        if (!table_ready[device_]) {
+            uint8_t t[256];
+            srgb_table(t);
+            CK(cudaMemcpyToSymbol(c_srgb_encode, t, 256));
+            table_ready[device_] = true;
+        }
+    }
+    if ((rc = m.srgb_tmp.ensure(bytes, m.st))) return rc;
+    m.small_tail = false;
+    const size_t n_words = bytes / 16;
+    const uint32_t grid = div_up(n_words, 256);
+    if (format == FTL_RGBA8P) srgb_convert<FTL_RGBA8P><<<grid, 256, 0, m.st>>>((const uint4 *)dptr, (uint4 *)m.srgb_tmp.p, n_words);
+    else srgb_convert<FTL_GRAYA8P><<<grid, 256, 0, m.st>>>((const uint4 *)dptr, (uint4 *)m.srgb_tmp.p, n_words);
+    LAUNCHED();
+    CK(cudaGetLastError());
+    return copy_out(dst, m.srgb_tmp.p, bytes);
 }
 
 int Engine::sync() {

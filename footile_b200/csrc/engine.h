@@ -74,9 +74,13 @@ public:
     int debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops,
                       std::vector<int32_t> *xy, std::vector<uint32_t> *subs);
     int last_fill_info(FillInfo *info);
+    // top_row (fig.rs:496) of jobs [first, first + count) of the resident job set after its last run; INT32_MAX for an empty job.
+    int job_top_rows(uint32_t first, uint32_t count, int32_t *out);
     // Probe: the edge records stage (b) built for job 0 of the last fill, 6 values per edge:
     // x_bot, inv_slope, step_pix, y_upper, y_lower (Fixed), sign (+1 / -1) (fig.rs:47-66,179-210,286).
     int debug_edges(std::vector<int32_t> *out);
+    // Probe: the i16 signed-area deltas geometry row `row` receives from the edges of job 0 of the last fill (stage (c) alone).
+    int debug_area(int32_t row, uint32_t width, std::vector<int16_t> *out);
     int accumulate_rows(int rule, const int16_t *src, uint8_t *dst, size_t n, size_t rows);
     int checksums(const void *rasters, size_t raster_bytes, uint32_t count, uint64_t *out);
 
@@ -87,6 +91,8 @@ public:
     int memset_async(void *dptr, int value, size_t bytes);
     int copy_in(void *dptr, const void *src, size_t bytes);   // blocking
     int copy_out(void *dst, const void *dptr, size_t bytes);  // blocking
+    int copy_out_srgb(void *dst, const void *dptr, size_t bytes, int format);  // blocking; converted for output (pack_kernels.cuh)
+    static void srgb_encode_table(uint8_t t[256]);
 
     static int device_count(int *count);
     static uint64_t launch_count();

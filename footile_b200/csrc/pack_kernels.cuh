@@ -53,3 +53,39 @@ __global__ void __launch_bounds__(256) fnv_rasters(const uint8_t *__restrict__ b
         out[blockIdx.x] = g;
     }
 }
+
+// ---------------------------------------------------------------------------
+// Output conversion (examples/fishy.rs:33, examples/png/mod.rs:22-27): the raster the reference hands to its PNG
+// encoder is Raster::<SRgba8>::with_raster(&p.raster()) - every Rgba8p pixel (linear, premultiplied) becomes SRgba8
+// (sRGB gamma, straight alpha): colour / alpha in Ch8, then the sRGB transfer function; alpha is copied.  Graya8p ->
+// SGraya8 likewise; a Matte8 raster is reinterpreted as SGray8 byte for byte (png/mod.rs:22-27: no arithmetic).
+// pix_compat.cuh isolates the RECALLED pix arithmetic (Ch8 division = min((c << 8) / a, 255), 0 for a = 0; the encode
+// table is round(255 * srgb(i / 255))).  One 16-byte word per thread: a pure streaming pass.
+// ---------------------------------------------------------------------------
+__constant__ uint8_t c_srgb_encode[256];
+template <int FMT>
+__global__ void __launch_bounds__(256) srgb_convert(const uint4 *__restrict__ src, uint4 *__restrict__ dst, size_t n_words) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_words) return;
+    const uint4 v = src[i];
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        if (FMT == FTL_RGBA8P) {
+            const uint32_t a = w[k] >> 24;
+            uint32_t o = a << 24;
+#pragma unroll
+            for (int ch = 0; ch < 3; ch++) o |= (uint32_t)c_srgb_encode[pix::ch8_div((w[k] >> (8 * ch)) & 0xFFu, a)] << (8 * ch);
+            w[k] = o;
+        } else {  // two (gray, alpha) pixels per word
+            uint32_t o = 0;
+#pragma unroll
+            for (int e = 0; e < 2; e++) {
+                const uint32_t px = (w[k] >> (16 * e)) & 0xFFFFu, a = px >> 8;
+                o |= ((uint32_t)c_srgb_encode[pix::ch8_div(px & 0xFFu, a)] | (a << 8)) << (16 * e);
+            }
+            w[k] = o;
+        }
+    }
+    dst[i] = make_uint4(w[0], w[1], w[2], w[3]);
+}

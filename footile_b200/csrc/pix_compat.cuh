@@ -20,6 +20,12 @@ FTL_HD uint32_t ch8_add(uint32_t a, uint32_t b) {
     uint32_t s = a + b;
     return s > 255u ? 255u : s;
 }
+// Ch8 / Ch8 (the Premultiplied -> Straight alpha decode of a conversion): (c << 8) / a, at most 255; 0 for a = 0.
+FTL_HD uint32_t ch8_div(uint32_t c, uint32_t a) {
+    if (a == 0u) return 0u;
+    const uint32_t q = (c << 8) / a;
+    return q > 255u ? 255u : q;
+}
 // One channel of dst.composite_channels_alpha(&src, SrcOver, &alpha):
 //   d' = (s * alpha) + d * (255 - alpha * src_alpha)
 FTL_HD uint32_t src_over_ch(uint32_t d, uint32_t s, uint32_t alpha, uint32_t sa1) {

@@ -608,7 +608,7 @@ __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefe
 template <int FMT, bool ALIGNED>
 __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict__ E, const JobDesc *__restrict__ jobs,
                                                        const JobState *__restrict__ JS, Params P, const Counters *__restrict__ C) {
-    if (C->overflow) return;
+    if (C->overflow || C->n_big == P.n_jobs) return;  // every job goes to raster_bins: nothing to scan for
     extern __shared__ __align__(16) int32_t smem[];
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5, warps_per_cta = blockDim.x >> 5;
     const uint32_t cells = smem_addr(smem) + 4u * warp * P.warp_words, mask = cells + 4u * P.win_rows * P.win_chunks * CHUNK;

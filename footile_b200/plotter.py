@@ -196,6 +196,13 @@ class Plotter:
     def into_raster(self):
         return self.raster()
 
+    def raster_srgb(self):
+        """The owned rows converted for output on the device (examples/fishy.rs:33: SRgba8 / SGraya8 / SGray8 bytes)."""
+        n_rows = self._rows[1] - self._rows[0]
+        out = np.empty((n_rows, self._w * self._bpp), dtype=np.uint8)
+        _lib.check(_lib.lib().ftl_read_raster_srgb(self._handle, out.ctypes.data if out.size else None, out.size))
+        return out
+
     def write_raster(self, pixels):
         a = np.ascontiguousarray(np.asarray(pixels, dtype=np.uint8)).ravel()
         _lib.check(_lib.lib().ftl_write_raster(self._handle, a.ctypes.data if a.size else None, a.size))
@@ -223,6 +230,12 @@ class Plotter:
         info = np.zeros(3, dtype=np.int32)
         _lib.check(_lib.lib().ftl_debug_last_fill(self._handle, info.ctypes.data))
         return {"dir": int(info[0]), "top_row": int(info[1]), "n_points": int(info[2])}
+
+    def debug_area(self, row):
+        """int16[width]: the signed-area deltas of raster row `row` of the last fill before the prefix sum (stage (c) probe)."""
+        out = np.zeros(self._w, dtype=np.int16)
+        _lib.check(_lib.lib().ftl_debug_area(self._handle, int(row), out.ctypes.data, self._w))
+        return out
 
     def debug_edges(self):
         """(n, 6) int32 edges of the last fill: x_bot, inv_slope, step_pix, y_upper, y_lower, sign (stage (b) probe)."""
@@ -340,6 +353,13 @@ class Batch:
         count = self.capacity - first if count is None else count
         out = np.zeros(count, dtype=np.uint64)
         _lib.check(_lib.lib().ftl_batch_checksums(self._handle, first, count, out.ctypes.data))
+        return out
+
+    def top_rows(self, first=0, count=None):
+        """top_row of each job of the last fill / run (int32; INT32_MAX for a job that drew nothing)."""
+        count = self.capacity - first if count is None else count
+        out = np.zeros(count, dtype=np.int32)
+        _lib.check(_lib.lib().ftl_batch_debug_top_rows(self._handle, first, count, out.ctypes.data))
         return out
 
     def device_ptr(self):

@@ -121,6 +121,11 @@ int ftl_stroke_outline(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl
 /* Plotter::raster() / into_raster() (plotter.rs:368-380): synchronise and copy
  * the owned rows to host memory.  nbytes must equal rows*width*bpp. */
 int ftl_read_raster(ftl_plotter *p, void *dst, size_t nbytes);
+/* The owned rows converted for output, as the reference's examples do before encoding a PNG:
+ * Raster::<SRgba8>::with_raster(&p.raster()) (examples/fishy.rs:33) for FTL_RGBA8P - colour / alpha, then the sRGB
+ * transfer function, alpha copied -, SGraya8 likewise for FTL_GRAYA8P, and the byte-for-byte SGray8 view of a
+ * FTL_MATTE8 raster (examples/png/mod.rs:22-27).  The conversion runs on the device; same size as ftl_read_raster. */
+int ftl_read_raster_srgb(ftl_plotter *p, void *dst, size_t nbytes);
 /* Plotter::raster_mut() (plotter.rs:373-375): replace the owned rows. */
 int ftl_write_raster(ftl_plotter *p, const void *src, size_t nbytes);
 int ftl_sync(ftl_plotter *p);
@@ -161,6 +166,28 @@ int ftl_batch_device_ptr(ftl_batch *b, void **dptr, size_t *nbytes);
 int ftl_batch_stream(ftl_batch *b, void **stream);
 int ftl_stream(ftl_plotter *p, void **stream);
 
+/* ---- Several GPUs behind one handle (one host thread per device, no data-path collective) ---------------- */
+/* The two ways the path shards (BASELINE north_star): independent paths / rasters in contiguous blocks of jobs over the
+ * devices, and ONE raster split into row bands with every device culling the sub-figures outside its band.  One process
+ * per GPU (how bench.py runs) needs only ftl_shard_range / ftl_band_rows and the per-device entry points above. */
+typedef struct ftl_ctx ftl_ctx;
+/* devices: n_devices CUDA device indices (NULL: 0..n_devices-1; n_devices <= 0: every device).  An index may repeat. */
+int ftl_ctx_new(int n_devices, const int *devices, ftl_ctx **out);
+int ftl_ctx_free(ftl_ctx *c);
+int ftl_ctx_size(const ftl_ctx *c);
+/* Contiguous block of range(n) owned by `rank` of `world`. */
+int ftl_shard_range(uint32_t n, uint32_t rank, uint32_t world, uint32_t *first, uint32_t *count);
+/* Row band [row_begin, row_end) of `rank`; band boundaries are multiples of `align` rows (0: 32, the binned kernel's band). */
+int ftl_band_rows(uint32_t height, uint32_t rank, uint32_t world, uint32_t align, uint32_t *row_begin, uint32_t *row_end);
+/* n_jobs independent fills (the arguments of ftl_batch_fill) sharded over the devices; every raster (cleared first) comes
+ * back in dst, job after job.  tolerance <= 0: the default 0.3. */
+int ftl_ctx_fill_batch(ftl_ctx *c, uint32_t width, uint32_t height, int format, float tolerance, uint32_t n_jobs, const ftl_path_op *ops,
+                       const uint64_t *op_offsets, const uint8_t *rules, const float *transforms, const uint8_t *colors, void *dst, size_t nbytes);
+/* One fill of one width x height raster, rows split into one band per device; init_pixels (NULL: clear) / dst cover the
+ * whole raster.  Equal, byte for byte, to the unsplit Plotter::fill (fig.rs:497,539 only loops rows). */
+int ftl_ctx_fill_bands(ftl_ctx *c, uint32_t width, uint32_t height, int format, int rule, const ftl_path_op *ops, size_t n_ops, const float transform[6],
+                       float tolerance, const uint8_t *color, const void *init_pixels, void *dst, size_t nbytes);
+
 /* ---- Device-resident replay (bench `value` leg: inputs already in HBM) ---- */
 /* Upload the jobs of a batch once; ftl_batch_run() then repeats the device
  * pipeline on the resident ops without touching host memory. */
@@ -200,12 +227,19 @@ int ftl_time_fills(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_op
  * receives up to sub_cap (start,len) pairs.  Blocking. */
 int ftl_debug_flatten(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, int32_t *xy, size_t cap,
                       size_t *n_points, uint32_t *subs, size_t sub_cap, size_t *n_subs);
+/* Stage (c) probe: the signed-area deltas row `row` of the last ftl_fill receives from its edges BEFORE the prefix sum -
+ * the contents of the reference's i16 area buffer when Fig::fill reaches accumulate for that row (fig.rs:285-302,
+ * 536-573; plotter.rs:45).  `row` counts as the reference's scan loop does (row 0 = top_row when top_row < 0). */
+int ftl_debug_area(ftl_plotter *p, int32_t row, int16_t *area, size_t width);
 /* (dir, top_row, n_points) of the last fill (fig.rs:495-496); dir 0 = Forward. */
 int ftl_debug_last_fill(ftl_plotter *p, int32_t info[3]);
 /* Stage (b) probe: the edges of the last ftl_fill (Edge::new, fig.rs:179-210, with the winding sign of fig.rs:286), in no
  * particular order: 6 int32 per edge = x_bot, inv_slope, step_pix, y_upper, y_lower (Fixed 16.16), sign (+1/-1).
  * Writes min(*n_edges, cap) records. */
 int ftl_debug_edges(ftl_plotter *p, int32_t *rec, size_t cap, size_t *n_edges);
+/* top_row (fig.rs:496) of jobs [first, first + count) of the batch's last fill / run: the first row the reference would
+ * resolve is max(top_row, 0).  INT32_MAX for a job that drew nothing. */
+int ftl_batch_debug_top_rows(ftl_batch *b, uint32_t first, uint32_t count, int32_t *top_rows);
 /* Development aid: with FTL_SMALL_PROF=1 in the environment, the SM clock (clock64) at the nine phase boundaries of the
  * last one-launch small fill: start, flatten, vertices, top vertex, edges, staged, scatter, resolve, end. */
 int ftl_debug_small_profile(ftl_plotter *p, int64_t stamps[9]);

@@ -62,6 +62,8 @@ def lib():
         L.orc_has_ssse3.restype = C.c_int
         L.orc_src_over.restype = None
         L.orc_src_over.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_uint8]
+        L.orc_convert_srgb.restype = None
+        L.orc_convert_srgb.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
         L.orc_fig_fill.restype = C.c_int
         L.orc_fig_fill.argtypes = [C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_uint32,
                                    C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_void_p, C.c_void_p]
@@ -316,3 +318,11 @@ class Plotter:
             if k <= cap:
                 return out[:k].copy()
             cap = k
+
+
+def convert_srgb(fmt, pixels):
+    """Output conversion of examples/fishy.rs:33 on the CPU: Rgba8p -> SRgba8 / Graya8p -> SGraya8 / Matte8 -> SGray8 bytes."""
+    a = np.ascontiguousarray(np.asarray(pixels, dtype=np.uint8))
+    out = np.empty_like(a)
+    lib().orc_convert_srgb(int(fmt), a.ctypes.data, out.ctypes.data, a.size // BPP[fmt])
+    return out

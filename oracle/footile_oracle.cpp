@@ -743,6 +743,35 @@ int orc_has_ssse3(void) {
     return 0;
 #endif
 }
+// Output conversion of examples/fishy.rs:33 (Raster::<SRgba8>::with_raster) and its Graya8p analogue: Premultiplied ->
+// Straight (Ch8 division, RECALLED: min((c << 8) / a, 255), 0 for a = 0), then the sRGB transfer function through the
+// 256-entry table round(255 * srgb(i / 255)); alpha copied.  fmt: 1 Graya8p -> SGraya8, 2 Rgba8p -> SRgba8, 0 Matte8 -> SGray8 (bytes kept).
+void orc_convert_srgb(int fmt, const uint8_t *src, uint8_t *dst, size_t n_pixels) {
+    uint8_t enc[256];
+    for (int i = 0; i < 256; i++) {
+        const double u = i / 255.0;
+        const double e = u <= 0.0031308 ? 12.92 * u : 1.055 * pow(u, 1.0 / 2.4) - 0.055;
+        const double r = floor(e * 255.0 + 0.5);
+        enc[i] = (uint8_t)(r < 0 ? 0 : (r > 255 ? 255 : r));
+    }
+    auto div8 = [](uint32_t c, uint32_t a) -> uint32_t {
+        if (a == 0) return 0;
+        uint32_t q = (c << 8) / a;
+        return q > 255 ? 255 : q;
+    };
+    const int bpp = fmt == 0 ? 1 : (fmt == 1 ? 2 : 4);
+    for (size_t i = 0; i < n_pixels; i++) {
+        const uint8_t *s = src + i * bpp;
+        uint8_t *d = dst + i * bpp;
+        if (fmt == 0) d[0] = s[0];
+        else {
+            const uint32_t a = s[bpp - 1];
+            for (int ch = 0; ch < bpp - 1; ch++) d[ch] = enc[div8(s[ch], a)];
+            d[bpp - 1] = (uint8_t)a;
+        }
+    }
+}
+
 // pix_compat hook
 void orc_src_over(uint8_t *dst, const uint8_t *src, int n, uint8_t alpha) { pix_compat::src_over_alpha(dst, src, n, alpha); }
 

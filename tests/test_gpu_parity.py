@@ -912,3 +912,87 @@ def test_batch_stroke_equals_one_plotter_per_stroke(join):
         o.set_transform(tr[j])
         o.stroke(path, (200, 120, 40, 255))
         assert np.array_equal(got[j], o.raster()), j
+
+
+# ---- output conversion (examples/fishy.rs:33, examples/png/mod.rs:22-27) on the device ----------------------
+@pytest.mark.parametrize("fmt", [Format.Rgba8p, Format.Graya8p, Format.Matte8])
+def test_read_raster_srgb_matches_oracle_conversion(fmt):
+    rng = np.random.default_rng(17)
+    w, h = 256, 96
+    bpp = {Format.Matte8: 1, Format.Graya8p: 2, Format.Rgba8p: 4}[fmt]
+    px = rng.integers(0, 256, (h, w, bpp), dtype=np.uint8)
+    if bpp > 1:  # premultiplied: colour <= alpha; include alpha 0 and 255 rows
+        px[0, :, -1] = 0
+        px[1, :, -1] = 255
+        px[..., :-1] = np.minimum(px[..., :-1], px[..., -1:])
+    init = px.reshape(h, w * bpp)
+    g = Plotter(Raster(w, h, fmt, init))
+    fish, eye = scenes.fishy_example()
+    if fmt != Format.Matte8:
+        g.fill(FillRule.NonZero, fish, (127, 96, 96, 255)[:bpp] if bpp == 4 else (127, 255))
+    got = g.raster_srgb()
+    exp = oracle.convert_srgb(FMT[fmt], g.raster().pixels)
+    assert np.array_equal(got, exp)
+    if fmt == Format.Matte8:
+        assert np.array_equal(got, init)  # SGray8 view: the bytes themselves
+
+
+def test_fishy_example_srgb_output_semantics():
+    """examples/fishy.rs:29-33 end to end on the device; the conversion keeps alpha, leaves clear pixels clear and makes opaque
+    mid-gray brighter (sRGB encode of linear 127/255 is 187)."""
+    fish, eye = scenes.fishy_example()
+    g = Plotter(Raster(128, 128, Format.Rgba8p))
+    g.fill(FillRule.NonZero, fish, (127, 96, 96, 255))
+    g.stroke(fish, (255, 208, 208, 255))
+    g.stroke(eye, (0, 0, 0, 255))
+    lin = g.raster().pixels.reshape(128, 128, 4)
+    srgb = g.raster_srgb().reshape(128, 128, 4)
+    assert np.array_equal(lin[..., 3], srgb[..., 3])
+    assert not srgb[lin[..., 3] == 0].any()
+    body = (lin[..., 3] == 255) & (lin[..., 0] == 127)
+    assert body.any() and (srgb[body][:, 0] == 187).all()
+
+
+# ---- stage (c) alone: the i16 area rows before the prefix sum -------------------------------------------------
+def test_debug_area_rows_match_the_reference_area_buffer():
+    """ftl_debug_area against the area buffer of the oracle's sequential scan (the reference's own loop, fig.rs:536-573),
+    including a figure that starts above the raster (rows shift: SURVEY A.6-3) and spans that leave it on both sides."""
+    rng = np.random.default_rng(31)
+    for it in range(8):
+        w, h = int(rng.integers(20, 200)), int(rng.integers(20, 120))
+        n = int(rng.integers(3, 40))
+        pts = [(float(rng.uniform(-30, w + 30)), float(rng.uniform(-25 if it & 1 else 2, h + 10))) for _ in range(n)]
+        for general in (False, True):
+            _general_path(general)
+            try:
+                g = Plotter(Raster(w, h, Format.Matte8))
+                g.fill(FillRule.NonZero, poly(pts), (255,))
+                _, info, area = oracle.fig_fill(w, h, oracle.MATTE8, 0, [pts], want_area=True)
+                assert g.debug_last_fill()["top_row"] == info["top_row"]
+                first = max(info["top_row"], 0)
+                for row in sorted(set([first, min(first + 1, h - 1), h // 2, h - 1])):
+                    if row < first:
+                        continue
+                    assert np.array_equal(g.debug_area(row), area[row]), (it, general, row)
+            finally:
+                _general_path(False)
+
+
+# ---- several shards behind one C handle (ftl_ctx_*): a device index may repeat, so one GPU exercises the logic ------
+def test_ctx_fill_batch_and_bands_equal_single_device_results():
+    from footile_b200.sharding import Context
+    ctx = Context([0, 0, 0])  # three shards on device 0
+    assert ctx.size() == 3
+    ops, offs, rules = scenes.random_curve_paths(500, 7, segments=12, size=160)
+    got = ctx.fill_batch(160, 160, Format.Matte8, ops, offs, rules=rules)
+    for j in range(7):
+        o = oracle.Plotter(160, 160, oracle.MATTE8)
+        o.fill(int(rules[j]), ops[int(offs[j]): int(offs[j + 1])], (255,))
+        assert np.array_equal(got[j], o.raster()), j
+    size = 700  # bands of 32-row multiples: 256 + 224 + 220 rows
+    big = scenes.random_polygons(3, 90, vertices=24, size=size, extent=200)
+    base = np.full((size, size * 4), 60, dtype=np.uint8)
+    whole = ctx.fill_bands(size, size, Format.Rgba8p, FillRule.EvenOdd, big, (10, 200, 30, 180), init=base)
+    o = oracle.Plotter(size, size, oracle.RGBA8P, init=base, vid_cap=1 << 30, orderfree=True)
+    o.fill(oracle.EVENODD, big, (10, 200, 30, 180))
+    assert np.array_equal(whole, o.raster())
