@@ -79,5 +79,6 @@ struct Params {  // per-call constants, passed by value
     uint32_t b_nbands, b_nwin, b_wc, n_bins;     // bins = n_jobs * b_nbands * b_nwin
     uint32_t b_lookback;                         // 1: one (band, window) tile per ticket, row sums passed through `look`; 0: a ticket walks all windows of a band
     uint32_t job_begin, job_end;                 // jobs this launch of the binned kernel covers
+    uint32_t has_curves;                         // the job set holds Quad / Cubic ops (flatten parks their points between its two passes)
     uint32_t cull;                               // 1: flatten only the sub-figures that can reach rows [row_begin, row_end) or hold the top vertex
 };

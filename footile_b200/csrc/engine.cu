@@ -138,6 +138,7 @@ struct Engine::Impl {
     size_t max_smem = 0;
     DevBuf ops, jobs, jstate, cnt, off, partials, vtx, edges, sub_last, tcount, toff, tpart, entries, counters, opw, wide, misc, tickets, look;
     DevBuf cull_mark, cull_head, cull_part, cull_lo, cull_hi, cull_job;  // row-band culling (front_kernels.cuh)
+    DevBuf slabs;                         // points of curve ops parked by the counting pass of flatten_ops
     uint32_t look_epoch = 0;              // launch epoch of the look-back words (0: the buffer must be cleared first)
     std::vector<uint8_t> host_direct;    // per job: provably at most DIRECT_MAX edge slots (line-only, few ops)
     // small fills (small_kernel.cuh): one launch each, issued without waiting; a fill that did not fit raises its flag
@@ -228,7 +229,7 @@ Engine::~Engine() {
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
                               &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.cull_mark, &m.cull_head, &m.cull_part, &m.cull_lo,
-                              &m.cull_hi, &m.cull_job, &m.small_poison, &m.srgb_tmp, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.cull_hi, &m.cull_job, &m.slabs, &m.small_poison, &m.srgb_tmp, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
                 b->release();
             m.drop_graph();
             for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1], &m.small_flags}) b->release();
@@ -416,17 +417,20 @@ static int validate_ops(const ftl_path_op *ops, size_t n) {
 
 // Validate ops[0, n) and copy them into the pinned staging buffer in one pass over the caller's memory; large
 // arrays (config 5 sends 291 MB per fill) are split over host threads.  Returns the first failure in op order.
-static int stage_ops(ftl_path_op *dst, const ftl_path_op *ops, size_t n) {
-    auto one = [](ftl_path_op *d, const ftl_path_op *o, size_t cnt, int *status) {
+static int stage_ops(ftl_path_op *dst, const ftl_path_op *ops, size_t n, std::atomic<bool> *has_curves) {
+    auto one = [has_curves](ftl_path_op *d, const ftl_path_op *o, size_t cnt, int *status) {
         int st = FTL_OK;
+        bool curves = false;
         for (size_t i = 0; i < cnt && st == FTL_OK; i++) {
             const ftl_path_op op = o[i];
             if (op.tag > FTL_OP_PENWIDTH) st = FTL_ERR_INVALID;
+            curves |= op.tag == FTL_OP_QUAD || op.tag == FTL_OP_CUBIC;
             const int nv = op.tag == FTL_OP_CLOSE ? 0 : (op.tag == FTL_OP_QUAD ? 4 : (op.tag == FTL_OP_CUBIC ? 6 : (op.tag == FTL_OP_PENWIDTH ? 1 : 2)));
             for (int k = 0; k < nv; k++)
                 if (!(op.v[k] - op.v[k] == 0.0f) && st == FTL_OK) st = FTL_ERR_NONFINITE;
             d[i] = op;
         }
+        if (curves) has_curves->store(true, std::memory_order_relaxed);
         *status = st;
     };
     unsigned nt = n < (1u << 16) ? 1u : std::min(8u, std::max(1u, std::thread::hardware_concurrency()));
@@ -477,6 +481,7 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
     P.all_direct = 1;
     P.all_tiny = 1;
+    P.has_curves = 0;
     m.host_direct.assign(jobs.size(), 1);
     for (size_t jx = 0; jx < jobs.size(); jx++) {
         const HostJob &h = jobs[jx];
@@ -519,15 +524,17 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     // validate + stage + copy in pieces: the DMA of one piece runs while the host threads stage the next
     {
         const size_t PIECE = 1u << 20;  // ops per piece (28 MB)
+        std::atomic<bool> curves{false};
         for (size_t at = 0; at < n_ops; at += PIECE) {
             const size_t cnt = std::min(PIECE, n_ops - at);
-            if ((rc = stage_ops((ftl_path_op *)m.pin_ops.p + at, ops + at, cnt))) {
+            if ((rc = stage_ops((ftl_path_op *)m.pin_ops.p + at, ops + at, cnt, &curves))) {
                 cudaStreamSynchronize(m.st);
                 return rc;
             }
             CK(cudaMemcpyAsync((ftl_path_op *)m.ops.p + at, (const ftl_path_op *)m.pin_ops.p + at, cnt * sizeof(ftl_path_op), cudaMemcpyHostToDevice, m.st));
             g_h2d_bytes.fetch_add(cnt * sizeof(ftl_path_op), std::memory_order_relaxed);
         }
+        P.has_curves = curves.load() ? 1u : 0u;
     }
     JobDesc *jd = (JobDesc *)m.pin_jobs.p;
     for (size_t j = 0; j < jobs.size(); j++) {
@@ -693,6 +700,16 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
         if ((rc = m.cull_job.ensure((size_t)P.n_jobs * 2 * sizeof(int32_t), st))) return rc;
         cull = CullBufs{(const uint32_t *)m.cull_head.p, (const int32_t *)m.cull_lo.p, (const int32_t *)m.cull_hi.p, (const int32_t *)m.cull_job.p};
     }
+    // Curves are subdivided once: the counting pass parks up to slab_pts points per op (8 bytes each), the emitting pass
+    // copies them.  Only when the job set has curves, and within 256 MB of scratch.
+    uint32_t slab_pts = 0;
+    if (P.has_curves && P.n_ops > 0) {
+        slab_pts = (uint32_t)std::min<size_t>(32, ((size_t)256 << 20) / ((size_t)P.n_ops * sizeof(int2)));
+        if (slab_pts < 8) slab_pts = 0;
+        if (const char *ev = getenv("FTL_SLAB_PTS")) slab_pts = (uint32_t)std::max(0, std::min(64, atoi(ev)));  // tuning knob
+        if (slab_pts && (rc = m.slabs.ensure((size_t)P.n_ops * slab_pts * sizeof(int2), st))) return rc;
+    }
+    int2 *d_slabs = slab_pts ? (int2 *)m.slabs.p : nullptr;
     auto front = [&](bool sync_sizes) -> int {
         CK(cudaMemsetAsync(d_cnt, 0, sizeof(Counters), st));
         uint32_t nv_hint = cap_v;
@@ -705,7 +722,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 if (r1) return r1;
                 cull_sub_extents<<<cb, 256, 0, st>>>(d_ops, d_jobs, P, (const uint32_t *)m.cull_head.p, (int32_t *)m.cull_lo.p, (int32_t *)m.cull_hi.p); LAUNCHED();
             }
-            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, cull); LAUNCHED();
+            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, cull, d_slabs, slab_pts); LAUNCHED();
             const bool small_ops = !sync_sizes && P.n_ops <= SCAN_SMALL_MAX;  // one-block scan + the capacity guard in one launch
             int r2 = FTL_OK;
             if (small_ops) {
@@ -728,17 +745,19 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 nv_hint = nv;
             }
             if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
-            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull); LAUNCHED();
+            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull, d_slabs, slab_pts); LAUNCHED();
         }
         init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt); LAUNCHED();
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
         vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
         job_finalize<<<div_up(P.n_jobs, 128), 128, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (const uint32_t *)m.sub_last.p, P.n_jobs); LAUNCHED();
-        edge_build<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p); LAUNCHED();
-        if (P.all_direct) return FTL_OK;  // every tile scans its job's own edges: nothing to bin
+        if (P.all_direct) {  // every tile scans its job's own edges: nothing to bin
+            edge_build<false><<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p, P, nullptr); LAUNCHED();
+            return FTL_OK;
+        }
         CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
-        bin_edges<false><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, nullptr, nullptr); LAUNCHED();
+        edge_build<true><<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (EdgeRec *)m.edges.p, P, (uint32_t *)m.tcount.p); LAUNCHED();
         const bool small_bins = !sync_sizes && P.n_bins <= SCAN_SMALL_MAX;
         int r3 = FTL_OK;
         if (small_bins) {
@@ -754,8 +773,8 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
         }
         if (!small_bins) { set_entry_count<<<1, 1, 0, st>>>(d_cnt, (const uint32_t *)m.toff.p, P.n_bins, cap_e); LAUNCHED(); }
         CK(cudaMemsetAsync(m.tcount.p, 0, (size_t)P.n_bins * sizeof(uint32_t), st));
-        bin_edges<true><<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
-                                            (uint32_t *)m.entries.p); LAUNCHED();
+        bin_fill<<<vb, 256, 0, st>>>((const EdgeRec *)m.edges.p, d_cnt, d_js, P, (uint32_t *)m.tcount.p, (const uint32_t *)m.toff.p,
+                                     (uint32_t *)m.entries.p); LAUNCHED();
         CK(cudaGetLastError());
         return FTL_OK;
     };
@@ -772,7 +791,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands, P.cull,
+                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands, P.cull, slab_pts, (uint64_t)(uintptr_t)m.slabs.p,
                                      (uint64_t)(uintptr_t)m.cull_mark.p, (uint64_t)(uintptr_t)m.cull_head.p, (uint64_t)(uintptr_t)m.cull_part.p,
                                      (uint64_t)(uintptr_t)m.cull_lo.p, (uint64_t)(uintptr_t)m.cull_hi.p, (uint64_t)(uintptr_t)m.cull_job.p};
         if (!m.graph || key != m.graph_key) {

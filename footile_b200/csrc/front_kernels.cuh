@@ -102,6 +102,8 @@ struct OpSink {
     Vtx *vout = nullptr;
     float *wout = nullptr;
     uint32_t sub = 0, job = 0;
+    int2 *slab = nullptr;   // counting pass of a curve: the first slab_cap kept points are parked here, so that the
+    uint32_t slab_cap = 0;  // emitting pass copies them instead of subdividing the curve a second time
     __device__ __forceinline__ void put(WPt q) {
         if (WIDE) {
             if (EMIT) {
@@ -114,6 +116,7 @@ struct OpSink {
             int32_t fx = fx_from_f32(q.p.x), fy = fx_from_f32(q.p.y);
             if (force || fx != px || fy != py) {
                 if (EMIT) vout[n] = {fx, fy, sub, job};
+                else if (n < slab_cap) slab[n] = make_int2(fx, fy);
                 n++;
             }
             force = false;
@@ -269,7 +272,8 @@ template <bool WIDE, bool EMIT>
 __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                    const float *__restrict__ opw, SumHead *__restrict__ cnt,
                                                    const SumHead *__restrict__ off, Vtx *__restrict__ vout,
-                                                   float *__restrict__ wout, const Counters *__restrict__ C, CullBufs cull) {
+                                                   float *__restrict__ wout, const Counters *__restrict__ C, CullBufs cull,
+                                                   int2 *__restrict__ slabs = nullptr, uint32_t slab_pts = 0) {
     if (EMIT && C && C->overflow) return;
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
         const ftl_path_op op = ops[i];
@@ -291,6 +295,23 @@ __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict
                     sink.vout = vout + o.sum;
                     sink.sub = starts ? o.sum : o.head;
                     sink.job = j;
+                }
+            }
+            const bool curve = op.tag == FTL_OP_QUAD || op.tag == FTL_OP_CUBIC;
+            if (!WIDE && curve && slab_pts) {
+                int2 *slab = slabs + (size_t)i * slab_pts;
+                if (!EMIT) {
+                    sink.slab = slab;
+                    sink.slab_cap = slab_pts;
+                } else {
+                    const uint32_t cnt_i = off[i + 1].sum - off[i].sum;
+                    if (cnt_i <= slab_pts) {  // the counting pass parked every point of this curve: copy, do not subdivide again
+                        for (uint32_t k = 0; k < cnt_i; k++) {
+                            const int2 q = slab[k];
+                            sink.vout[k] = {q.x, q.y, sink.sub, sink.job};
+                        }
+                        continue;
+                    }
                 }
             }
             float w_pen = WIDE ? opw[2 * (size_t)i] : 0.0f, w_now = WIDE ? opw[2 * (size_t)i + 1] : 0.0f;
@@ -431,32 +452,6 @@ __device__ __forceinline__ EdgeRec make_edge(const Vtx &p0, const Vtx &p1, uint3
     return e;
 }
 
-// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most
-// one edge, directed from its upper to its lower vertex.  This is the same
-// set of edges the reference creates in update_edges/add_edge (fig.rs:576-600)
-// when it visits both neighbours of every vertex.
-__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, const Counters *__restrict__ C, const JobState *__restrict__ JS,
-                                                  EdgeRec *__restrict__ E) {
-    const uint32_t nv = C->nv;
-    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < nv; k += gridDim.x * blockDim.x) {
-        Vtx v = V[k];
-        bool last = vtx_is_last(V, nv, k);
-        bool pop = last && vtx_same(v, V[v.sub]);
-        EdgeRec e;
-        e.flags = 0;
-        if (!pop) {
-            uint32_t w = vtx_next_fwd(V, nv, k, v, last);
-            if (w != k) {
-                Vtx q = V[w];
-                if (q.y > v.y) e = make_edge(v, q, v.job, 0u, JS[v.job]);        // v is upper; w is v's Forward neighbour
-                else if (q.y < v.y) e = make_edge(q, v, v.job, 1u, JS[v.job]);   // w is upper; v is w's Reverse neighbour
-            }
-        }
-        if (e.flags) E[k] = e;
-        else E[k].flags = 0;
-    }
-}
-
 // Band range (bands of 32 rows, raster_bins) of an edge inside this device's rows; returns false if none.
 __device__ __forceinline__ bool edge_bands(const EdgeRec &e, const Params &P, uint32_t *b0, uint32_t *b1) {
     int32_t lo = e.ry0, hi = e.ry1;  // ry0 >= first_row >= 0 by construction
@@ -512,40 +507,83 @@ __device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t t
         if (FILL) entries[bin_off[bin] + slot] = k;
     }
 }
+// The bins of the warp's 32 edges (lane = edge k0 + lane; e.flags == 0: nothing).  Short edges are handled by their own
+// lane; an edge crossing many bands is spread over the warp (its record travels by shuffle).
 template <bool FILL>
-__global__ void __launch_bounds__(256) bin_edges(const EdgeRec *__restrict__ E, const Counters *__restrict__ C,
-                                                 const JobState *__restrict__ JS, Params P, uint32_t *__restrict__ bin_count,
-                                                 const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ entries) {
-    if (FILL && C->overflow) return;
+__device__ __forceinline__ void bin_warp(EdgeRec e, uint32_t k0, const JobState *__restrict__ JS, const Params &P, uint32_t *bin_count,
+                                         const uint32_t *bin_off, uint32_t *entries) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t b0 = 0, nb = 0, tbase = 0, b1;
+    if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
+        const JobState &js = JS[e.job];
+        if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
+            nb = b1 - b0 + 1;
+            tbase = e.job * P.b_nbands;
+        }
+    }
+    if (nb > 0 && nb <= 4)
+        for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k0 + lane, tbase + b, b, P, bin_count, bin_off, entries);
+    uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
+    while (tall) {
+        const int src = __ffs(tall) - 1;
+        tall &= tall - 1;
+        const uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src), stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
+        EdgeRec es;
+        es.x_bot0 = __shfl_sync(0xFFFFFFFFu, e.x_bot0, src);
+        es.inv_slope = __shfl_sync(0xFFFFFFFFu, e.inv_slope, src);
+        es.step_pix = 0;
+        es.ry0 = __shfl_sync(0xFFFFFFFFu, e.ry0, src);
+        es.ry1 = __shfl_sync(0xFFFFFFFFu, e.ry1, src);
+        es.fr = 0; es.job = 0; es.flags = 1u;
+        for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + (uint32_t)src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);
+    }
+}
+
+// Counting sort of edges by (job, band of 32 rows, column window): the COUNT pass rides in edge_build (the edge is in
+// registers there), this FILL pass writes edge ids at the scanned offsets.  Jobs with at most DIRECT_MAX edge slots are
+// not binned at all.
+__global__ void __launch_bounds__(256) bin_fill(const EdgeRec *__restrict__ E, const Counters *__restrict__ C, const JobState *__restrict__ JS, Params P,
+                                                uint32_t *__restrict__ bin_count, const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ entries) {
+    if (C->overflow) return;
     const uint32_t nv = C->nv;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t span = gridDim.x * blockDim.x;
     for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < nv; k0 += span) {
-        uint32_t k = k0 + lane;
-        uint32_t b0 = 0, nb = 0, tbase = 0;
+        EdgeRec e;
+        e.flags = 0;
+        if (k0 + lane < nv) e = E[k0 + lane];
+        bin_warp<true>(e, k0, JS, P, bin_count, bin_off, entries);
+    }
+}
+
+// One thread per vertex k: the ring segment (k, next_fwd(k)) becomes at most one edge, directed from its upper to its
+// lower vertex.  This is the same set of edges the reference creates in update_edges/add_edge (fig.rs:576-600) when it
+// visits both neighbours of every vertex.  COUNT: the edge's bins are counted here (first pass of the counting sort).
+template <bool COUNT>
+__global__ void __launch_bounds__(256) edge_build(const Vtx *__restrict__ V, const Counters *__restrict__ C, const JobState *__restrict__ JS,
+                                                  EdgeRec *__restrict__ E, Params P, uint32_t *__restrict__ bin_count) {
+    const uint32_t nv = C->nv;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t span = gridDim.x * blockDim.x;
+    for (uint32_t k0 = blockIdx.x * blockDim.x + threadIdx.x - lane; k0 < nv; k0 += span) {
+        const uint32_t k = k0 + lane;
         EdgeRec e;
         e.flags = 0;
         if (k < nv) {
-            e = E[k];
-            uint32_t b1;
-            if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
-                const JobState &js = JS[e.job];
-                if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
-                    nb = b1 - b0 + 1;
-                    tbase = e.job * P.b_nbands;
+            Vtx v = V[k];
+            bool last = vtx_is_last(V, nv, k);
+            bool pop = last && vtx_same(v, V[v.sub]);
+            if (!pop) {
+                uint32_t w = vtx_next_fwd(V, nv, k, v, last);
+                if (w != k) {
+                    Vtx q = V[w];
+                    if (q.y > v.y) e = make_edge(v, q, v.job, 0u, JS[v.job]);        // v is upper; w is v's Forward neighbour
+                    else if (q.y < v.y) e = make_edge(q, v, v.job, 1u, JS[v.job]);   // w is upper; v is w's Reverse neighbour
                 }
             }
+            if (e.flags) E[k] = e;
+            else E[k].flags = 0;
         }
-        if (nb > 0 && nb <= 4)
-            for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k, tbase + b, b, P, bin_count, bin_off, entries);
-        uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
-        while (tall) {
-            int src = __ffs(tall) - 1;
-            tall &= tall - 1;
-            uint32_t sb0 = __shfl_sync(0xFFFFFFFFu, b0, src), snb = __shfl_sync(0xFFFFFFFFu, nb, src);
-            uint32_t stb = __shfl_sync(0xFFFFFFFFu, tbase, src);
-            const EdgeRec es = E[k0 + src];
-            for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);
-        }
+        if (COUNT) bin_warp<false>(e, k0, JS, P, bin_count, nullptr, nullptr);
     }
 }
