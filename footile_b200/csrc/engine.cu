@@ -1045,7 +1045,7 @@ int Engine::debug_edges(std::vector<int32_t> *out) {
     CK(cudaStreamSynchronize(m.st));
     CK(cudaMemcpy(&js, m.jstate.p, sizeof(js), cudaMemcpyDeviceToHost));
     const uint32_t n = js.vtx_end - js.vtx_begin;
-    if (n == 0) return FTL_OK;
+    if (n == 0 || js.top_vid == NONE32) return FTL_OK;  // nothing was drawn: no edges were built
     std::vector<EdgeRec> e(n);
     CK(cudaMemcpy(e.data(), (const EdgeRec *)m.edges.p + js.vtx_begin, (size_t)n * sizeof(EdgeRec), cudaMemcpyDeviceToHost));
     for (const EdgeRec &r : e) {
