@@ -11,6 +11,7 @@
 #include <vector>
 
 #include "engine.h"
+#include "libm_compat.cuh"
 
 using namespace ftl;
 
@@ -237,10 +238,45 @@ static int stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, std:
     return FTL_OK;
 }
 
+// Where the stroker runs.  FTL_DEVICE_STROKE=1 / 0 forces the device / the host; otherwise a single stroke of a few
+// hundred ops is outlined on the host in microseconds (less than the device path's one synchronisation), larger ones and
+// every batch go to the device (stroke_kernels.cuh).
+static bool stroke_on_device(size_t n_ops, bool batch) {
+    if (const char *ev = getenv("FTL_DEVICE_STROKE")) return atoi(ev) != 0;
+    return batch || n_ops >= 512;
+}
+
+// Plotter::stroke with the stroker on the device; *done = false when the host stroker has to take the call.
+static int stroke_device(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color, bool *done) {
+    *done = false;
+    std::vector<float> opw;
+    const float final_w = stroke_widths(p->s_width, ops, n_ops, &opw);
+    std::vector<HostJob> jobs(1);
+    HostJob &j = jobs[0];
+    j.op_begin = 0; j.op_end = (uint32_t)n_ops;
+    memcpy(j.e, p->e, sizeof(j.e));
+    j.tol_sq = p->tol_sq;
+    j.rule = FTL_NONZERO;
+    if (color) memcpy(j.color, color, p->geo.bpp());
+    j.raster = p->raster;
+    bool needs_host = false;
+    int rc = p->eng.stroke(p->geo, jobs, ops, n_ops, opw.data(), p->join, p->miter_limit, &needs_host);
+    if (rc) return rc;
+    if (needs_host) return FTL_OK;
+    p->s_width = final_w;
+    *done = true;
+    return FTL_OK;
+}
+
 int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color) {
     GUARD_BEGIN
     if (!p) return bad("null plotter");
     if (n_ops && !ops) return bad("ops is null");
+    if (n_ops && n_ops < 0x7FFFFFFFull && stroke_on_device(n_ops, false)) {
+        bool done = false;
+        int rc = stroke_device(p, ops, n_ops, color, &done);
+        if (rc || done) return rc;
+    }
     std::vector<ftl_path_op> outline;
     int rc = stroke_ops(p, ops, n_ops, &outline);
     if (rc) return rc;
@@ -402,6 +438,19 @@ int ftl_batch_stroke(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, cons
         if (op_offsets[j + 1] < op_offsets[j] || op_offsets[j + 1] > 0x7FFFFFFFull) return bad("op_offsets must be non-decreasing");
     int rc = check_finite_ops(ops, n_ops);
     if (rc) return rc;
+    if (n_ops && stroke_on_device(n_ops, true)) {
+        std::vector<float> opw(2 * n_ops), w1;
+        std::vector<HostJob> jobs;
+        if ((rc = batch_jobs(b, n_jobs, op_offsets, nullptr, transforms, colors, &jobs))) return rc;
+        for (uint32_t j = 0; j < n_jobs; j++) {
+            const size_t o0 = (size_t)op_offsets[j], jn = (size_t)(op_offsets[j + 1] - op_offsets[j]);
+            stroke_widths(1.0f, ops + o0, jn, &w1);  // a new Plotter starts with pen width 1 (plotter.rs:112)
+            if (jn) memcpy(opw.data() + 2 * o0, w1.data(), 2 * jn * sizeof(float));
+        }
+        bool needs_host = false;
+        if ((rc = b->eng.stroke(b->geo, jobs, ops, n_ops, opw.data(), b->join, b->miter_limit, &needs_host))) return rc;
+        if (!needs_host) return FTL_OK;
+    }
     std::vector<std::vector<ftl_path_op>> outlines(n_jobs);
     StrokeParams sp;
     sp.join = b->join; sp.miter_limit = b->miter_limit; sp.tol_sq = b->tol_sq;
@@ -619,6 +668,79 @@ int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, f
     if (rc) return rc;
     if (n_out) *n_out = outline.size();
     if (out) memcpy(out, outline.data(), sizeof(ftl_path_op) * (outline.size() < cap ? outline.size() : cap));
+    return FTL_OK;
+    GUARD_END
+}
+// The outline as the DEVICE stroker builds it (stroke_kernels.cuh); *fell_back = 1 when it declined (the host stroker
+// would take the call) and nothing was written.
+int ftl_debug_stroke_ops_device(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap, size_t *n_out, int *fell_back) {
+    GUARD_BEGIN
+    if (!p || (n_ops && !ops)) return bad("null argument");
+    std::vector<float> opw;
+    stroke_widths(p->s_width, ops, n_ops, &opw);
+    std::vector<HostJob> jobs(1);
+    jobs[0].op_begin = 0; jobs[0].op_end = (uint32_t)n_ops;
+    memcpy(jobs[0].e, p->e, sizeof(jobs[0].e));
+    jobs[0].tol_sq = p->tol_sq;
+    jobs[0].raster = p->raster;
+    bool needs_host = false;
+    std::vector<ftl_path_op> outline;
+    int rc = p->eng.stroke(p->geo, jobs, ops, n_ops, opw.data(), p->join, p->miter_limit, &needs_host, &outline);
+    if (rc) return rc;
+    if (fell_back) *fell_back = needs_host ? 1 : 0;
+    if (n_out) *n_out = outline.size();
+    if (out) memcpy(out, outline.data(), sizeof(ftl_path_op) * (outline.size() < cap ? outline.size() : cap));
+    return FTL_OK;
+    GUARD_END
+}
+// Pin of libm_compat.cuh: n random (y, x) pairs per input class through hypotf_glibc / atan2f_glibc and through this
+// host's libm; counts the results that differ in any bit.  Runs on the CPU.
+int ftl_debug_libm_selftest(uint64_t n, uint64_t seed, uint64_t *hypot_mismatches, uint64_t *atan2_mismatches, uint64_t *sin_mismatches,
+                            uint64_t *sin_undecided) {
+    GUARD_BEGIN
+    uint64_t s = seed ? seed : 88172645463325252ull, bad_h = 0, bad_a = 0;
+    auto rnd = [&s]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return s; };
+    auto draw = [&rnd](int mode) -> float {
+        if (mode == 0) return (float)((int64_t)(rnd() % 2000000) - 1000000) / 37.0f;            // pixel-scale coordinates
+        if (mode == 1) return (float)((int64_t)(rnd() % 4000) - 2000) / 8.0f;                    // many exact ties / axis-aligned
+        uint32_t u = (uint32_t)rnd();                                                            // any finite bit pattern
+        if (mode == 2) u = (u & 0x807FFFFFu) | ((100u + (uint32_t)(rnd() % 56)) << 23);          // mid exponents
+        float f;
+        memcpy(&f, &u, 4);
+        return f;
+    };
+    for (int mode = 0; mode < 4; mode++)
+        for (uint64_t i = 0; i < n; i++) {
+            const float y = draw(mode), x = draw(mode);
+            const float h0 = hypotf(x, y), h1 = libm::hypotf_glibc(x, y);
+            const float a0 = atan2f(y, x), a1 = libm::atan2f_glibc(y, x);
+            if (libm::f2u(h0) != libm::f2u(h1) && !(h0 != h0 && h1 != h1)) bad_h++;
+            if (libm::f2u(a0) != libm::f2u(a1) && !(a0 != a0 && a1 != a1)) bad_a++;
+        }
+    // the two |sin| comparisons of the miter join: every float within 2e-3 of pi/2 (both signs) for `sm < 1`, random
+    // angles and thresholds for `sm >= sm_min`; a prediction of 0 / 1 must agree with the host's sinf
+    uint64_t bad_s = 0, undecided = 0;
+    {
+        float lo = 1.5707963705e+00f - 2.0e-3f, hi = 1.5707963705e+00f + 2.0e-3f;
+        for (float x = lo; x <= hi; x = nextafterf(x, 4.0f))
+            for (int sg = 0; sg < 2; sg++) {
+                const float v = sg ? -x : x;
+                const int p = libm::abs_sin_lt_one(v);
+                if (p < 0) undecided++;
+                else if ((fabsf(sinf(v)) < 1.0f) != (p == 1)) bad_s++;
+            }
+        for (uint64_t i = 0; i < n; i++) {
+            const float x = (float)((double)(rnd() % 2000001) / 1000000.0 - 1.0) * 1.5707964f;
+            const float t = i & 1 ? (float)((double)(rnd() % 1000001) / 1000000.0) : fabsf(sinf(x)) + (float)((int)(rnd() % 9) - 4) * 3.0e-8f;
+            const int p = libm::abs_sin_ge(x, t);
+            if (p < 0) undecided++;
+            else if ((fabsf(sinf(x)) >= t) != (p == 1)) bad_s++;
+        }
+    }
+    if (hypot_mismatches) *hypot_mismatches = bad_h;
+    if (atan2_mismatches) *atan2_mismatches = bad_a;
+    if (sin_mismatches) *sin_mismatches = bad_s;
+    if (sin_undecided) *sin_undecided = undecided;
     return FTL_OK;
     GUARD_END
 }

@@ -45,6 +45,7 @@
 
 #include "engine.h"
 #include "fixed.cuh"
+#include "libm_compat.cuh"
 #include "pix_compat.cuh"
 #include "pointy_compat.cuh"
 
@@ -78,6 +79,7 @@ static std::atomic<bool> g_profiling{false};
 #include "tile_kernel.cuh"
 #include "bin_kernel.cuh"
 #include "small_kernel.cuh"
+#include "stroke_kernels.cuh"
 #include "pack_kernels.cuh"
 
 // ---------------------------------------------------------------------------
@@ -155,6 +157,10 @@ struct Engine::Impl {
     PinBuf small_flags;                   // SMALL_RING overflow flags + the completion word
     DevBuf small_poison;                  // [0] poison, [1] CTA completion counter
     DevBuf srgb_tmp;                      // converted copy of a raster on its way to the host
+    // device stroker (stroke_kernels.cuh): inputs in one blob, then the intermediate arrays; capacities persist
+    DevBuf s_in, s_wop, s_keep, s_kidx, s_kp, s_info, s_cnt2, s_off2, s_counters, s_part;
+    PinBuf pin_stroke;
+    bool skip_graph = false;              // the next pipeline pass runs once with these sizes: do not capture a graph for it
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
     PinBuf pin_ring, pin_pack[2], pin_lit[2];
     DevBuf pack_fixed, pack_cnt, pack_lit;
@@ -229,10 +235,11 @@ Engine::~Engine() {
             Impl &m = *impl_;
             for (DevBuf *b : {&m.ops, &m.jobs, &m.jstate, &m.cnt, &m.off, &m.partials, &m.vtx, &m.edges, &m.sub_last, &m.tcount, &m.toff,
                               &m.tpart, &m.entries, &m.counters, &m.opw, &m.wide, &m.misc, &m.tickets, &m.look, &m.cull_mark, &m.cull_head, &m.cull_part, &m.cull_lo,
-                              &m.cull_hi, &m.cull_job, &m.slabs, &m.small_poison, &m.srgb_tmp, &m.pack_fixed, &m.pack_cnt, &m.pack_lit})
+                              &m.cull_hi, &m.cull_job, &m.slabs, &m.small_poison, &m.srgb_tmp, &m.pack_fixed, &m.pack_cnt, &m.pack_lit, &m.s_in, &m.s_wop, &m.s_keep, &m.s_kidx, &m.s_kp,
+                              &m.s_info, &m.s_cnt2, &m.s_off2, &m.s_counters, &m.s_part})
                 b->release();
             m.drop_graph();
-            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1], &m.small_flags}) b->release();
+            for (PinBuf *b : {&m.pin_ops, &m.pin_jobs, &m.pin_small, &m.pin_misc, &m.pin_ring, &m.pin_pack[0], &m.pin_pack[1], &m.pin_lit[0], &m.pin_lit[1], &m.small_flags, &m.pin_stroke}) b->release();
             cudaStreamDestroy(impl_->st);
         }
         delete impl_;
@@ -242,7 +249,7 @@ Engine::~Engine() {
 static int engine_init(Engine::Impl *m, int device, void **stream_out);
 static int run_pipeline(Engine::Impl &m, bool exact);
 static int resolve_pending(Engine::Impl &m);
-static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered);
+static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered, bool ops_on_device = false);
 
 typedef void (*TileKernel)(const EdgeRec *, const JobDesc *, const JobState *, Params, const Counters *);
 static TileKernel tile_kernel(int fmt, bool aligned) {
@@ -465,7 +472,9 @@ int Engine::upload(const Geometry &g, const std::vector<HostJob> &jobs, const ft
     return upload_jobs(m, g, jobs, ops, n_ops, layered);
 }
 
-static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered) {
+// ops_on_device: the ops are written into m.ops by kernels after this call (the device stroker's outline: Line / Close
+// ops only), and so are the op ranges of the job descriptors; nothing is staged or validated here.
+static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered, bool ops_on_device) {
     m.have_jobs = false;  // stays false if anything below fails
     m.last_small = false;
     m.small_tail = false;
@@ -488,7 +497,8 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     for (size_t jx = 0; jx < jobs.size(); jx++) {
         const HostJob &h = jobs[jx];
         if (h.op_end - h.op_begin > 8u) P.all_tiny = 0;
-        bool direct = h.op_end - h.op_begin <= DIRECT_MAX;
+        bool direct = !ops_on_device && h.op_end - h.op_begin <= DIRECT_MAX;
+        if (ops_on_device) P.all_tiny = 0;
         for (uint32_t i = h.op_begin; i < h.op_end && direct; i++)
             if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) direct = false;
         if (!direct) {
@@ -519,12 +529,12 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     size_t ops_bytes = n_ops * sizeof(ftl_path_op), jobs_bytes = jobs.size() * sizeof(JobDesc);
     // the previous call's async copies out of the pinned staging must be done before it is overwritten or freed
     CK(cudaStreamSynchronize(m.st));
-    if ((rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
+    if (!ops_on_device && (rc = m.pin_ops.ensure(ops_bytes ? ops_bytes : 1))) return rc;
     if ((rc = m.pin_jobs.ensure(jobs_bytes))) return rc;
     if ((rc = m.ops.ensure(ops_bytes ? ops_bytes : 1, m.st))) return rc;
     if ((rc = m.jobs.ensure(jobs_bytes, m.st))) return rc;
     // validate + stage + copy in pieces: the DMA of one piece runs while the host threads stage the next
-    {
+    if (!ops_on_device) {
         const size_t PIECE = 1u << 20;  // ops per piece (28 MB)
         std::atomic<bool> curves{false};
         for (size_t at = 0; at < n_ops; at += PIECE) {
@@ -652,6 +662,172 @@ int Engine::fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, con
     return replay();
 }
 
+// Plotter::stroke on the device (plotter.rs:356-365 with stroker.rs:204-416 as stroke_kernels.cuh).
+int Engine::stroke(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, const float *opw, int join,
+                   float miter_limit, bool *needs_host, std::vector<ftl_path_op> *outline, std::vector<uint32_t> *outline_offsets) {
+    ENSURE_INIT();
+    Impl &m = *impl_;
+    *needs_host = false;
+    if (outline) outline->clear();
+    if (outline_offsets) outline_offsets->assign(jobs.size() + 1, 0u);
+    int rc = resolve_pending(m);
+    if (rc) return rc;
+    if (jobs.empty() || n_ops == 0) return FTL_OK;
+    if (n_ops >= 0x7FFFFFFFull || jobs.size() >= 0x7FFFFFFFull) {
+        set_error("too many ops/jobs for one call");
+        return FTL_ERR_INVALID;
+    }
+    if ((rc = validate_ops(ops, n_ops))) return rc;
+    cudaStream_t st = m.st;
+    m.small_tail = false;
+    m.have_jobs = false;
+    m.last_small = false;
+    const uint32_t n_jobs = (uint32_t)jobs.size(), no = (uint32_t)n_ops;
+    // ---- host: sub-strokes from the ops, job descriptors of the flatten ----
+    std::vector<uint32_t> subs, op_sub(n_ops, NONE32), jfs(n_jobs + 1, 0u);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        jfs[j] = (uint32_t)(subs.size() / 4);
+        stroke_sub_table(ops, jobs[j].op_begin, jobs[j].op_end, j, &subs, op_sub.data());
+    }
+    const uint32_t n_subs = (uint32_t)(subs.size() / 4);
+    jfs[n_jobs] = n_subs;
+    if (n_subs == 0) return FTL_OK;  // no drawing op: Stroke::path_ops is empty and the fill draws nothing (fig.rs:491)
+    auto up16 = [](size_t v) { return (v + 15u) & ~(size_t)15u; };
+    const size_t o_ops = 0, o_jobs = up16(o_ops + n_ops * sizeof(ftl_path_op)), o_opw = up16(o_jobs + (size_t)n_jobs * sizeof(JobDesc)),
+                 o_opsub = up16(o_opw + n_ops * 2 * sizeof(float)), o_subs = up16(o_opsub + n_ops * sizeof(uint32_t)),
+                 o_jfs = up16(o_subs + subs.size() * sizeof(uint32_t)), in_bytes = up16(o_jfs + jfs.size() * sizeof(uint32_t));
+    CK(cudaStreamSynchronize(st));  // the previous call's copy out of the pinned staging is done
+    if ((rc = m.pin_stroke.ensure(in_bytes + sizeof(StrokeCounters)))) return rc;
+    if ((rc = m.s_in.ensure(in_bytes, st))) return rc;
+    uint8_t *hp = (uint8_t *)m.pin_stroke.p;
+    memcpy(hp + o_ops, ops, n_ops * sizeof(ftl_path_op));
+    JobDesc *jd = (JobDesc *)(hp + o_jobs);
+    for (uint32_t j = 0; j < n_jobs; j++) {
+        JobDesc d{};
+        d.op_begin = jobs[j].op_begin; d.op_end = jobs[j].op_end;
+        for (int k = 0; k < 6; k++) {
+            d.e[k] = jobs[j].e[k];
+            if (!(d.e[k] - d.e[k] == 0.0f)) {
+                set_error("non-finite transform");
+                return FTL_ERR_NONFINITE;
+            }
+        }
+        d.tol_sq = jobs[j].tol_sq;
+        jd[j] = d;
+    }
+    memcpy(hp + o_opw, opw, n_ops * 2 * sizeof(float));
+    memcpy(hp + o_opsub, op_sub.data(), n_ops * sizeof(uint32_t));
+    memcpy(hp + o_subs, subs.data(), subs.size() * sizeof(uint32_t));
+    memcpy(hp + o_jfs, jfs.data(), jfs.size() * sizeof(uint32_t));
+    CK(cudaMemcpyAsync(m.s_in.p, hp, in_bytes, cudaMemcpyHostToDevice, st));
+    g_h2d_bytes.fetch_add(in_bytes, std::memory_order_relaxed);
+    const uint8_t *dp = (const uint8_t *)m.s_in.p;
+    const ftl_path_op *d_ops = (const ftl_path_op *)(dp + o_ops);
+    const JobDesc *d_jobs = (const JobDesc *)(dp + o_jobs);
+    const float *d_opw = (const float *)(dp + o_opw);
+    const uint32_t *d_opsub = (const uint32_t *)(dp + o_opsub);
+    const StrokeSub *d_subs = (const StrokeSub *)(dp + o_subs);
+    const uint32_t *d_jfs = (const uint32_t *)(dp + o_jfs);
+
+    if ((rc = m.cnt.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
+    if ((rc = m.off.ensure((n_ops + 1) * sizeof(SumHead), st))) return rc;
+    if ((rc = m.s_counters.ensure(sizeof(StrokeCounters), st))) return rc;
+    if ((rc = m.s_info.ensure((size_t)n_subs * sizeof(StrokeSubInfo), st))) return rc;
+    if ((rc = m.wide.ensure(3 * sizeof(float), st))) return rc;
+    StrokeCounters *d_sc = (StrokeCounters *)m.s_counters.p;
+    StrokeCounters *h_sc = (StrokeCounters *)(hp + in_bytes);
+    Params P{};
+    P.n_jobs = n_jobs;
+    P.n_ops = no;
+    const StrokeJoin sj{join, miter_limit, jobs[0].tol_sq};
+    const uint32_t fb = std::min<uint32_t>(div_up(no, FLAT_THREADS), (uint32_t)m.n_sms * 16);
+    const CullBufs no_cull{nullptr, nullptr, nullptr, nullptr};
+    uint32_t cap_raw = 0, n_slots = 0;
+    for (int attempt = 0; attempt < 2; attempt++) {
+        // capacity of the point arrays: what earlier calls needed (the first call learns it from its overflow)
+        cap_raw = (uint32_t)std::min<size_t>(m.wide.cap / (3 * sizeof(float)), (size_t)0x3FFFFFFF);
+        if ((rc = m.s_wop.ensure((size_t)cap_raw * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.s_keep.ensure((size_t)cap_raw * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.s_kidx.ensure(((size_t)cap_raw + 1) * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.s_kp.ensure((size_t)cap_raw * sizeof(float4), st))) return rc;
+        n_slots = 2u * (cap_raw + n_subs);
+        if ((rc = m.s_cnt2.ensure((size_t)n_slots * sizeof(uint32_t), st))) return rc;
+        if ((rc = m.s_off2.ensure(((size_t)n_slots + 1) * sizeof(uint32_t), st))) return rc;
+        CK(cudaMemsetAsync(d_sc, 0, sizeof(StrokeCounters), st));
+        flatten_ops<true, false><<<fb, FLAT_THREADS, 0, st>>>(d_ops, d_jobs, P, d_opw, (SumHead *)m.cnt.p, nullptr, nullptr, nullptr, nullptr, no_cull); LAUNCHED();
+        if ((rc = run_scan<SumHeadOp>(st, (const SumHead *)m.cnt.p, no, (SumHead *)m.off.p, m.partials))) return rc;
+        stroke_set_raw<<<div_up(n_jobs, 256), 256, 0, st>>>(d_sc, (const SumHead *)m.off.p, d_jobs, n_jobs, no, cap_raw); LAUNCHED();
+        flatten_ops<true, true><<<fb, FLAT_THREADS, 0, st>>>(d_ops, d_jobs, P, d_opw, nullptr, (const SumHead *)m.off.p, nullptr, (float *)m.wide.p, &d_sc->overflow,
+                                                           no_cull, nullptr, 0, (uint32_t *)m.s_wop.p); LAUNCHED();
+        const uint32_t pb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(cap_raw, 256), (uint32_t)m.n_sms * 8));
+        stroke_keep<<<pb, 256, 0, st>>>((const float *)m.wide.p, (const uint32_t *)m.s_wop.p, (const SumHead *)m.off.p, d_opsub, d_subs, d_sc, cap_raw,
+                                       (uint32_t *)m.s_keep.p); LAUNCHED();
+        if ((rc = run_scan<AddU32>(st, (const uint32_t *)m.s_keep.p, cap_raw, (uint32_t *)m.s_kidx.p, m.s_part))) return rc;
+        stroke_compact<<<pb, 256, 0, st>>>((const float *)m.wide.p, (const uint32_t *)m.s_wop.p, d_opsub, (const uint32_t *)m.s_keep.p,
+                                          (const uint32_t *)m.s_kidx.p, d_sc, cap_raw, (float4 *)m.s_kp.p); LAUNCHED();
+        stroke_sub_info<<<div_up(n_subs, 128), 128, 0, st>>>(d_subs, n_subs, (const SumHead *)m.off.p, (const uint32_t *)m.s_kidx.p, d_sc,
+                                                            (StrokeSubInfo *)m.s_info.p); LAUNCHED();
+        CK(cudaMemsetAsync(m.s_cnt2.p, 0, (size_t)n_slots * sizeof(uint32_t), st));
+        const uint32_t sb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(2ull * cap_raw, 128), (uint32_t)m.n_sms * 16));
+        stroke_segments<false><<<sb, 128, 0, st>>>(sj, (const float4 *)m.s_kp.p, (const StrokeSubInfo *)m.s_info.p, d_sc, (uint32_t *)m.s_cnt2.p, nullptr, nullptr); LAUNCHED();
+        if ((rc = run_scan<AddU32>(st, (const uint32_t *)m.s_cnt2.p, n_slots, (uint32_t *)m.s_off2.p, m.s_part))) return rc;
+        stroke_set_out<<<1, 1, 0, st>>>(d_sc, (const uint32_t *)m.s_off2.p, n_slots); LAUNCHED();
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h_sc, d_sc, sizeof(StrokeCounters), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));  // the one host round trip of a device stroke: the outline's size
+        if (!h_sc->overflow) break;
+        if (attempt == 1) {
+            set_error("device stroker: the point capacity guard tripped twice");
+            return FTL_ERR_CUDA;
+        }
+        if ((rc = m.wide.ensure((size_t)h_sc->need_raw * 3 * sizeof(float), st))) return rc;
+    }
+    if (h_sc->fallback) {
+        *needs_host = true;
+        return FTL_OK;
+    }
+    const uint32_t n_out = h_sc->n_out;
+    const uint32_t sb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(2ull * h_sc->nk, 128), (uint32_t)m.n_sms * 16));
+    if (outline) {  // probe: hand the outline back instead of filling it
+        if ((rc = m.ops.ensure((size_t)std::max(n_out, 1u) * sizeof(ftl_path_op), st))) return rc;
+        if ((rc = m.jobs.ensure((size_t)n_jobs * sizeof(JobDesc), st))) return rc;
+        stroke_segments<true><<<sb, 128, 0, st>>>(sj, (const float4 *)m.s_kp.p, (const StrokeSubInfo *)m.s_info.p, d_sc, nullptr, (const uint32_t *)m.s_off2.p,
+                                                 (ftl_path_op *)m.ops.p); LAUNCHED();
+        stroke_patch_jobs<<<div_up(n_jobs, 128), 128, 0, st>>>((JobDesc *)m.jobs.p, n_jobs, d_jfs, n_subs, (const StrokeSubInfo *)m.s_info.p,
+                                                              (const uint32_t *)m.s_off2.p, d_sc); LAUNCHED();
+        CK(cudaGetLastError());
+        outline->resize(n_out);
+        std::vector<JobDesc> hj(n_jobs);
+        if (n_out) CK(cudaMemcpyAsync(outline->data(), m.ops.p, (size_t)n_out * sizeof(ftl_path_op), cudaMemcpyDeviceToHost, st));
+        CK(cudaMemcpyAsync(hj.data(), m.jobs.p, (size_t)n_jobs * sizeof(JobDesc), cudaMemcpyDeviceToHost, st));
+        CK(cudaStreamSynchronize(st));
+        if (outline_offsets) {
+            for (uint32_t j = 0; j < n_jobs; j++) (*outline_offsets)[j] = hj[j].op_begin;
+            (*outline_offsets)[n_jobs] = n_out;
+        }
+        return FTL_OK;
+    }
+    if (n_out == 0) return FTL_OK;
+    // ---- the fill of the outline (NonZero, plotter.rs:364): its ops and op ranges are written by the two kernels below ----
+    std::vector<HostJob> fjobs(jobs);
+    for (HostJob &h : fjobs) {
+        h.op_begin = h.op_end = 0;
+        h.rule = FTL_NONZERO;
+    }
+    if ((rc = upload_jobs(m, g, fjobs, nullptr, n_out, false, true))) return rc;
+    if (!m.have_jobs) return FTL_OK;
+    stroke_segments<true><<<sb, 128, 0, st>>>(sj, (const float4 *)m.s_kp.p, (const StrokeSubInfo *)m.s_info.p, d_sc, nullptr, (const uint32_t *)m.s_off2.p,
+                                             (ftl_path_op *)m.ops.p); LAUNCHED();
+    stroke_patch_jobs<<<div_up(n_jobs, 128), 128, 0, st>>>((JobDesc *)m.jobs.p, n_jobs, d_jfs, n_subs, (const StrokeSubInfo *)m.s_info.p,
+                                                          (const uint32_t *)m.s_off2.p, d_sc); LAUNCHED();
+    CK(cudaGetLastError());
+    m.skip_graph = true;
+    const bool exact = m.vtx.cap == 0 || m.edges.cap == 0 || m.entries.cap == 0;
+    rc = run_pipeline(m, exact);
+    m.skip_graph = false;
+    return rc;
+}
+
 // One pass of the device pipeline over the resident job set.
 //   exact = true : sizes are read back after each scan (two host round trips) and the scratch
 //                  buffers are grown to fit; used for the first call and after an overflow.
@@ -747,7 +923,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                 nv_hint = nv;
             }
             if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
-            flatten_ops<false, true><<<fb, FLAT_THREADS, P.has_curves ? FLAT_SMEM_BYTES : 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, d_cnt, cull, d_slabs, slab_pts); LAUNCHED();
+            flatten_ops<false, true><<<fb, FLAT_THREADS, P.has_curves ? FLAT_SMEM_BYTES : 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, &d_cnt->overflow, cull, d_slabs, slab_pts); LAUNCHED();
         }
         init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt); LAUNCHED();
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
@@ -784,7 +960,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
     if (exact) {
         m.drop_graph();
         if ((rc = front(true))) return rc;
-    } else if (!m.use_graph) {
+    } else if (!m.use_graph || m.skip_graph) {
         if ((rc = front(false))) return rc;
     } else {
         // the sequence depends only on these values: replay the captured graph while they are unchanged

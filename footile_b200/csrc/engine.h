@@ -62,6 +62,13 @@ public:
     // The jobs are layers drawn in order onto ONE raster (all jobs carry the same raster pointer):
     // flatten / edge prep / binning run once for all layers, the tile kernel once per layer.
     int fill_layers(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops);
+    // Plotter::stroke for a set of jobs with the stroker on the device (stroke_kernels.cuh): flatten with widths, outline
+    // and fill without the outline leaving HBM; one host synchronisation (the outline's size).  opw: per op (pen_w, s_width)
+    // as stroke_widths() computes them per job.  *needs_host is set, and nothing is drawn, when the device could not
+    // reproduce the host stroker's decisions (libm_compat.cuh): the caller then outlines on the host.
+    // outline (optional probe): the outline ops and their per-job offsets are copied back instead of being filled.
+    int stroke(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, const float *opw, int join,
+               float miter_limit, bool *needs_host, std::vector<ftl_path_op> *outline = nullptr, std::vector<uint32_t> *outline_offsets = nullptr);
     // Upload only (device-resident replay).
     int upload(const Geometry &g, const std::vector<HostJob> &jobs, const ftl_path_op *ops, size_t n_ops, bool layered = false);
     int replay();
@@ -122,6 +129,9 @@ void stroke_outline(const StrokeParams &sp, const ftl_path_op *ops, size_t n_ops
                     std::vector<ftl_path_op> *out);
 // The stroke-side flatten on the host (same bits as Engine::flatten_wide; stroker.cpp).
 void flatten_wide_host(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, const float *opw, WideFlat *out);
+// Sub-strokes of ops[op_begin, op_end) as Stroke::add_point / close form them (stroker.rs:204-236): appends 4 words per
+// sub-stroke to `subs` (first drawing op, one past the last, joined, job) and sets op_sub[i] for every drawing op.
+void stroke_sub_table(const ftl_path_op *ops, uint32_t op_begin, uint32_t op_end, uint32_t job, std::vector<uint32_t> *subs, uint32_t *op_sub);
 // Per-op (pen_w, s_width) from the PenWidth ops; returns the final s_width
 // (plotter.rs:128-130,151-153,233-236,293-298).
 float stroke_widths(float s_width, const ftl_path_op *ops, size_t n_ops, std::vector<float> *opw);

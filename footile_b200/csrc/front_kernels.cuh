@@ -101,6 +101,8 @@ struct OpSink {
     int32_t px = 0, py = 0;
     Vtx *vout = nullptr;
     float *wout = nullptr;
+    uint32_t *wop = nullptr;  // wide mode, device stroker: the op each point came from
+    uint32_t opi = 0;
     uint32_t sub = 0, job = 0;
     int2 *slab = nullptr;   // counting pass of a curve: the first slab_cap kept points are parked here, so that the
     uint32_t slab_cap = 0;  // emitting pass copies them instead of subdividing the curve a second time
@@ -110,6 +112,7 @@ struct OpSink {
                 wout[3 * (size_t)n] = q.p.x;
                 wout[3 * (size_t)n + 1] = q.p.y;
                 wout[3 * (size_t)n + 2] = q.w;
+                if (wop) wop[n] = opi;
             }
             n++;
         } else {
@@ -309,9 +312,9 @@ template <bool WIDE, bool EMIT>
 __global__ void __launch_bounds__(FLAT_THREADS) flatten_ops(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                    const float *__restrict__ opw, SumHead *__restrict__ cnt,
                                                    const SumHead *__restrict__ off, Vtx *__restrict__ vout,
-                                                   float *__restrict__ wout, const Counters *__restrict__ C, CullBufs cull,
-                                                   int2 *__restrict__ slabs = nullptr, uint32_t slab_pts = 0) {
-    if (EMIT && C && C->overflow) return;
+                                                   float *__restrict__ wout, const uint32_t *__restrict__ stop, CullBufs cull,
+                                                   int2 *__restrict__ slabs = nullptr, uint32_t slab_pts = 0, uint32_t *__restrict__ wop = nullptr) {
+    if (EMIT && stop && *stop) return;  // a capacity guard tripped (Counters::overflow / StrokeCounters::overflow): draw nothing
     extern __shared__ __align__(16) float flat_smem[];
     FlatStack<WIDE> stk(flat_smem);
     for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
@@ -329,8 +332,13 @@ __global__ void __launch_bounds__(FLAT_THREADS) flatten_ops(const ftl_path_op *_
             sink.force = starts;
             if (EMIT) {
                 SumHead o = off[i];
-                if (WIDE) sink.wout = wout + 3 * (size_t)o.sum;
-                else {
+                if (WIDE) {
+                    sink.wout = wout + 3 * (size_t)o.sum;
+                    if (wop) {
+                        sink.wop = wop + o.sum;
+                        sink.opi = i;
+                    }
+                } else {
                     sink.vout = vout + o.sum;
                     sink.sub = starts ? o.sum : o.head;
                     sink.job = j;

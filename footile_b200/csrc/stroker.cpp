@@ -248,6 +248,32 @@ float stroke_widths(float s_width, const ftl_path_op *ops, size_t n_ops, std::ve
     return s_width;
 }
 
+void stroke_sub_table(const ftl_path_op *ops, uint32_t op_begin, uint32_t op_end, uint32_t job, std::vector<uint32_t> *subs, uint32_t *op_sub) {
+    bool have_points = false, pending = true;  // pending: the next drawing op starts a sub-stroke
+    size_t cur = 0;
+    for (uint32_t i = op_begin; i < op_end; i++) {
+        const uint32_t tag = ops[i].tag;
+        op_sub[i] = 0xFFFFFFFFu;
+        if (tag == FTL_OP_PENWIDTH) continue;
+        if (tag == FTL_OP_CLOSE || tag == FTL_OP_MOVE) {  // Stroke::close(joined) acts on the current sub-stroke, also when it is already done
+            if (have_points) {
+                (*subs)[cur + 2] = tag == FTL_OP_CLOSE ? 1u : 0u;
+                pending = true;
+            }
+            if (tag == FTL_OP_CLOSE) continue;
+        }
+        if (pending) {
+            cur = subs->size();
+            const uint32_t rec[4] = {i, i + 1, 0u, job};
+            subs->insert(subs->end(), rec, rec + 4);
+            pending = false;
+        }
+        op_sub[i] = (uint32_t)(cur / 4);
+        (*subs)[cur + 1] = i + 1;
+        have_points = true;
+    }
+}
+
 void stroke_outline(const StrokeParams &sp, const ftl_path_op *ops, size_t n_ops, const WideFlat &flat, std::vector<ftl_path_op> *out) {
     out->clear();
     Outline o(sp, out);

@@ -260,6 +260,29 @@ class Plotter:
                 return out[: n.value].copy()
             cap = n.value
 
+    def debug_stroke_ops_device(self, ops):
+        """The outline as the device stroker builds it (stroke_kernels.cuh), or None when it declined the call."""
+        a = as_ops(ops)
+        cap = 1 << 16
+        while True:
+            out = np.zeros(cap, dtype=OP_DTYPE)
+            n, fb = C.c_size_t(), C.c_int()
+            _lib.check(_lib.lib().ftl_debug_stroke_ops_device(self._handle, a.ctypes.data if len(a) else None, len(a), out.ctypes.data, cap,
+                                                              C.byref(n), C.byref(fb)))
+            if fb.value:
+                return None
+            if n.value <= cap:
+                return out[: n.value].copy()
+            cap = n.value
+
+
+def debug_libm_selftest(n, seed=0):
+    """libm_compat.cuh against this host's libm: (hypotf mismatches, atan2f mismatches, wrong |sin| predictions, undecided
+    |sin| predictions) over 4 * n random inputs and every float next to +-pi/2. Pure host code."""
+    h, a, sm, su = C.c_uint64(), C.c_uint64(), C.c_uint64(), C.c_uint64()
+    _lib.check(_lib.lib().ftl_debug_libm_selftest(int(n), int(seed), C.byref(h), C.byref(a), C.byref(sm), C.byref(su)))
+    return h.value, a.value, sm.value, su.value
+
 
 def debug_accumulate(rule, src, device=0):
     """Row accumulate alone (imgbuf.rs:38-51,141-154) on the device. src: (rows, n) or (n,) i16."""

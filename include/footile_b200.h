@@ -103,7 +103,11 @@ float ftl_pen_width(const ftl_plotter *p);                  /* the persistent s_
  * (premultiplied); ignored for FTL_MATTE8 exactly as the reference ignores it
  * (fig.rs:632-636).  Asynchronous on the handle's stream. */
 int ftl_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
-/* Plotter::stroke(ops, clr) (plotter.rs:356-365). */
+/* Plotter::stroke(ops, clr) (plotter.rs:356-365).  The stroker (stroker.rs:204-416) runs on the device for strokes of
+ * 512 ops or more (flatten with widths -> outline -> fill, the outline never leaves HBM; one host synchronisation) and
+ * on the host for smaller ones, where it costs microseconds; both produce the same outline bit for bit (the device
+ * restates glibc's hypotf / atan2f exactly and hands the call to the host stroker when a |sin| comparison of a miter
+ * join is too close to call).  FTL_DEVICE_STROKE=1 / 0 in the environment forces one or the other. */
 int ftl_stroke(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, const uint8_t *color);
 
 /* A scene: n_layers fills drawn IN ORDER onto the plotter's raster by one pass of the device
@@ -151,8 +155,9 @@ int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const 
 /* Plotter::set_join for every stroke of the batch (plotter.rs:158-161). */
 int ftl_batch_set_join(ftl_batch *b, int join, float miter_limit);
 /* n_jobs independent `Plotter::new(raster_j).set_transform(..).stroke(ops_j, color_j)` calls (plotter.rs:356-365) in one
- * pass: the outlines are made on host threads (the stroker is sequential f32 arithmetic over libm: stroker.rs:204-416)
- * and filled NonZero by one pass of the device pipeline.  Every job starts with pen width 1 like a new Plotter. */
+ * pass: flatten with widths, outline (stroker.rs:204-416) and NonZero fill all run on the device, one thread per
+ * (point, side) of the outline; the host stroker (threads) takes the batch when the device declines (see ftl_stroke) or
+ * FTL_DEVICE_STROKE=0.  Every job starts with pen width 1 like a new Plotter. */
 int ftl_batch_stroke(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const float *transforms,
                      const uint8_t *colors);
 /* Copy rasters [first, first+count) to host (blocking). */
@@ -246,6 +251,16 @@ int ftl_debug_small_profile(ftl_plotter *p, int64_t stamps[9]);
 /* The outline ops Plotter::stroke hands to fill (stroker.rs:239-247). */
 int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
                          size_t *n_out);
+/* The same outline as the DEVICE stroker builds it (stroke_kernels.cuh); *fell_back = 1 (and *n_out = 0) when it
+ * declined and the host stroker would take the call.  The parity tests compare the two bit for bit. */
+int ftl_debug_stroke_ops_device(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
+                                size_t *n_out, int *fell_back);
+/* Pin of the libm restatement the device stroker uses (csrc/libm_compat.cuh: glibc's hypotf and atan2f): 4 * n random
+ * inputs through it and through this host's libm, counting results that differ in any bit; and the two three-valued
+ * |sin| comparisons of the miter join against the host's sinf (wrong predictions, and how many were left undecided -
+ * about half of the n `>=` probes sit within 1.2e-7 of their threshold on purpose).  Pure host code. */
+int ftl_debug_libm_selftest(uint64_t n, uint64_t seed, uint64_t *hypot_mismatches, uint64_t *atan2_mismatches,
+                            uint64_t *sin_mismatches, uint64_t *sin_undecided);
 /* The host stroker alone (stroker.rs:204-416) on an already flattened wide
  * polyline: counts[i] points of op i, xyw = (x, y, width) per point.  Pure
  * host code; needs no device. */

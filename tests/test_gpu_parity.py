@@ -914,6 +914,119 @@ def test_batch_stroke_equals_one_plotter_per_stroke(join):
         assert np.array_equal(got[j], o.raster()), j
 
 
+# ---- the stroker on the device (stroke_kernels.cuh) against the host stroker and the oracle ------------------
+JOINS = [JoinStyle.Miter(4.0), JoinStyle.Bevel, JoinStyle.Round, JoinStyle.Miter(1.5)]
+
+
+def test_libm_restatement_on_this_box():
+    """The same pin as tests/test_host.py::test_libm_restatement_matches_glibc, on the GPU box's own CPU and glibc."""
+    from footile_b200.plotter import debug_libm_selftest
+    h, a, s_wrong, _ = debug_libm_selftest(1_000_000, 99)
+    assert (h, a, s_wrong) == (0, 0, 0)
+
+
+def test_device_stroker_outline_equals_host_on_the_example_scenes():
+    """stroker.rs:204-416 on the device: the outline ops equal the host stroker's (and the oracle's) bit for bit."""
+    declined = 0
+    for scale in (1.0, 30.0):
+        for join in JOINS:
+            for name, path in list(scenes.stroke_scenes(scale).items()) + [("fishy", scenes.fishy_example()[0]), ("eye", scenes.fishy_example()[1])]:
+                g, o = both(128, 128, Format.Matte8, join=join)
+                dev = g.debug_stroke_ops_device(path)
+                ref = o.debug_stroke_ops(path)
+                if dev is None:
+                    declined += 1
+                    continue
+                assert len(dev) == len(ref) and dev.tobytes() == ref.tobytes(), (name, scale, str(join))
+    assert declined == 0, declined  # none of the reference's scenes has a join on a sin threshold
+
+
+def test_device_stroker_outline_equals_host_on_random_paths():
+    rng = np.random.default_rng(2024)
+    declined = 0
+    n_cases = 60
+    for it in range(n_cases):
+        parts = []
+        for _ in range(int(rng.integers(1, 5))):  # several sub-strokes: Move / Close / PenWidth between them
+            parts.append(np.array([PathOp.PenWidth(float(rng.uniform(0.3, 25.0)))], dtype=OP_DTYPE))
+            parts.append(random_path(rng, 300, int(rng.integers(1, 14)), closed_prob=0.5))
+            if rng.random() < 0.3:
+                parts.append(np.array([PathOp.Close()], dtype=OP_DTYPE))  # a second close on the same sub-stroke
+        ops = np.concatenate(parts)
+        join = JOINS[it % 4]
+        tr = None if it % 3 else [1.25, 0.1, 5.0, -0.2, 0.9, 11.0]
+        g, o = both(320, 320, Format.Matte8, join=join, tol=0.3 if it & 1 else 0.05, transform=tr)
+        dev = g.debug_stroke_ops_device(ops)
+        host = g.debug_stroke_ops(ops)
+        ref = o.debug_stroke_ops(ops)
+        assert host.tobytes() == ref.tobytes(), it
+        if dev is None:
+            declined += 1
+            continue
+        assert len(dev) == len(ref) and dev.tobytes() == ref.tobytes(), it
+    assert declined <= n_cases // 10, declined
+
+
+def test_device_stroker_degenerate_inputs():
+    P = PathOp
+    cases = [
+        [P.Move(10, 10)],                                              # one point: no segment, nothing drawn
+        [P.Move(10, 10), P.Close()],                                   # joined sub-stroke of one point
+        [P.Move(10, 10), P.Line(10, 10), P.Line(40, 10)],              # coincident points are dropped (stroker.rs:209)
+        [P.Line(30, 30), P.Line(60, 30), P.Line(60, 60), P.Close(), P.Move(5, 5), P.Line(9, 50)],  # Move after Close un-joins (stroker.rs:230-236)
+        [P.Close(), P.Close(), P.Line(3, 3), P.Line(50, 20), P.Close(), P.Close()],
+        [P.Move(20, 20), P.Line(80, 20), P.Line(20, 20), P.Close()],   # a reversal and a closing segment of zero length
+        [P.Move(20, 20), P.Line(50, 20), P.Line(80, 20), P.Line(80, 50), P.Line(80, 80)],  # collinear points, axis-aligned
+        [P.PenWidth(0.0), P.Move(20, 20), P.Line(80, 30), P.Line(30, 80)],  # zero width
+        [P.PenWidth(7.0)],
+    ]
+    for join in JOINS:
+        for k, ops in enumerate(cases):
+            ops = np.array(ops, dtype=OP_DTYPE)
+            g, o = both(100, 100, Format.Matte8, join=join)
+            dev = g.debug_stroke_ops_device(ops)
+            ref = o.debug_stroke_ops(ops)
+            assert dev is not None, (k, str(join))
+            assert len(dev) == len(ref) and dev.tobytes() == ref.tobytes(), (k, str(join))
+
+
+@pytest.mark.parametrize("join", [JoinStyle.Round, JoinStyle.Miter(4.0), JoinStyle.Bevel])
+def test_device_stroker_pixels_4k(join, monkeypatch):
+    """Plotter::stroke with the stroker forced onto the device: flatten -> outline -> fill without leaving HBM."""
+    monkeypatch.setenv("FTL_DEVICE_STROKE", "1")
+    w, h = 3840, 2160
+    base = Raster.with_color(w, h, Format.Rgba8p, (64, 128, 64, 255)).pixels
+    g, o = both(w, h, Format.Rgba8p, init=base, join=join)
+    from footile_b200 import launch_count
+    before = launch_count()
+    for name, path in scenes.stroke_scenes(30.0).items():
+        g.stroke(path, (255, 255, 0, 255))
+        o.stroke(path, (255, 255, 0, 255))
+    assert launch_count() - before > 30 * len(scenes.stroke_scenes(30.0))  # the device stroker's kernels ran
+    assert_same(g, o)
+    # the persistent pen width is the same as after the host path (plotter.rs:151-153)
+    monkeypatch.setenv("FTL_DEVICE_STROKE", "0")
+    g2, _ = both(64, 64, Format.Matte8, join=join)
+    for name, path in scenes.stroke_scenes(30.0).items():
+        g2.stroke(path, (255,))
+    assert g.pen_width() == g2.pen_width()
+
+
+def test_batch_stroke_device_equals_host_path(monkeypatch):
+    paths = list(scenes.stroke_scenes(4.0).values()) + [scenes.fishy_bench(), scenes.fishy_example()[0]]
+    ops, offs = Batch.pack(paths)
+    n = len(paths)
+    tr = np.tile(np.array([1, 0, 0, 0, 1, 0], dtype=np.float32), (n, 1))
+    tr[1] = [0.8, 0.1, 6, -0.1, 1.1, 3]
+    got = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("FTL_DEVICE_STROKE", mode)
+        b = Batch(512, 512, Format.Matte8, n).set_join(JoinStyle.Round)
+        b.stroke(ops, offs, transforms=tr)
+        got[mode] = b.read()
+    assert got["1"].any() and np.array_equal(got["1"], got["0"])
+
+
 # ---- output conversion (examples/fishy.rs:33, examples/png/mod.rs:22-27) on the device ----------------------
 @pytest.mark.parametrize("fmt", [Format.Rgba8p, Format.Graya8p, Format.Matte8])
 def test_read_raster_srgb_matches_oracle_conversion(fmt):

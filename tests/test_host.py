@@ -142,3 +142,14 @@ def test_ch8_mul_by_255_identity():
     for d in range(256):
         got = int(oracle.src_over([d, 0], [0, 0], 0)[0])  # alpha 0: d' = 0 + d*(255-0)
         assert got == (d - 1 if 1 <= d <= 15 else d), d
+
+
+def test_libm_restatement_matches_glibc():
+    """csrc/libm_compat.cuh (what the device stroker evaluates for stroker.rs:305,354,389,407) returns the bits of this
+    host's hypotf / atan2f: 4 x 2 M random inputs (pixel-scale, tie-heavy, mid-exponent and arbitrary bit patterns)."""
+    from footile_b200.plotter import debug_libm_selftest
+    h, a, s_wrong, s_undecided = debug_libm_selftest(2_000_000, 12345)
+    assert (h, a, s_wrong) == (0, 0, 0)
+    # the exhaustive sweep next to +-pi/2 (67 k floats) is decided everywhere; of the `>=` probes only those placed within
+    # 1.2e-7 of their threshold may stay open (half of them are placed there on purpose)
+    assert s_undecided <= 1_000_100
