@@ -541,6 +541,65 @@ def run_batch(D, args, name, batch, fmt, steps, warmup, full=True):
 
     pinned.close()
 
+    # ---- config 3 only: the batched public call alone (no read-back), stroker on the device against stroker on host threads ----
+    if name == "strokes4k" and D.rank == 0:
+        sops, soffs, _ = wl["stroke"]
+        bs = {}
+        keep_env = os.environ.get("FTL_DEVICE_STROKE")
+        for mode, label in (("1", "device_stroker"), ("0", "host_stroker")):
+            os.environ["FTL_DEVICE_STROKE"] = mode
+            for _ in range(3):
+                b.stroke(sops, soffs, colors=colors)
+            b.sync()
+            reps = 20
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                b.stroke(sops, soffs, colors=colors)
+            b.sync()
+            dt = (time.perf_counter() - t0) / reps
+            bs[label] = {"ms_per_step": 1e3 * dt, "strokes_per_s": batch / dt, "value": px_step / dt / 1e9, "unit": "Gpx/s"}
+        if keep_env is None:
+            os.environ.pop("FTL_DEVICE_STROKE", None)
+        else:
+            os.environ["FTL_DEVICE_STROKE"] = keep_env
+        bs["what"] = ("ftl_batch_stroke of %d strokes + ftl_batch_sync, rasters stay in HBM, host wall clock: flatten with widths, outline (stroker.rs:204-416) and fill on the "
+                      "device (stroke_kernels.cuh), against the same call with the outlines made by the host stroker on threads" % batch)
+        line["batch_stroke"] = bs
+
+    # ---- config 4 only: the same paths STROKED (pen width 3, Round joins): the stroker on the device against host threads ----
+    if name == "batch512" and D.rank == 0 and fmt == "matte8":
+        n_jobs = len(wl["offs"]) - 1
+        pw = np.zeros(1, dtype=wl["ops"].dtype)
+        pw["tag"] = 5
+        pw["v"][0, 0] = 3.0
+        sops = np.insert(wl["ops"], np.asarray(wl["offs"][:-1], dtype=np.int64), pw)
+        soffs = np.asarray(wl["offs"], dtype=np.uint64) + np.arange(n_jobs + 1, dtype=np.uint64)
+        b.set_join(fb.JoinStyle.Round)
+        bs = {}
+        keep_env = os.environ.get("FTL_DEVICE_STROKE")
+        sums = {}
+        for mode, label in (("1", "device_stroker"), ("0", "host_stroker")):
+            os.environ["FTL_DEVICE_STROKE"] = mode
+            for _ in range(2):
+                b.stroke(sops, soffs, transforms=wl["tr"])
+            b.sync()
+            sums[label] = b.checksums(0, n_jobs).copy()
+            reps = 5
+            t0 = time.perf_counter()
+            for _ in range(reps):
+                b.stroke(sops, soffs, transforms=wl["tr"])
+            b.sync()
+            dt = (time.perf_counter() - t0) / reps
+            bs[label] = {"ms_per_step": 1e3 * dt, "strokes_per_s": n_jobs / dt}
+        if keep_env is None:
+            os.environ.pop("FTL_DEVICE_STROKE", None)
+        else:
+            os.environ["FTL_DEVICE_STROKE"] = keep_env
+        bs["same_pixels"] = bool(np.array_equal(sums["device_stroker"], sums["host_stroker"]))
+        bs["what"] = ("ftl_batch_stroke of the %d paths of this workload (pen width 3, Round joins) + ftl_batch_sync, rasters stay in HBM, host wall clock: stroker on the "
+                      "device (stroke_kernels.cuh) against the host stroker on 8 threads; same_pixels compares the raster checksums of the two" % n_jobs)
+        line["batch_stroke"] = bs
+
     # ---- config 3 only: the single-plotter call, Plotter::stroke (host flatten + host stroker -> device fill) ----
     if name == "strokes4k" and D.rank == 0:
         from footile_b200 import scenes as _scenes
@@ -564,7 +623,8 @@ def run_batch(D, args, name, batch, fmt, steps, warmup, full=True):
         dt = time.perf_counter() - t0
         n_calls = reps * len(paths)
         line["plotter_stroke"] = {"calls": n_calls, "ms_per_stroke": 1e3 * dt / n_calls, "strokes_per_s": n_calls / dt, "value": px_step / batch * n_calls / dt / 1e9, "unit": "Gpx/s",
-                                  "what": "ftl_stroke through the Plotter mirror, one call per scene, rasters stay in HBM: host flatten + host stroker, one device fill"}
+                                  "what": "ftl_stroke through the Plotter mirror, one call per scene, rasters stay in HBM: the library's default placement of the stroker "
+                                          "(host below 512 ops: these scenes have 3-12 ops each), one device fill"}
         del plotters
 
     # ---- cpu baseline: oracle, one thread, bounded sample (rank 0, N=1 only) ----

@@ -238,12 +238,12 @@ static int stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, std:
     return FTL_OK;
 }
 
-// Where the stroker runs.  FTL_DEVICE_STROKE=1 / 0 forces the device / the host; otherwise a single stroke of a few
-// hundred ops is outlined on the host in microseconds (less than the device path's one synchronisation), larger ones and
-// every batch go to the device (stroke_kernels.cuh).
+// Where the stroker runs.  FTL_DEVICE_STROKE=1 / 0 forces the device / the host; otherwise a stroke of a few hundred ops
+// is outlined on the host in microseconds (less than the device path's launches and its one synchronisation, and it
+// overlaps the device's work on the previous call), larger strokes and batches go to the device (stroke_kernels.cuh).
 static bool stroke_on_device(size_t n_ops, bool batch) {
     if (const char *ev = getenv("FTL_DEVICE_STROKE")) return atoi(ev) != 0;
-    return batch || n_ops >= 512;
+    return n_ops >= (batch ? 2048u : 512u);
 }
 
 // Plotter::stroke with the stroker on the device; *done = false when the host stroker has to take the call.

@@ -156,8 +156,9 @@ int ftl_batch_fill(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const 
 int ftl_batch_set_join(ftl_batch *b, int join, float miter_limit);
 /* n_jobs independent `Plotter::new(raster_j).set_transform(..).stroke(ops_j, color_j)` calls (plotter.rs:356-365) in one
  * pass: flatten with widths, outline (stroker.rs:204-416) and NonZero fill all run on the device, one thread per
- * (point, side) of the outline; the host stroker (threads) takes the batch when the device declines (see ftl_stroke) or
- * FTL_DEVICE_STROKE=0.  Every job starts with pen width 1 like a new Plotter. */
+ * (point, side) of the outline; the host stroker (threads) takes batches of fewer than 2048 ops (microseconds of work
+ * that overlap the device), and any batch the device declines (see ftl_stroke) or when FTL_DEVICE_STROKE=0.  Every job
+ * starts with pen width 1 like a new Plotter. */
 int ftl_batch_stroke(ftl_batch *b, uint32_t n_jobs, const ftl_path_op *ops, const uint64_t *op_offsets, const float *transforms,
                      const uint8_t *colors);
 /* Copy rasters [first, first+count) to host (blocking). */
