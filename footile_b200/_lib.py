@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libfootile_b200.so")
 SYMBOLS = [
     "ftl_abi_version", "ftl_last_error", "ftl_device_count",
     "ftl_plotter_new", "ftl_plotter_new_band", "ftl_plotter_free", "ftl_width", "ftl_height",
-    "ftl_set_tolerance", "ftl_set_transform", "ftl_set_join", "ftl_pen_width",
+    "ftl_set_tolerance", "ftl_set_transform", "ftl_set_join", "ftl_set_strict_vid", "ftl_pen_width",
     "ftl_fill", "ftl_stroke", "ftl_fill_layers", "ftl_stroke_outline", "ftl_read_raster", "ftl_read_raster_srgb", "ftl_write_raster", "ftl_sync", "ftl_raster_device_ptr",
     "ftl_batch_new", "ftl_batch_free", "ftl_batch_set_tolerance", "ftl_batch_clear", "ftl_batch_fill", "ftl_batch_set_join", "ftl_batch_stroke",
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
@@ -57,6 +57,7 @@ def lib():
         "ftl_set_tolerance": (i32, [vp, f32]),
         "ftl_set_transform": (i32, [vp, vp]),
         "ftl_set_join": (i32, [vp, i32, f32]),
+        "ftl_set_strict_vid": (i32, [vp, i32]),
         "ftl_pen_width": (f32, [vp]),
         "ftl_fill": (i32, [vp, i32, vp, sz, vp]),
         "ftl_stroke": (i32, [vp, vp, sz, vp]),

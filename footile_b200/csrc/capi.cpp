@@ -8,9 +8,11 @@
 #include <algorithm>
 #include <new>
 #include <thread>
+#include <utility>
 #include <vector>
 
 #include "engine.h"
+#include "fixed.cuh"
 #include "libm_compat.cuh"
 
 using namespace ftl;
@@ -24,6 +26,7 @@ struct ftl_plotter {
     float s_width = 1.0f;             // plotter.rs:112
     int join = FTL_JOIN_MITER;        // JoinStyle::Miter(4.0) (plotter.rs:113)
     float miter_limit = 4.0f;
+    bool strict_vid = false;          // reproduce Fig::add_point's 65 535-point cap (fig.rs:430)
     explicit ftl_plotter(int device) : eng(device) {}
 };
 
@@ -125,12 +128,74 @@ int ftl_set_transform(ftl_plotter *p, const float e[6]) {
     memcpy(p->e, e, sizeof(p->e));
     return FTL_OK;
 }
+int ftl_set_strict_vid(ftl_plotter *p, int enabled) {
+    if (!p) return bad("null plotter");
+    p->strict_vid = enabled != 0;
+    return FTL_OK;
+}
 int ftl_set_join(ftl_plotter *p, int join, float miter_limit) {
     if (!p) return bad("null plotter");
     if (join < FTL_JOIN_MITER || join > FTL_JOIN_ROUND) return bad("unknown join style");
     p->join = join;
     p->miter_limit = miter_limit;
     return FTL_OK;
+}
+
+static int check_finite_ops(const ftl_path_op *ops, size_t n_ops);
+
+// Strict Vid(u16) mode (ftl_set_strict_vid): the reference keeps vertex ids in a u16 and Fig::add_point ignores every
+// point while 65 535 are stored (fig.rs:428-442, vid.rs:20-24) - a sequential rule, because Fig::close pops a closing
+// point (fig.rs:373-383) and so makes room for one more.  A fill that can reach the cap is therefore taken through
+// the intake on the host: the path is flattened here (the same f32 ops as the device kernel, stroker.cpp), add_point /
+// close are replayed with the cap, and the points that were stored travel on as Move / Line ops under the identity
+// transform (1*x + 0*y + 0 is x), one Move per sub-figure.  Returns false when the cap is never reached: the fill
+// then takes the ordinary path unchanged.
+static bool strict_intake(const float e[6], float tol_sq, const ftl_path_op *ops, size_t n_ops, std::vector<ftl_path_op> *out) {
+    bool curves = false;
+    for (size_t i = 0; i < n_ops && !curves; i++) curves = ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC;
+    if (!curves && n_ops < 65535) return false;  // one point per Move / Line at most
+    std::vector<float> opw(2 * n_ops, 0.0f);
+    WideFlat flat;
+    flatten_wide_host(e, tol_sq, ops, n_ops, opw.data(), &flat);
+    if (flat.xyw.size() / 3 < 65535) return false;
+    out->clear();
+    size_t stored = 0, at = 0;              // points.len()
+    std::vector<std::pair<fx_t, fx_t>> sub;  // the points of the current sub-figure
+    bool done = false, capped = false;
+    auto close = [&]() {  // Fig::close (fig.rs:457-461) -> sub_set_done (fig.rs:373-383)
+        if (stored == 0 || sub.empty()) return;
+        if (sub.back() == sub.front()) {  // the closing point is popped (also the only point of a one-point sub-figure)
+            sub.pop_back();
+            stored--;
+        }
+        done = true;
+    };
+    for (size_t i = 0; i < n_ops; i++) {
+        if (ops[i].tag == FTL_OP_CLOSE || ops[i].tag == FTL_OP_MOVE) close();
+        for (uint32_t k = 0; k < flat.counts[i]; k++, at++) {
+            if (stored >= 65535) {  // fig.rs:430
+                capped = true;
+                continue;
+            }
+            const std::pair<fx_t, fx_t> q(fx_from_f32(flat.xyw[3 * at]), fx_from_f32(flat.xyw[3 * at + 1]));
+            const bool start = done || stored == 0;
+            // is_coincident compares with points.last(): the current sub-figure's last point (a sub-figure emptied by a
+            // pop is always `done`, so `start` covers it)
+            if (start || q != sub.back()) {
+                if (start) {
+                    sub.clear();
+                    done = false;
+                }
+                ftl_path_op o{};
+                o.tag = start ? FTL_OP_MOVE : FTL_OP_LINE;
+                o.v[0] = flat.xyw[3 * at]; o.v[1] = flat.xyw[3 * at + 1];
+                out->push_back(o);
+                sub.push_back(q);
+                stored++;
+            }
+        }
+    }
+    return capped;
 }
 
 static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_ops, const uint8_t *color, bool upload_only = false) {
@@ -140,6 +205,20 @@ static int plot_fill(ftl_plotter *p, int rule, const ftl_path_op *ops, size_t n_
     HostJob &j = jobs[0];
     j.op_begin = 0; j.op_end = (uint32_t)n_ops;
     memcpy(j.e, p->e, sizeof(j.e));
+    std::vector<ftl_path_op> strict_ops;
+    if (p->strict_vid && n_ops) {
+        int rc0 = check_finite_ops(ops, n_ops);
+        if (rc0) return rc0;
+        if (strict_intake(p->e, p->tol_sq, ops, n_ops, &strict_ops)) {
+            for (size_t i = 0; i < n_ops; i++)  // PenWidth persists on the plotter (plotter.rs:151-153)
+                if (ops[i].tag == FTL_OP_PENWIDTH) p->s_width = ops[i].v[0];
+            ops = strict_ops.data();
+            n_ops = strict_ops.size();
+            j.op_end = (uint32_t)n_ops;
+            const float ident[6] = {1, 0, 0, 0, 1, 0};
+            memcpy(j.e, ident, sizeof(j.e));
+        }
+    }
     j.tol_sq = p->tol_sq;
     j.rule = rule;
     if (color) memcpy(j.color, color, p->geo.bpp());

@@ -116,6 +116,11 @@ class Plotter:
         _lib.check(_lib.lib().ftl_set_join(self._handle, js.kind, js.limit))
         return self
 
+    def set_strict_vid(self, on=True):
+        """Reproduce the reference's Vid(u16) cap: Fig::add_point ignores points while 65 535 are stored (fig.rs:430)."""
+        _lib.check(_lib.lib().ftl_set_strict_vid(self._handle, 1 if on else 0))
+        return self
+
     def pen_width(self):
         return float(_lib.lib().ftl_pen_width(self._handle))
 

@@ -22,7 +22,7 @@
  *     Fig::add_point silently drops every point once 65 535 are stored (src/fig.rs:430); fills here
  *     render all points (up to 2^31 - 1 per call).  The stroker keeps the reference's cap per
  *     stroke (src/stroker.rs:63).  Inputs that stay below 65 535 flattened points per fill - every
- *     example and benchmark of the reference - are unaffected;
+ *     example and benchmark of the reference - are unaffected; ftl_set_strict_vid(p, 1) restores the cap;
  *   - curve subdivision is capped at depth 16 (the reference recurses without bound, README.md:32-33);
  *   - NaN/Inf coordinates are rejected with FTL_ERR_NONFINITE instead of recursing forever.
  */
@@ -97,6 +97,11 @@ uint32_t ftl_height(const ftl_plotter *p);                  /* Plotter::height (
 int ftl_set_tolerance(ftl_plotter *p, float t);             /* Plotter::set_tolerance, clamped >= 0.01 (plotter.rs:133-137) */
 int ftl_set_transform(ftl_plotter *p, const float e[6]);    /* Plotter::set_transform (plotter.rs:140-143); e = pointy Transform rows [a b tx; c d ty] */
 int ftl_set_join(ftl_plotter *p, int join, float miter_limit); /* Plotter::set_join (plotter.rs:158-161) */
+/* Strict Vid(u16) mode, off by default: ftl_fill then reproduces the reference's vertex cap - Fig::add_point ignores
+ * points while 65 535 are stored (fig.rs:428-442, vid.rs:20-24).  Fills that stay below the cap are unaffected; one
+ * that reaches it has its point intake replayed on the host (sequential by nature: a Fig::close can pop a point and
+ * make room again) before the device rasterises the surviving points.  Applies to ftl_fill / ftl_fill_upload. */
+int ftl_set_strict_vid(ftl_plotter *p, int enabled);
 float ftl_pen_width(const ftl_plotter *p);                  /* the persistent s_width (plotter.rs:53,151-153) */
 
 /* Plotter::fill(rule, ops, clr) (plotter.rs:339-350).  color: bpp bytes

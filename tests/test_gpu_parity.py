@@ -1027,6 +1027,76 @@ def test_batch_stroke_device_equals_host_path(monkeypatch):
     assert got["1"].any() and np.array_equal(got["1"], got["0"])
 
 
+# ---- strict Vid(u16) mode: Fig::add_point's 65 535-point cap (fig.rs:428-442) -----------------------------------
+@pytest.mark.parametrize("curved", [False, True])
+def test_strict_vid_mode_reproduces_the_point_cap(curved):
+    """ftl_set_strict_vid(1): points are ignored while 65 535 are stored, a Fig::close that pops a point makes room for
+    one more (the oracle's default vid_cap is the reference's); without the flag every point is drawn (u32 ids)."""
+    rng = np.random.default_rng(65535)
+    p = Path2D().absolute()
+    n_sub = 40 if curved else 90
+    for s in range(n_sub):  # closed sub-figures of ~800 points each: the cap falls inside one of them
+        cx, cy = rng.uniform(40, 216, 2)
+        p = p.move_to(cx, cy)
+        if curved:
+            for k in range(60):
+                p = p.quad_to(*(np.array([cx, cy, cx, cy]) + rng.uniform(-40, 40, 4)))
+        else:
+            for k in range(799):
+                p = p.line_to(cx + rng.uniform(-30, 30), cy + rng.uniform(-30, 30))
+        p = p.line_to(cx, cy).close()  # the closing point equals the first: popped by Fig::close
+    ops = p.finish()
+    tol = 0.01 if curved else None
+    g, o = both(256, 256, Format.Matte8, tol=tol)
+    g.set_strict_vid(True)
+    g.fill(FillRule.EvenOdd, ops, (255,))
+    o.fill(oracle.EVENODD, ops, (255,))
+    assert 65500 <= o.last_info()["n_points"] <= 65535, o.last_info()  # the oracle did hit the cap (closing points popped since)
+    assert_same(g, o, "strict")
+    assert g.debug_last_fill() == o.last_info()
+    strict = g.raster().pixels.copy()
+    g2, o2 = both(256, 256, Format.Matte8, tol=tol, vid_cap=1 << 30)
+    g2.fill(FillRule.EvenOdd, ops, (255,))
+    o2.fill(oracle.EVENODD, ops, (255,))
+    assert_same(g2, o2, "u32 ids")
+    assert not np.array_equal(strict, g2.raster().pixels)
+    # a fill below the cap is untouched by the flag
+    small = scenes.fishy_example()[0]
+    g3, o3 = both(128, 128, Format.Matte8)
+    g3.set_strict_vid(True)
+    g3.fill(FillRule.NonZero, small, (255,))
+    o3.fill(oracle.NONZERO, small, (255,))
+    assert_same(g3, o3, "below the cap")
+
+
+def test_strict_vid_mode_a_popped_closing_point_makes_room():
+    """65 533 distinct points and the closing point (= the first, popped by Fig::close, fig.rs:376-380) leave room for two
+    more: of the triangle that follows only A and B are stored, the next triangle is ignored altogether."""
+    n = 65533
+    th = np.linspace(0.0, 2 * np.pi, n, endpoint=False)
+    xs, ys = 128 + 100 * np.cos(th), 128 + 100 * np.sin(th)
+    p = Path2D().absolute().move_to(xs[0], ys[0])
+    for k in range(1, n):
+        p = p.line_to(xs[k], ys[k])
+    p = p.line_to(xs[0], ys[0]).close()
+    p = p.move_to(100, 100).line_to(160, 110).line_to(120, 170).close()
+    p = p.move_to(60, 60).line_to(90, 70).line_to(70, 95).close()
+    ops = p.finish()
+    g, o = both(256, 256, Format.Matte8)
+    g.set_strict_vid(True)
+    g.fill(FillRule.EvenOdd, ops, (255,))
+    o.fill(oracle.EVENODD, ops, (255,))
+    assert o.last_info()["n_points"] == 65535
+    assert_same(g, o, "strict")
+    assert g.debug_last_fill() == o.last_info()
+    assert g.raster().pixels[120, 125] == 255  # inside the circle and inside the (undrawn) first triangle: EvenOdd would have cleared it
+    g2, o2 = both(256, 256, Format.Matte8, vid_cap=1 << 30)
+    g2.fill(FillRule.EvenOdd, ops, (255,))
+    o2.fill(oracle.EVENODD, ops, (255,))
+    assert_same(g2, o2, "u32 ids")
+    assert g2.raster().pixels[120, 125] == 0
+
+
 # ---- output conversion (examples/fishy.rs:33, examples/png/mod.rs:22-27) on the device ----------------------
 @pytest.mark.parametrize("fmt", [Format.Rgba8p, Format.Graya8p, Format.Matte8])
 def test_read_raster_srgb_matches_oracle_conversion(fmt):
