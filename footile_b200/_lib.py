@@ -20,7 +20,7 @@ SYMBOLS = [
     "ftl_batch_read", "ftl_batch_checksums", "ftl_batch_sync", "ftl_batch_device_ptr",
     "ftl_batch_upload", "ftl_batch_run", "ftl_batch_stream", "ftl_stream", "ftl_fill_upload", "ftl_fill_replay",
     "ftl_ctx_new", "ftl_ctx_free", "ftl_ctx_size", "ftl_shard_range", "ftl_band_rows", "ftl_ctx_fill_batch", "ftl_ctx_fill_bands",
-    "ftl_launch_count", "ftl_transfer_bytes", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_time_fills",
+    "ftl_launch_count", "ftl_transfer_bytes", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_plotter_tile_kernel_time", "ftl_batch_tile_kernel_time", "ftl_time_fills",
     "ftl_debug_area", "ftl_debug_small_profile", "ftl_batch_debug_top_rows", "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
     "ftl_debug_stroke_ops_device", "ftl_debug_libm_selftest",
 ]
@@ -96,6 +96,8 @@ def lib():
         "ftl_transfer_bytes": (i32, [i32, vp, vp]),
         "ftl_set_profiling": (i32, [i32]),
         "ftl_tile_kernel_time": (i32, [i32, vp, vp]),
+        "ftl_plotter_tile_kernel_time": (i32, [vp, i32, vp, vp]),
+        "ftl_batch_tile_kernel_time": (i32, [vp, i32, vp, vp]),
         "ftl_time_fills": (i32, [vp, i32, vp, sz, vp, u32, i32, vp]),
         "ftl_debug_flatten": (i32, [vp, vp, sz, vp, sz, vp, vp, sz, vp]),
         "ftl_debug_last_fill": (i32, [vp, vp]),

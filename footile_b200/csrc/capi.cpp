@@ -650,6 +650,16 @@ int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches) {
     Engine::tile_kernel_time(reset != 0, ms, launches);
     return FTL_OK;
 }
+int ftl_plotter_tile_kernel_time(ftl_plotter *p, int reset, double *ms, uint64_t *launches) {
+    if (!p) return bad("null plotter");
+    p->eng.tile_time(reset != 0, ms, launches);
+    return FTL_OK;
+}
+int ftl_batch_tile_kernel_time(ftl_batch *b, int reset, double *ms, uint64_t *launches) {
+    if (!b) return bad("null batch");
+    b->eng.tile_time(reset != 0, ms, launches);
+    return FTL_OK;
+}
 
 // Per-call latency of Plotter::fill through this ABI, timed inside the library so that no binding overhead is counted:
 // `iters` calls of ftl_fill (+ ftl_sync after each one when sync_each != 0, one ftl_sync at the end otherwise).

@@ -126,13 +126,13 @@ struct PinBuf {
     }
 };
 
+// Tile-kernel timing (CUDA events around every tile launch while profiling is on) is kept PER ENGINE, so that two handles
+// profiling at the same time do not mix their numbers; the process-wide query sums over the live engines.
 struct ProfSpan {
     cudaEvent_t a, b;
 };
-static std::vector<ProfSpan> g_spans;
-static std::mutex g_spans_mu;
-static double g_tile_ms = 0.0;
-static uint64_t g_tile_launches = 0;
+static std::vector<Engine::Impl *> g_engines;  // live engines, for the process-wide sum
+static std::mutex g_engines_mu;
 
 struct Engine::Impl {
     cudaStream_t st = nullptr;
@@ -160,6 +160,30 @@ struct Engine::Impl {
     // device stroker (stroke_kernels.cuh): inputs in one blob, then the intermediate arrays; capacities persist
     DevBuf s_in, s_wop, s_keep, s_kidx, s_kp, s_info, s_cnt2, s_off2, s_counters, s_part;
     PinBuf pin_stroke;
+    std::vector<ProfSpan> spans;          // tile launches timed but not yet collected
+    std::mutex spans_mu;
+    double tile_ms = 0.0;
+    uint64_t tile_launches = 0;
+    // fold the finished spans into (tile_ms, tile_launches); returns them, optionally resetting
+    void collect_tile_time(bool reset, double *ms, uint64_t *launches) {
+        std::lock_guard<std::mutex> lock(spans_mu);
+        for (ProfSpan &s : spans) {
+            float t = 0.f;
+            if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
+                tile_ms += t;
+                tile_launches++;
+            }
+            cudaEventDestroy(s.a);
+            cudaEventDestroy(s.b);
+        }
+        spans.clear();
+        *ms += tile_ms;
+        *launches += tile_launches;
+        if (reset) {
+            tile_ms = 0.0;
+            tile_launches = 0;
+        }
+    }
     bool skip_graph = false;              // the next pipeline pass runs once with these sizes: do not capture a graph for it
     PinBuf pin_ops, pin_jobs, pin_small, pin_misc;
     PinBuf pin_ring, pin_pack[2], pin_lit[2];
@@ -206,29 +230,39 @@ void Engine::transfer_bytes(bool reset, uint64_t *h2d, uint64_t *d2h) {
 }
 void Engine::set_profiling(bool on) { g_profiling.store(on); }
 void Engine::tile_kernel_time(bool reset, double *ms, uint64_t *launches) {
-    std::lock_guard<std::mutex> lock(g_spans_mu);
-    for (ProfSpan &s : g_spans) {
-        float t = 0.f;
-        if (cudaEventSynchronize(s.b) == cudaSuccess && cudaEventElapsedTime(&t, s.a, s.b) == cudaSuccess) {
-            g_tile_ms += t;
-            g_tile_launches++;
-        }
-        cudaEventDestroy(s.a);
-        cudaEventDestroy(s.b);
-    }
-    g_spans.clear();
-    if (ms) *ms = g_tile_ms;
-    if (launches) *launches = g_tile_launches;
-    if (reset) {
-        g_tile_ms = 0.0;
-        g_tile_launches = 0;
-    }
+    double t = 0.0;
+    uint64_t n = 0;
+    std::lock_guard<std::mutex> lock(g_engines_mu);
+    for (Engine::Impl *m : g_engines) m->collect_tile_time(reset, &t, &n);
+    if (ms) *ms = t;
+    if (launches) *launches = n;
+}
+void Engine::tile_time(bool reset, double *ms, uint64_t *launches) {
+    double t = 0.0;
+    uint64_t n = 0;
+    cudaSetDevice(device_);
+    impl_->collect_tile_time(reset, &t, &n);
+    if (ms) *ms = t;
+    if (launches) *launches = n;
 }
 
-Engine::Engine(int device) : impl_(new Impl()), device_(device), stream_(nullptr) {}
+Engine::Engine(int device) : impl_(new Impl()), device_(device), stream_(nullptr) {
+    std::lock_guard<std::mutex> lock(g_engines_mu);
+    g_engines.push_back(impl_);
+}
 
 Engine::~Engine() {
     if (impl_) {
+        {
+            std::lock_guard<std::mutex> lock(g_engines_mu);
+            g_engines.erase(std::remove(g_engines.begin(), g_engines.end(), impl_), g_engines.end());
+        }
+        {
+            double t = 0.0;
+            uint64_t n = 0;
+            if (impl_->st) cudaSetDevice(device_);
+            impl_->collect_tile_time(false, &t, &n);  // destroys the events of spans nobody collected
+        }
         if (impl_->st) {
             cudaSetDevice(device_);
             cudaStreamSynchronize(impl_->st);
@@ -1060,8 +1094,8 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
         }
         if (prof) {
             CK(cudaEventRecord(span.b, st));
-            std::lock_guard<std::mutex> lock(g_spans_mu);
-            g_spans.push_back(span);
+            std::lock_guard<std::mutex> lock(m.spans_mu);
+            m.spans.push_back(span);
         }
     }
     CK(cudaGetLastError());

@@ -105,7 +105,8 @@ public:
     static uint64_t launch_count();
     static void transfer_bytes(bool reset, uint64_t *h2d, uint64_t *d2h);
     static void set_profiling(bool on);
-    static void tile_kernel_time(bool reset, double *ms, uint64_t *launches);
+    static void tile_kernel_time(bool reset, double *ms, uint64_t *launches);  // summed over the live engines of the process
+    void tile_time(bool reset, double *ms, uint64_t *launches);                // this engine's tile launches only
 
     struct Impl;
 

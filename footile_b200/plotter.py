@@ -191,6 +191,12 @@ class Plotter:
         _lib.check(_lib.lib().ftl_sync(self._handle))
         return self
 
+    def tile_kernel_time(self, reset=False):
+        """(ms, launches) of this handle's tile kernels while profiling is on (the state is per handle)."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _lib.check(_lib.lib().ftl_plotter_tile_kernel_time(self._handle, 1 if reset else 0, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
+
     def raster(self):
         """Read the owned rows back: Raster of (rows, width)."""
         n_rows = self._rows[1] - self._rows[0]
@@ -368,6 +374,12 @@ class Batch:
     def sync(self):
         _lib.check(_lib.lib().ftl_batch_sync(self._handle))
         return self
+
+    def tile_kernel_time(self, reset=False):
+        """(ms, launches) of this handle's tile kernels while profiling is on (the state is per handle)."""
+        ms, n = C.c_double(0), C.c_uint64(0)
+        _lib.check(_lib.lib().ftl_batch_tile_kernel_time(self._handle, 1 if reset else 0, C.byref(ms), C.byref(n)))
+        return ms.value, int(n.value)
 
     def read(self, first=0, count=None, out=None):
         count = self.capacity - first if count is None else count

@@ -225,7 +225,10 @@ int ftl_transfer_bytes(int reset, uint64_t *h2d, uint64_t *d2h);
  * profiling is enabled via ftl_set_profiling(1) (adds two event records per
  * launch; off by default). */
 int ftl_set_profiling(int enabled);
-int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches);
+int ftl_tile_kernel_time(int reset, double *ms, uint64_t *launches);          /* summed over the live handles of the process */
+/* The same for one handle: the timing state lives in the handle, so handles profiled at the same time do not mix. */
+int ftl_plotter_tile_kernel_time(ftl_plotter *p, int reset, double *ms, uint64_t *launches);
+int ftl_batch_tile_kernel_time(ftl_batch *b, int reset, double *ms, uint64_t *launches);
 
 /* Per-call latency of ftl_fill (benches/fishyb.rs:10-39 times exactly this call), measured inside the library so that
  * no binding overhead is counted: iters calls, each followed by ftl_sync when sync_each != 0 (otherwise one at the end). */

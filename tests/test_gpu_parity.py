@@ -1097,6 +1097,33 @@ def test_strict_vid_mode_a_popped_closing_point_makes_room():
     assert g2.raster().pixels[120, 125] == 0
 
 
+def test_profiling_state_is_per_handle():
+    from footile_b200 import set_profiling, tile_kernel_time
+    tile_kernel_time(reset=True)
+    set_profiling(True)
+    try:
+        a = Plotter(Raster(256, 256, Format.Matte8))
+        b = Plotter(Raster(256, 256, Format.Matte8))
+        import os
+        os.environ["FTL_NO_SMALL"] = "1"  # the one-launch small fill is not a tile-kernel launch
+        try:
+            for _ in range(3):
+                a.fill(FillRule.NonZero, scenes.fishy_bench(), (255,))
+            b.fill(FillRule.NonZero, scenes.fishy_bench(), (255,))
+        finally:
+            os.environ.pop("FTL_NO_SMALL", None)
+        a.sync(); b.sync()
+        ms_a, n_a = a.tile_kernel_time()
+        ms_b, n_b = b.tile_kernel_time(reset=True)
+        assert n_a == 3 * n_b and n_b >= 1 and ms_a > 0 and ms_b > 0
+        ms_all, n_all = tile_kernel_time()
+        assert n_all == n_a  # b was reset; the process-wide figure sums the live handles
+        assert b.tile_kernel_time() == (0.0, 0)
+    finally:
+        set_profiling(False)
+        tile_kernel_time(reset=True)
+
+
 # ---- output conversion (examples/fishy.rs:33, examples/png/mod.rs:22-27) on the device ----------------------
 @pytest.mark.parametrize("fmt", [Format.Rgba8p, Format.Graya8p, Format.Matte8])
 def test_read_raster_srgb_matches_oracle_conversion(fmt):
