@@ -248,8 +248,8 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
                     *q4 = t;
                 }
             } else {
-#pragma unroll
-                for (uint32_t i = 0; i < 4; i++)
+#pragma unroll 1
+                for (uint32_t i = 0; i < 4; i++)  // ragged end of a row: rolled, the general blend is large
                     if (x + 4 * j + i < W) d[4 * j + i] = blend_rgba(d[4 * j + i], color, (w >> (8 * i)) & 0xFF, clr_a);
             }
         }
@@ -289,8 +289,8 @@ __device__ __forceinline__ void emit16(uint8_t *dst, uint32_t x, uint32_t W, uin
             }
             return;
         }
-#pragma unroll
-        for (uint32_t i = 0; i < 16; i++) {
+#pragma unroll 1
+        for (uint32_t i = 0; i < 16; i++) {  // ragged end of a row: rolled, the general blend is large
             uint32_t w = i < 4 ? a0 : (i < 8 ? a1 : (i < 12 ? a2 : a3));
             if (x + i < W) {
                 uint32_t al = (w >> (8 * (i & 3))) & 0xFF, p = d[i];
@@ -356,6 +356,48 @@ __device__ __forceinline__ void fill_const(uint8_t *drow, uint32_t lo, uint32_t 
             }
             p[u] = t;
         }
+    }
+}
+
+// Alpha 0 over a long span, staged through the warp's shared-memory window.  The register version above has four
+// 16-byte loads in flight per lane and pays one DRAM round trip per 2 KiB of the span (plus one per leftover 512 bytes):
+// the Rgba8p / Graya8p composite of a scene that is mostly background is bound by exactly that latency.  Here every
+// lane copies its 16-byte words with cp.async into the window (no registers held), two half-windows in flight, and tests
+// them from shared memory: one round trip per half-window (4 KiB for the usual 8 KiB window), the next one already under
+// way.  Every lane reads back only what it copied itself, so no warp synchronisation is needed.  The window must be
+// re-zeroed before the scatter path uses it again (the caller keeps a `dirty` flag).
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(saddr), "l"(g) : "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ uint4 slds_u4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a) : "memory");
+    return v;
+}
+__device__ __forceinline__ void fill_zero_staged(uint8_t *drow, uint32_t u0, uint32_t end, uint32_t stage, uint32_t half_u4) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint4 *p = reinterpret_cast<uint4 *>(drow);
+    const uint32_t nb = (end - u0 + half_u4 - 1u) / half_u4;
+    const uint32_t my = stage + lane * 16u;
+    auto issue = [&](uint32_t b) {
+        const uint32_t sbase = my + (b & 1u) * half_u4 * 16u;
+        uint32_t u = u0 + b * half_u4 + lane;
+        const uint32_t stop = min(end, u0 + (b + 1u) * half_u4);
+#pragma unroll 2
+        for (uint32_t k = 0; u < stop; u += 32, k++) cp_async16(sbase + k * 512u, p + u);
+        cp_async_commit();
+    };
+    issue(0);
+    if (nb > 1) issue(1);
+#pragma unroll 1
+    for (uint32_t b = 0; b < nb; b++) {
+        if (b + 1 < nb) asm volatile("cp.async.wait_group 1;" ::: "memory");
+        else asm volatile("cp.async.wait_group 0;" ::: "memory");
+        const uint32_t sbase = my + (b & 1u) * half_u4 * 16u;
+        uint32_t u = u0 + b * half_u4 + lane;
+        const uint32_t stop = min(end, u0 + (b + 1u) * half_u4);
+#pragma unroll 2
+        for (uint32_t k = 0; u < stop; u += 32, k++) mul255_rmw(p + u, slds_u4(sbase + k * 512u));
+        if (b + 2 < nb) issue(b + 2);
     }
 }
 
@@ -499,7 +541,7 @@ __device__ __forceinline__ uint32_t rule_alpha_rt(int32_t sum, bool even_odd) {
 // Returns the rows (bit r) that were NOT drawn and need the shared-memory path.
 template <int FMT>
 __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32_t my_r, int32_t n_rows, int32_t W, uint8_t *dst, uint32_t pitch,
-                                                  bool even_odd, uint32_t color) {
+                                                  bool even_odd, uint32_t color, uint32_t stage, uint32_t half_u4, bool &dirty) {
     const uint32_t clr_a = FMT == FTL_RGBA8P ? (color >> 24) : ((color >> 8) & 0xFF);
     const uint32_t ngroups = (uint32_t)W >> 4;
     const bool active = st.cov > 0 && (int32_t)my_r < n_rows;
@@ -579,19 +621,52 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
             a[0] = a[1] = a[2] = a[3] = after;  // the span continues in the next group
         }
     }
-    // ---- the constant spans: right of every span, and left of the first one ----
+    // ---- the constant spans: left of the first span of every row, then right of every span ----
+    // ONE loop and one call site for both kinds (the fill routines are large, and this kernel's hot path must stay inside
+    // the instruction cache): iterations 0 .. n_rows - 1 are the leading spans, the rest walk the owners.
     const uint32_t owners = __ballot_sync(0xFFFFFFFFu, active && row_ok);
-    const uint32_t my_span = (gb + 1u) | (next_ga << 16);
+    if (FMT != FTL_RGBA8P) {  // Matte8 (plain stores) and Graya8p (8 KiB rows: one or two round trips per span anyway): two tight loops; the merged loop below costs them 7-9 %
+        const uint32_t my_span8 = (gb + 1u) | (next_ga << 16);
 #pragma unroll 1
-    for (uint32_t m = owners; m; m &= m - 1) {
-        const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
-        const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span, s), q = __shfl_sync(0xFFFFFFFFu, after_a, s);
-        fill_const<FMT>(dst + (size_t)(s >> 3) * pitch, sp & 0xFFFFu, sp >> 16, q, color, clr_a);
+        for (uint32_t mm = owners; mm; mm &= mm - 1) {
+            const uint32_t s = (uint32_t)__ffs((int)mm) - 1u;
+            const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span8, s), q = __shfl_sync(0xFFFFFFFFu, after_a, s);
+            fill_const<FMT>(dst + (size_t)(s >> 3) * pitch, sp & 0xFFFFu, sp >> 16, q, color, clr_a);
+        }
+#pragma unroll 1
+        for (int r = 0; r < n_rows; r++) {
+            const uint32_t hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
+            if (!((redo >> r) & 1u)) fill_const<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, color, clr_a);
+        }
+        return redo;
     }
+    const uint32_t my_span = (gb + 1u) | (next_ga << 16);
+    constexpr uint32_t U = 4u;  // 16-byte words per 16-pixel group of Rgba8p
+    uint32_t m = owners;
 #pragma unroll 1
-    for (int r = 0; r < n_rows; r++) {
-        const uint32_t hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
-        if (!((redo >> r) & 1u)) fill_const<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, color, clr_a);
+    for (int it = 0;; it++) {
+        uint32_t row, lo, hi, q;
+        if (it < n_rows) {
+            row = (uint32_t)it;
+            lo = 0u;
+            hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * it), ngroups);
+            q = 0u;
+            if ((redo >> it) & 1u) continue;
+        } else {
+            if (!m) break;
+            const uint32_t s = (uint32_t)__ffs((int)m) - 1u;
+            m &= m - 1;
+            const uint32_t sp = __shfl_sync(0xFFFFFFFFu, my_span, s);
+            q = __shfl_sync(0xFFFFFFFFu, after_a, s);
+            row = s >> 3;
+            lo = sp & 0xFFFFu;
+            hi = sp >> 16;
+        }
+        uint8_t *d = dst + (size_t)row * pitch;
+        if (q == 0u && half_u4 && hi > lo && (hi - lo) * U > 128u) {
+            fill_zero_staged(d, lo * U, hi * U, stage, half_u4);
+            dirty = true;
+        } else fill_const<FMT>(d, lo, hi, q, color, clr_a);
     }
     return redo;
 }
@@ -619,6 +694,11 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
     const uint32_t n_warps = gridDim.x * warps_per_cta;
     // analytic rows need full 16-pixel groups on 16-byte boundaries (and group indices below 0xFFFF)
     const bool analytic_ok = ALIGNED && (P.W & 15u) == 0 && (P.W >> 4) < 0xFFFFu;
+    // the analytic rows use the (otherwise idle) cell window as a staging area for long alpha-0 spans: two halves of a
+    // power-of-two number of 16-byte words; `dirty`: the window no longer holds the zeros the scatter path relies on
+    const uint32_t win_u4 = (P.win_rows * P.win_chunks * CHUNK) / 4u;
+    const uint32_t half_u4 = FMT != FTL_RGBA8P || win_u4 < 256u ? 0u : (1u << (31 - __clz(win_u4))) / 2u;
+    bool dirty = false;
     uint32_t j = (P.tile_begin + blockIdx.x * warps_per_cta + warp) / P.n_bands, j_next = 0;
     for (uint32_t tile = P.tile_begin + blockIdx.x * warps_per_cta + warp; tile < P.tile_end; tile += n_warps, j = j_next) {
         const uint32_t band = tile - j * P.n_bands;
@@ -664,7 +744,12 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
             const int32_t rr_end = min(rows_per_pass, row_hi - ry_base);
             uint32_t redo = 0xFFFFFFFFu;
             if (ry_base + rows_per_pass >= row_hi && vb_next + lane < ve_next && lane < 8) prefetch_l1(&E[vb_next + lane]);  // last pass
-            if (analytic_ok && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color);
+            if (analytic_ok && gl == 3u) redo = analytic_rows<FMT>(st, my_r, rr_end, W, dst, P.pitch, rule == FTL_EVENODD, color, cells, half_u4, dirty);
+            if (dirty && redo) {  // rows for the scatter path follow: give it back a window of zeros
+                for (uint32_t i = lane; i < win_u4; i += 32) ssts4_zero(cells + 16u * i);
+                __syncwarp();
+                dirty = false;
+            }
             const int32_t ry_last = ry_base + rr_end - 1;
             for (int32_t rr = 0; rr < rr_end; rr++, dst += P.pitch) {
                 if (!((redo >> rr) & 1u)) continue;
