@@ -378,7 +378,7 @@ __global__ void __launch_bounds__(32) raster_bins(const EdgeRec *__restrict__ E,
         }
         const uint32_t j = P.job_begin + jb / P.b_nbands, band = jb % P.b_nbands;
         const JobState js = JS[j];
-        if (js.vtx_end - js.vtx_begin <= DIRECT_MAX) continue;  // drawn by raster_tiles from the job's own edge range
+        if (js.vtx_end - js.vtx_begin <= P.direct_max) continue;  // drawn by raster_tiles from the job's own edge range
         const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << BIN_LOG2R);
         const int32_t row = row0 + (int32_t)lane;
         const bool row_ok = row >= js.first_row && row < (int32_t)P.row_end;  // rows above the figure are untouched (fig.rs:497)

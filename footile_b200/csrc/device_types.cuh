@@ -47,7 +47,7 @@ struct __align__(16) EdgeRec {  // 32 B: one per ring segment whose end points d
     uint32_t job;
     uint32_t flags;     // bit0 valid, bit1 set when the edge runs against the figure direction (sign -1, fig.rs:286)
 };
-constexpr uint32_t DIRECT_MAX = 64;  // jobs with at most this many edge slots skip binning: raster_tiles scans the job's own edges; larger jobs go to raster_bins
+constexpr uint32_t DIRECT_MAX = 64;  // upper bound of Params::direct_max: jobs with at most direct_max edge slots skip binning (raster_tiles scans the job's own edges); larger jobs go to raster_bins
 
 struct __align__(8) SumHead {  // scan element over ops: vertex count + position of the last sub-figure head
     uint32_t sum, head;
@@ -80,5 +80,6 @@ struct Params {  // per-call constants, passed by value
     uint32_t b_lookback;                         // 1: one (band, window) tile per ticket, row sums passed through `look`; 0: a ticket walks all windows of a band
     uint32_t job_begin, job_end;                 // jobs this launch of the binned kernel covers
     uint32_t has_curves;                         // the job set holds Quad / Cubic ops (flatten parks their points between its two passes)
+    uint32_t direct_max;                         // jobs with at most this many edge slots (<= DIRECT_MAX) are drawn by raster_tiles, larger ones by raster_bins
     uint32_t cull;                               // 1: flatten only the sub-figures that can reach rows [row_begin, row_end) or hold the top vertex
 };

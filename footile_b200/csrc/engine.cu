@@ -440,6 +440,15 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     return FTL_OK;
 }
 
+// Jobs of at most this many edge slots are drawn by raster_tiles straight from their own edge range (no binning).
+// 8 = the jobs whose rows can take the analytic path (tile_kernel.cuh); anything larger is faster through the bins:
+// raster_tiles' lanes-are-edges scatter of 9..64 edges measured 2.56 ms on the batched fishy fills (33 edges, 256^2)
+// against 0.42 ms for raster_bins, and 0.35 against 0.24 ms on the 4K stroke scenes.  FTL_DIRECT_MAX (1 .. 64): tuning knob.
+static uint32_t direct_max_setting() {
+    if (const char *ev = getenv("FTL_DIRECT_MAX")) return (uint32_t)std::min<int>((int)DIRECT_MAX, std::max(1, atoi(ev)));
+    return 8u;
+}
+
 static int validate_ops(const ftl_path_op *ops, size_t n) {
     for (size_t i = 0; i < n; i++) {
         int nv = ops[i].tag == FTL_OP_CLOSE ? 0 : (ops[i].tag == FTL_OP_QUAD ? 4 : (ops[i].tag == FTL_OP_CUBIC ? 6 : (ops[i].tag == FTL_OP_PENWIDTH ? 1 : 2)));
@@ -524,6 +533,7 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     int rc = FTL_OK;
     Params P{};
     // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
+    P.direct_max = direct_max_setting();
     P.all_direct = 1;
     P.all_tiny = 1;
     P.has_curves = 0;
@@ -531,7 +541,7 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     for (size_t jx = 0; jx < jobs.size(); jx++) {
         const HostJob &h = jobs[jx];
         if (h.op_end - h.op_begin > 8u) P.all_tiny = 0;
-        bool direct = !ops_on_device && h.op_end - h.op_begin <= DIRECT_MAX;
+        bool direct = !ops_on_device && h.op_end - h.op_begin <= P.direct_max;
         if (ops_on_device) P.all_tiny = 0;
         for (uint32_t i = h.op_begin; i < h.op_end && direct; i++)
             if (ops[i].tag == FTL_OP_QUAD || ops[i].tag == FTL_OP_CUBIC) direct = false;
@@ -959,7 +969,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
             if (!small_ops) { set_vertex_count<<<1, 1, 0, st>>>(d_cnt, (const SumHead *)m.off.p, P.n_ops, cap_v); LAUNCHED(); }
             flatten_ops<false, true><<<fb, FLAT_THREADS, P.has_curves ? FLAT_SMEM_BYTES : 0, st>>>(d_ops, d_jobs, P, nullptr, nullptr, (const SumHead *)m.off.p, (Vtx *)m.vtx.p, nullptr, &d_cnt->overflow, cull, d_slabs, slab_pts); LAUNCHED();
         }
-        init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt); LAUNCHED();
+        init_job_state<<<div_up(P.n_jobs, 256), 256, 0, st>>>(d_js, d_jobs, P.n_ops > 0 ? (const SumHead *)m.off.p : nullptr, P.n_jobs, d_cnt, P.direct_max); LAUNCHED();
         const uint32_t vb = std::max<uint32_t>(1u, std::min<uint32_t>(div_up(nv_hint, 256), (uint32_t)m.n_sms * 8));
         vtx_topkey<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js); LAUNCHED();
         vtx_topvid<<<vb, 256, 0, st>>>((const Vtx *)m.vtx.p, d_cnt, d_js, (uint32_t *)m.sub_last.p); LAUNCHED();
@@ -1003,7 +1013,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
                                      (uint64_t)(uintptr_t)m.sub_last.p, (uint64_t)(uintptr_t)m.tcount.p, (uint64_t)(uintptr_t)m.toff.p,
                                      (uint64_t)(uintptr_t)m.tpart.p, (uint64_t)(uintptr_t)m.entries.p, (uint64_t)(uintptr_t)m.counters.p,
                                      (uint64_t)(uintptr_t)m.jstate.p, cap_v, cap_e, P.W, P.H, P.row_begin, P.row_end, P.fmt, P.log2R, P.n_jobs, P.n_ops,
-                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.b_wc, P.b_nwin, P.b_nbands, P.cull, slab_pts, (uint64_t)(uintptr_t)m.slabs.p,
+                                     P.n_tiles, P.win_chunks, P.n_bins, P.all_direct, P.direct_max, P.b_wc, P.b_nwin, P.b_nbands, P.cull, slab_pts, (uint64_t)(uintptr_t)m.slabs.p,
                                      (uint64_t)(uintptr_t)m.cull_mark.p, (uint64_t)(uintptr_t)m.cull_head.p, (uint64_t)(uintptr_t)m.cull_part.p,
                                      (uint64_t)(uintptr_t)m.cull_lo.p, (uint64_t)(uintptr_t)m.cull_hi.p, (uint64_t)(uintptr_t)m.cull_job.p};
         if (!m.graph || key != m.graph_key) {

@@ -404,9 +404,9 @@ __device__ __forceinline__ uint32_t vtx_next_fwd(const Vtx *V, uint32_t nv, uint
     return k + 1;
 }
 
-__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs, Counters *C) {
+__global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, const SumHead *__restrict__ off, uint32_t n_jobs, Counters *C, uint32_t direct_max) {
     uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool big = j < n_jobs && off && off[jobs[j].op_end].sum - off[jobs[j].op_begin].sum > DIRECT_MAX;
+    const bool big = j < n_jobs && off && off[jobs[j].op_end].sum - off[jobs[j].op_begin].sum > direct_max;
     const uint32_t n_big = __popc(__ballot_sync(0xFFFFFFFFu, big));
     if ((threadIdx.x & 31u) == 0 && n_big) atomicAdd(&C->n_big, n_big);
     if (j >= n_jobs) return;
@@ -563,7 +563,7 @@ __device__ __forceinline__ void bin_warp(EdgeRec e, uint32_t k0, const JobState 
     uint32_t b0 = 0, nb = 0, tbase = 0, b1;
     if ((e.flags & 1u) && edge_bands(e, P, &b0, &b1)) {
         const JobState &js = JS[e.job];
-        if (js.vtx_end - js.vtx_begin > DIRECT_MAX) {
+        if (js.vtx_end - js.vtx_begin > P.direct_max) {
             nb = b1 - b0 + 1;
             tbase = e.job * P.b_nbands;
         }

@@ -717,7 +717,7 @@ __global__ void __launch_bounds__(128, 5) raster_tiles(const EdgeRec *__restrict
         if (row0 < js.first_row) row0 = js.first_row;  // rows above the figure are untouched (fig.rs:497)
         if (row0 >= row_hi) continue;
         const uint32_t ne = js.vtx_end - js.vtx_begin, e0 = js.vtx_begin;
-        if (ne > DIRECT_MAX) continue;  // a binned job: raster_bins draws it
+        if (ne > P.direct_max) continue;  // a binned job: raster_bins draws it
         const unsigned long long raster = jobs[j].raster;
         const uint32_t rule = jobs[j].rule, color = jobs[j].color;
         // Row groups: with few edges the 32 lanes are (row, edge) pairs of 4 (or 2) consecutive rows, so

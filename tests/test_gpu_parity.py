@@ -193,8 +193,18 @@ def test_empty_and_noop_paths():
 
 
 # ---- (b)+(c)+(d): random figures, all formats, both rules -------------------
+@pytest.mark.parametrize("route", ["default", "bins", "tiles64"])
 @pytest.mark.parametrize("fmt", [Format.Matte8, Format.Rgba8p, Format.Graya8p])
-def test_random_polygons_vs_oracle(fmt):
+def test_random_polygons_vs_oracle(fmt, route, monkeypatch):
+    # default: the one-launch small fill.  bins: the general pipeline, jobs of more than 8 edges through raster_bins.
+    # tiles64: the general pipeline with FTL_DIRECT_MAX=64, which keeps raster_tiles' own scatter of 9..64 edges covered.
+    if route != "default":
+        monkeypatch.setenv("FTL_NO_SMALL", "1")
+        monkeypatch.setenv("FTL_DIRECT_MAX", "8" if route == "bins" else "64")
+    _random_polygons_vs_oracle(fmt)
+
+
+def _random_polygons_vs_oracle(fmt):
     rng = np.random.default_rng(7 + int(fmt))
     for it in range(60):
         w = int(rng.choice([1, 3, 8, 17, 40, 130, 257]))
