@@ -153,3 +153,19 @@ def test_libm_restatement_matches_glibc():
     # the exhaustive sweep next to +-pi/2 (67 k floats) is decided everywhere; of the `>=` probes only those placed within
     # 1.2e-7 of their threshold may stay open (half of them are placed there on purpose)
     assert s_undecided <= 1_000_100
+
+
+def test_rust_shim_binds_only_exported_symbols():
+    """rust/footile-b200/src/sys.rs (the uncompiled Rust binding) declares nothing the library does not export,
+    and its ftl_path_op mirrors the header's layout (tag + six floats)."""
+    import ctypes
+    import re
+    from footile_b200 import _lib
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    src = open(os.path.join(root, "rust", "footile-b200", "src", "sys.rs")).read()
+    names = re.findall(r"pub fn (ftl_[a-z0-9_]+)\(", src)
+    assert len(names) >= 30
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+    assert "pub tag: u32" in src and "pub v: [f32; 6]" in src
