@@ -312,8 +312,8 @@ static SmallKernel small_kernel(int fmt, bool aligned) {
     }
 }
 static size_t small_smem_bytes() { return ((sizeof(SmallShared) + 15u) & ~(size_t)15u) + BIN_ROWS * (SMALL_MAX_DIM * 2 + BIN_ROW_PAD); }
-static BinKernel bin_kernel(int fmt, bool aligned, uint32_t wc) { return wc == 128 ? bin_kernel_wc<128>(fmt, aligned) : bin_kernel_wc<256>(fmt, aligned); }
-static size_t bin_smem_bytes(uint32_t wc) { return wc == 128 ? BinTile<128>::BYTES : BinTile<256>::BYTES; }
+static BinKernel bin_kernel(int fmt, bool aligned, uint32_t wc) { return wc == 64 ? bin_kernel_wc<64>(fmt, aligned) : (wc == 128 ? bin_kernel_wc<128>(fmt, aligned) : bin_kernel_wc<256>(fmt, aligned)); }
+static size_t bin_smem_bytes(uint32_t wc) { return wc == 64 ? BinTile<64>::BYTES : (wc == 128 ? BinTile<128>::BYTES : BinTile<256>::BYTES); }
 
 #define ENSURE_INIT()                                                        \
     do {                                                                     \
@@ -359,7 +359,7 @@ static int engine_init(Engine::Impl *m, int device, void **stream_out) {
                     CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)di.max_smem));
                     CK(cudaFuncSetAttribute(tile_kernel(f, a != 0), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     CK(cudaFuncSetAttribute(small_kernel(f, a != 0), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_smem_bytes()));
-                    for (uint32_t wc : {128u, 256u}) {
+                    for (uint32_t wc : {64u, 128u, 256u}) {
                         CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bin_smem_bytes(wc)));
                         CK(cudaFuncSetAttribute(bin_kernel(f, a != 0, wc), cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
                     }
@@ -429,13 +429,18 @@ static int choose_tiling(const Geometry &g, size_t max_smem, uint32_t jobs_per_l
     }
     // ---- binned tiles (raster_bins): bands of 32 rows x windows of b_wc columns ----
     P->b_wc = 128;  // 8.8 KB per warp: 21 resident warps per SM (256 columns: 12 warps, 20-30 % slower on every workload measured)
-    if (const char *ev = getenv("FTL_BIN_WC")) P->b_wc = atoi(ev) == 256 ? 256u : 128u;  // tuning knob
     P->b_nbands = div_up(g.rows(), BIN_ROWS);
     P->b_nwin = div_up(g.width, P->b_wc);
     // One ticket per (band, window) with the row sums handed to the right neighbour, unless the launch has
     // plenty of bands anyway (many narrow rasters): then a ticket walks the windows of its band serially.
     const uint32_t bin_slots = (uint32_t)n_sms * 12u;
     P->b_lookback = P->b_nwin > 1 && (uint64_t)jobs_per_launch * P->b_nbands < 8ull * bin_slots;
+    // Many narrow rasters (no look-back): windows of 64 columns halve the tile's shared memory, 40 warps per SM hide
+    // the per-tile load chain (ticket -> job -> bin -> entries -> edges) better than 21 do: the batched fishy fills
+    // 0.415 -> 0.349 ms, config 4 0.755 -> 0.66 ms per launch.  Wide rasters lose with 64 (config 5 34.6 -> 40.5 ms).
+    if (!P->b_lookback && P->b_nwin > 1) P->b_wc = 64;
+    if (const char *ev = getenv("FTL_BIN_WC")) P->b_wc = atoi(ev) == 256 ? 256u : (atoi(ev) == 64 ? 64u : (atoi(ev) == 128 ? 128u : P->b_wc));  // tuning knob
+    P->b_nwin = div_up(g.width, P->b_wc);
     if (const char *ev = getenv("FTL_BIN_LOOKBACK")) P->b_lookback = P->b_nwin > 1 && atoi(ev) != 0;  // tuning knob
     return FTL_OK;
 }
