@@ -106,6 +106,7 @@ struct OpSink {
     uint32_t sub = 0, job = 0;
     int2 *slab = nullptr;   // counting pass of a curve: the first slab_cap kept points are parked here, so that the
     uint32_t slab_cap = 0;  // emitting pass copies them instead of subdividing the curve a second time
+    size_t slab_stride = 0; // point k of op i lives at slabs[k * n_ops + i]: neighbouring lanes (ops) share sectors
     __device__ __forceinline__ void put(WPt q) {
         if (WIDE) {
             if (EMIT) {
@@ -119,7 +120,7 @@ struct OpSink {
             int32_t fx = fx_from_f32(q.p.x), fy = fx_from_f32(q.p.y);
             if (force || fx != px || fy != py) {
                 if (EMIT) vout[n] = {fx, fy, sub, job};
-                else if (n < slab_cap) slab[n] = make_int2(fx, fy);
+                else if (n < slab_cap) slab[(size_t)n * slab_stride] = make_int2(fx, fy);
                 n++;
             }
             force = false;
@@ -346,15 +347,16 @@ __global__ void __launch_bounds__(FLAT_THREADS) flatten_ops(const ftl_path_op *_
             }
             const bool curve = op.tag == FTL_OP_QUAD || op.tag == FTL_OP_CUBIC;
             if (!WIDE && curve && slab_pts) {
-                int2 *slab = slabs + (size_t)i * slab_pts;
+                int2 *slab = slabs + i;
                 if (!EMIT) {
                     sink.slab = slab;
                     sink.slab_cap = slab_pts;
+                    sink.slab_stride = P.n_ops;
                 } else {
                     const uint32_t cnt_i = off[i + 1].sum - off[i].sum;
                     if (cnt_i <= slab_pts) {  // the counting pass parked every point of this curve: copy, do not subdivide again
                         for (uint32_t k = 0; k < cnt_i; k++) {
-                            const int2 q = slab[k];
+                            const int2 q = slab[(size_t)k * P.n_ops];
                             sink.vout[k] = {q.x, q.y, sink.sub, sink.job};
                         }
                         continue;
