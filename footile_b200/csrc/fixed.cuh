@@ -21,7 +21,15 @@ FTL_HD fx_t fx_add(fx_t a, fx_t b) { return (fx_t)((uint32_t)a + (uint32_t)b); }
 FTL_HD fx_t fx_sub(fx_t a, fx_t b) { return (fx_t)((uint32_t)a - (uint32_t)b); }            // fixed.rs:32-38
 FTL_HD fx_t fx_mul(fx_t a, fx_t b) { return (fx_t)(((int64_t)a * (int64_t)b) >> 16); }      // fixed.rs:40-47
 FTL_HD fx_t fx_div(fx_t a, fx_t b) {                                                        // fixed.rs:49-56
+#if defined(__CUDA_ARCH__)
+    // The 48-by-32-bit truncating division through one double-precision division rounded towards zero: the numerator
+    // (|a| << 16 < 2^47) and the divisor are exact doubles, the integer part of the true quotient (< 2^48) is itself a
+    // double not above it in magnitude, so the quotient rounded towards zero lies between the two and truncates to exactly
+    // that integer part.  About a third of the instructions of the 64-bit integer division it replaces.
+    return (fx_t)__double2ll_rz(__ddiv_rz((double)a * 65536.0, (double)b));
+#else
     return (fx_t)((int64_t)((uint64_t)(int64_t)a << 16) / (int64_t)b);
+#endif
 }
 FTL_HD int32_t fx_to_i32(fx_t a) { return a >> 16; }                                        // fixed.rs:81-86
 FTL_HD fx_t fx_abs(fx_t a) { return a < 0 ? (fx_t)(0u - (uint32_t)a) : a; }                 // fixed.rs:122-124

@@ -520,23 +520,19 @@ __device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32
     *w0 = 0;
     *w1 = P.b_nwin - 1;
     if (P.b_nwin == 1) return;
-    int64_t lo = INT64_MAX, hi = INT64_MIN;
+    // X at the bottom / top of the two end rows; in 64 bits only to detect what would wrap the scatter's 32-bit arithmetic
     const int64_t slope = e.inv_slope;
-    for (int t = 0; t < 2; t++) {
-        const int32_t r = t ? rb : ra;
-        const int64_t x_bot = (int64_t)e.x_bot0 + (int64_t)(r - e.ry0) * slope;
-        const int64_t x_top = x_bot - slope;
-        if (x_bot != (int32_t)x_bot || x_top != (int32_t)x_top) return;
-        lo = min(lo, min(x_bot, x_top));
-        hi = max(hi, max(x_bot, x_top));
-    }
-    const int64_t run = (slope < 0 ? -slope : slope) >> 16;
-    int64_t lo_pix = (lo >> 16) - 1, hi_pix = (hi >> 16) + run + 3;
-    const int64_t wmax = (int64_t)P.W - 1;
-    lo_pix = lo_pix < 0 ? 0 : (lo_pix > wmax ? wmax : lo_pix);
-    hi_pix = hi_pix < 0 ? 0 : (hi_pix > wmax ? wmax : hi_pix);
-    *w0 = (uint32_t)lo_pix / P.b_wc;
-    *w1 = (uint32_t)hi_pix / P.b_wc;
+    const int64_t xa_bot = (int64_t)e.x_bot0 + (int64_t)(ra - e.ry0) * slope, xb_bot = (int64_t)e.x_bot0 + (int64_t)(rb - e.ry0) * slope;
+    const int64_t xa_top = xa_bot - slope, xb_top = xb_bot - slope;
+    if (xa_bot != (int32_t)xa_bot || xa_top != (int32_t)xa_top || xb_bot != (int32_t)xb_bot || xb_top != (int32_t)xb_top) return;
+    // X is monotone in the row: the extremes are the top of the first row and the bottom of the last one
+    const int32_t lo = slope >= 0 ? (int32_t)xa_top : (int32_t)xb_bot, hi = slope >= 0 ? (int32_t)xb_bot : (int32_t)xa_top;
+    const int32_t run = (int32_t)((slope < 0 ? -slope : slope) >> 16);
+    const int32_t wmax = (int32_t)P.W - 1;
+    const int32_t lo_pix = min(max((lo >> 16) - 1, 0), wmax), hi_pix = min(max((hi >> 16) + run + 3, 0), wmax);
+    const int sh = 31 - __clz((int)P.b_wc);  // the window width is a power of two
+    *w0 = (uint32_t)lo_pix >> sh;
+    *w1 = (uint32_t)hi_pix >> sh;
 }
 
 // Counting sort of edges by (job, band of 32 rows, column window): pass FILL=false counts, pass FILL=true

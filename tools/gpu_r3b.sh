@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 2400 python -m pytest tests -m gpu -x -q > gpurun_out/r3b_pytest.log 2>&1
+echo "pytest exit $?" >> gpurun_out/r3b_pytest.log
+tail -3 gpurun_out/r3b_pytest.log
+for args in "--workload fishy256" "--workload strokes4k" "--workload batch512" "--workload bigraster" ""; do
+  timeout 600 python bench.py $args --steps 10 --kernel-only > gpurun_out/r3b_tmp.json 2>/dev/null
+  python - "$args" <<PY
+import json,sys
+d=json.loads(open("gpurun_out/r3b_tmp.json").read().strip().splitlines()[-1])
+r=d.get("roofline") or {}
+print(sys.argv[1] or "heptagram", {k:round(d.get(k),4) for k in ("value","ms_per_step")}, "tile_ms", round(r.get("avg_launch_ms",0),4), "frac", round(r.get("frac",0),3))
+PY
+done
