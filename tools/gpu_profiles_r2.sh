@@ -14,7 +14,7 @@ python bench.py --format rgba8p > $O/p2_bench_heptagram_rgba8p.json 2> $O/p2_ben
 python bench.py --format graya8p > $O/p2_bench_heptagram_graya8p.json 2>> $O/p2_bench_heptagram_rgba8p.err
 nvidia-smi --query-gpu=index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active --format=csv > $O/p2_smi.csv 2>&1
 # launch lists (kernel-only legs)
-for wl in heptagram batch512 bigraster strokes4k; do
+for wl in heptagram batch512 bigraster strokes4k fishy256; do
   ncu --metrics gpu__time_duration.sum --clock-control none -s 30 -c 120 --csv --log-file $O/p2_launches_$wl.csv \
      python bench.py --workload $wl --steps 3 --warmup 3 --kernel-only > $O/p2_ll_$wl.log 2>&1
 done
@@ -32,6 +32,10 @@ cap heptagram_rgba8p raster_tiles 4 python bench.py --format rgba8p --steps 2 --
 cap batch512 raster_bins 3 python bench.py --workload batch512 --steps 2 --warmup 3 --kernel-only
 cap bigraster raster_bins 3 python bench.py --workload bigraster --steps 2 --warmup 3 --kernel-only
 cap strokes4k raster_bins 3 python bench.py --workload strokes4k --steps 2 --warmup 3 --kernel-only
-cap fishy256 raster_tiles 4 python bench.py --workload fishy256 --steps 2 --warmup 3 --kernel-only
+cap fishy256 raster_bins 3 python bench.py --workload fishy256 --steps 2 --warmup 3 --kernel-only
 cap small small_fill 20 python tools/one_fill_probe.py 30
+cap stroke_segments stroke_segments 2 env FTL_DEVICE_STROKE=1 python tools/stroke_probe.py 4096 1
+# the device stroker: kernel list of one batched stroke call, and device against host wall clock
+ncu --metrics gpu__time_duration.sum --clock-control none -s 60 -c 70 --csv --log-file $O/p2_launches_stroke.csv env FTL_DEVICE_STROKE=1 python tools/stroke_probe.py 4096 1 > $O/p2_ll_stroke.log 2>&1
+python tools/stroke_probe.py 4096 5 > $O/p2_stroke_probe.txt 2>&1
 du -sh $O; ls -la $O/p2_* | awk '{print $5, $9}'

@@ -67,7 +67,7 @@ def main():
     pre = "p2_"
     traffic = {}
     for wl, key in (("heptagram", "heptagram"), ("heptagram_rgba8p", "heptagram_rgba8p"), ("batch512", "batch512"), ("bigraster", "bigraster"),
-                    ("strokes4k", "strokes4k_rgba8p"), ("fishy256", "fishy256"), ("small", None)):
+                    ("strokes4k", "strokes4k_rgba8p"), ("fishy256", "fishy256"), ("small", None), ("stroke_segments", None)):
         rep = os.path.join(G, "%sraw_%s.csv" % (pre, wl))
         if os.path.exists(rep) and os.path.getsize(rep) > 0:
             t = ncu_summary(rep, os.path.join(P, "%s_%s_ncu.csv" % (rnd, wl)))
@@ -84,7 +84,7 @@ def main():
     traffic["source"] = "profiles/%s_*_ncu.csv: dram__bytes_read.sum + dram__bytes_write.sum of one launch of the dominant tile kernel (ncu --set full)" % rnd
     json.dump(traffic, open(os.path.join(P, "traffic.json"), "w"), indent=1)
     with open(os.path.join(P, "%s_launch_shares.txt" % rnd), "w") as f:
-        for wl in ("heptagram", "batch512", "bigraster", "strokes4k"):
+        for wl in ("heptagram", "batch512", "bigraster", "strokes4k", "fishy256", "stroke"):
             src = os.path.join(G, "%slaunches_%s.csv" % (pre, wl))
             if os.path.exists(src):
                 for k, n, avg, share in launch_summary(src, os.path.join(P, "%s_launches_%s.csv" % (rnd, wl))):
@@ -94,6 +94,8 @@ def main():
     for name in os.listdir(G):
         if name.startswith(pre + "bench_") and name.endswith(".json") and os.path.getsize(os.path.join(G, name)) > 0:
             shutil.copy(os.path.join(G, name), os.path.join(P, rnd + "_" + name[len(pre):]))
+    if os.path.exists(os.path.join(G, pre + "stroke_probe.txt")):
+        shutil.copy(os.path.join(G, pre + "stroke_probe.txt"), os.path.join(P, rnd + "_stroke_probe.txt"))
     if os.path.exists(os.path.join(G, pre + "smi.csv")):
         shutil.copy(os.path.join(G, pre + "smi.csv"), os.path.join(P, rnd + "_nvidia_smi_after.csv"))
     print(json.dumps(traffic))
