@@ -306,6 +306,9 @@ def bigraster_ours(D, steps, warmup, ops=None, full=True):
     size = BIG["size"]
     ops = big_ops() if ops is None else ops
     r0, r1 = sharding.band_rows(size, D.rank, D.world, align=32)
+    if os.environ.get("FTL_BENCH_BAND"):  # profiling aid: one GPU plays band R of W ("R/W"), e.g. for a launch list of an 8-GPU rank
+        er, ew = (int(v) for v in os.environ["FTL_BENCH_BAND"].split("/"))
+        r0, r1 = sharding.band_rows(size, er, ew, align=32)
     p = fb.Plotter.with_clear(size, size, Format.Matte8, device=D.local_rank, rows=(r0, r1))
     stream = torch.cuda.ExternalStream(p.stream(), device=D.local_rank)
     # ---- value: ops resident in HBM (ftl_fill_upload once, ftl_fill_replay per step) ----

@@ -253,27 +253,45 @@ __device__ __forceinline__ void op_y_range(const ftl_path_op &op, const float *e
 __global__ void __launch_bounds__(256) cull_op_extents(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
                                                        uint32_t *__restrict__ headmark, int32_t *__restrict__ sub_lo, int32_t *__restrict__ sub_hi,
                                                        int32_t *__restrict__ job_bound) {
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < P.n_ops; i += gridDim.x * blockDim.x) {
-        const ftl_path_op op = ops[i];
-        uint32_t mark = 0;
-        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
-            const uint32_t j = job_of_op(jobs, P.n_jobs, i);
-            const JobDesc &jd = jobs[j];
-            const PenInfo pi = find_pen(ops, jd.op_begin, i);
-            if (pi.starts_sub || op.tag == FTL_OP_MOVE) {
-                mark = i + 1;
-                sub_lo[i] = INT32_MAX;
-                sub_hi[i] = INT32_MIN;
-            }
-            float e[6];
+    const uint32_t lane = threadIdx.x & 31;
+    // whole warps iterate together: ops are stored job after job, so a warp usually holds one job and issues ONE pair of
+    // atomics for its 32 ops (one raster with 10 M ops would otherwise serialise 20 M atomics on two addresses)
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < P.n_ops; i0 += gridDim.x * blockDim.x) {
+        const uint32_t i = i0 + lane;
+        uint32_t mark = 0, j = NONE32;
+        int32_t lo = INT32_MAX, ye = INT32_MAX;
+        if (i < P.n_ops) {
+            const ftl_path_op op = ops[i];
+            if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+                j = job_of_op(jobs, P.n_jobs, i);
+                const JobDesc &jd = jobs[j];
+                const PenInfo pi = find_pen(ops, jd.op_begin, i);
+                if (pi.starts_sub || op.tag == FTL_OP_MOVE) {
+                    mark = i + 1;
+                    sub_lo[i] = INT32_MAX;
+                    sub_hi[i] = INT32_MIN;
+                }
+                float e[6];
 #pragma unroll
-            for (int k = 0; k < 6; k++) e[k] = jd.e[k];
-            int32_t lo, hi, ye;
-            op_y_range(op, e, pi, &lo, &hi, &ye);
+                for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+                int32_t hi;
+                op_y_range(op, e, pi, &lo, &hi, &ye);
+            }
+            headmark[i] = mark;
+        }
+        const uint32_t have = __ballot_sync(0xFFFFFFFFu, j != NONE32);
+        if (!have) continue;
+        const uint32_t j0 = __shfl_sync(0xFFFFFFFFu, j, __ffs((int)have) - 1);
+        if (__all_sync(0xFFFFFFFFu, j == NONE32 || j == j0)) {
+            const int32_t ye_min = __reduce_min_sync(0xFFFFFFFFu, ye), lo_min = __reduce_min_sync(0xFFFFFFFFu, lo);
+            if (lane == 0) {
+                atomicMin(&job_bound[2 * j0], ye_min);
+                atomicMin(&job_bound[2 * j0 + 1], lo_min);
+            }
+        } else if (j != NONE32) {
             atomicMin(&job_bound[2 * j], ye);
             atomicMin(&job_bound[2 * j + 1], lo);
         }
-        headmark[i] = mark;
     }
 }
 __global__ void __launch_bounds__(256) cull_sub_extents(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
