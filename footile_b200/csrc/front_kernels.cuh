@@ -587,6 +587,10 @@ __device__ __forceinline__ void bin_warp(EdgeRec e, uint32_t k0, const JobState 
     if (nb > 0 && nb <= 4)
         for (uint32_t b = b0; b < b0 + nb; b++) bin_one<FILL>(e, k0 + lane, tbase + b, b, P, bin_count, bin_off, entries);
     uint32_t tall = __ballot_sync(0xFFFFFFFFu, nb > 4);
+    // FILL: the slot of an entry comes back from an atomic, and the store that needs it would stall the warp for an L2 round
+    // trip per edge.  The stores of one tall edge are therefore issued after the atomics of the NEXT one (up to three windows
+    // of the lane's band are kept pending; anything beyond that is stored at once).
+    uint32_t p_off0 = 0, p_off1 = 0, p_off2 = 0, p_slot0 = 0, p_slot1 = 0, p_slot2 = 0, p_n = 0, p_k = 0;
     while (tall) {
         const int src = __ffs(tall) - 1;
         tall &= tall - 1;
@@ -598,7 +602,48 @@ __device__ __forceinline__ void bin_warp(EdgeRec e, uint32_t k0, const JobState 
         es.ry0 = __shfl_sync(0xFFFFFFFFu, e.ry0, src);
         es.ry1 = __shfl_sync(0xFFFFFFFFu, e.ry1, src);
         es.fr = 0; es.job = 0; es.flags = 1u;
-        for (uint32_t b = lane; b < snb; b += 32) bin_one<FILL>(es, k0 + (uint32_t)src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);
+        if (!FILL) {
+            for (uint32_t b = lane; b < snb; b += 32) bin_one<false>(es, k0 + (uint32_t)src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);
+            continue;
+        }
+        uint32_t c_off0 = 0, c_off1 = 0, c_off2 = 0, c_slot0 = 0, c_slot1 = 0, c_slot2 = 0, c_n = 0;
+        if (lane < snb) {  // the lane's first band of this edge: up to three windows pending
+            const uint32_t band = sb0 + lane, tile = stb + band;
+            const int32_t row0 = (int32_t)P.row_begin + (int32_t)(band << 5);
+            const int32_t ra = max(es.ry0, row0), rb = min(min(es.ry1, row0 + 31), (int32_t)P.row_end - 1);
+            uint32_t w0, w1;
+            edge_windows(es, ra, rb, P, &w0, &w1);
+            const uint32_t bin = tile * P.b_nwin + w0;
+            c_n = min(w1 - w0 + 1u, 3u);
+            c_off0 = bin_off[bin];
+            c_slot0 = atomicAdd(&bin_count[bin], 1u);
+            if (c_n > 1) {
+                c_off1 = bin_off[bin + 1];
+                c_slot1 = atomicAdd(&bin_count[bin + 1], 1u);
+            }
+            if (c_n > 2) {
+                c_off2 = bin_off[bin + 2];
+                c_slot2 = atomicAdd(&bin_count[bin + 2], 1u);
+            }
+            for (uint32_t w = w0 + 3; w <= w1; w++) {
+                const uint32_t bw = tile * P.b_nwin + w;
+                entries[bin_off[bw] + atomicAdd(&bin_count[bw], 1u)] = k0 + (uint32_t)src;
+            }
+        }
+        for (uint32_t b = lane + 32; b < snb; b += 32) bin_one<true>(es, k0 + (uint32_t)src, stb + sb0 + b, sb0 + b, P, bin_count, bin_off, entries);  // taller than 1024 rows
+        // the previous edge's stores: its atomics have had this iteration to complete
+        if (p_n > 0) entries[p_off0 + p_slot0] = p_k;
+        if (p_n > 1) entries[p_off1 + p_slot1] = p_k;
+        if (p_n > 2) entries[p_off2 + p_slot2] = p_k;
+        p_off0 = c_off0; p_off1 = c_off1; p_off2 = c_off2;
+        p_slot0 = c_slot0; p_slot1 = c_slot1; p_slot2 = c_slot2;
+        p_n = c_n;
+        p_k = k0 + (uint32_t)src;
+    }
+    if (FILL) {
+        if (p_n > 0) entries[p_off0 + p_slot0] = p_k;
+        if (p_n > 1) entries[p_off1 + p_slot1] = p_k;
+        if (p_n > 2) entries[p_off2 + p_slot2] = p_k;
     }
 }
 

@@ -1022,8 +1022,31 @@ def test_device_stroker_pixels_4k(join, monkeypatch):
     assert g.pen_width() == g2.pen_width()
 
 
+def test_device_stroker_hands_capped_strokes_to_the_host(monkeypatch):
+    """A stroke at Stroke::add_point's 65 535-point cap (stroker.rs:206) is declined by the device stroker and drawn through
+    the host stroker, in order, with the same pixels as the oracle."""
+    monkeypatch.setenv("FTL_DEVICE_STROKE", "1")
+    t = np.linspace(0.0, 40 * np.pi, 70000)
+    r = 10 + 100 * t / t[-1]
+    p = Path2D().absolute().pen_width(1.5).move_to(128 + r[0] * np.cos(t[0]), 128 + r[0] * np.sin(t[0]))
+    for k in range(1, len(t)):
+        p = p.line_to(128 + r[k] * np.cos(t[k]), 128 + r[k] * np.sin(t[k]))
+    ops = p.finish()
+    g, o = both(256, 256, Format.Matte8, join=JoinStyle.Bevel)
+    assert g.debug_stroke_ops_device(ops) is None
+    small = scenes.stroke_scenes(1.0)["round"]
+    g.stroke(small, (255,))   # device
+    g.stroke(ops, (255,))     # declined -> host
+    g.stroke(small, (255,))   # device again, after the fallback
+    for q in (small, ops, small):
+        o.stroke(q, (255,))
+    assert_same(g, o)
+
+
 def test_batch_stroke_device_equals_host_path(monkeypatch):
     paths = list(scenes.stroke_scenes(4.0).values()) + [scenes.fishy_bench(), scenes.fishy_example()[0]]
+    paths.insert(2, np.zeros(0, dtype=OP_DTYPE))                                 # a job without ops
+    paths.insert(5, np.array([PathOp.PenWidth(4.0), PathOp.Close()], dtype=OP_DTYPE))  # a job without drawing ops
     ops, offs = Batch.pack(paths)
     n = len(paths)
     tr = np.tile(np.array([1, 0, 0, 0, 1, 0], dtype=np.float32), (n, 1))
