@@ -254,44 +254,57 @@ __global__ void __launch_bounds__(256) cull_op_extents(const ftl_path_op *__rest
                                                        uint32_t *__restrict__ headmark, int32_t *__restrict__ sub_lo, int32_t *__restrict__ sub_hi,
                                                        int32_t *__restrict__ job_bound) {
     const uint32_t lane = threadIdx.x & 31;
-    // whole warps iterate together: ops are stored job after job, so a warp usually holds one job and issues ONE pair of
-    // atomics for its 32 ops (one raster with 10 M ops would otherwise serialise 20 M atomics on two addresses)
+    // The two minima of a job are kept in registers across the thread's whole grid-stride loop and flushed when the job
+    // changes and once at the end, there with one pair of atomics per warp: one raster with 10 M ops otherwise sends
+    // 650 k same-address atomics (one pair per warp and iteration) through one L2 slice, and the loads queue up behind them.
+    uint32_t cur_j = NONE32;
+    int32_t cur_ye = INT32_MAX, cur_lo = INT32_MAX;
     for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) - lane; i0 < P.n_ops; i0 += gridDim.x * blockDim.x) {
         const uint32_t i = i0 + lane;
-        uint32_t mark = 0, j = NONE32;
-        int32_t lo = INT32_MAX, ye = INT32_MAX;
-        if (i < P.n_ops) {
-            const ftl_path_op op = ops[i];
-            if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
-                j = job_of_op(jobs, P.n_jobs, i);
-                const JobDesc &jd = jobs[j];
-                const PenInfo pi = find_pen(ops, jd.op_begin, i);
-                if (pi.starts_sub || op.tag == FTL_OP_MOVE) {
-                    mark = i + 1;
-                    sub_lo[i] = INT32_MAX;
-                    sub_hi[i] = INT32_MIN;
-                }
-                float e[6];
+        if (i >= P.n_ops) continue;
+        const ftl_path_op op = ops[i];
+        uint32_t mark = 0;
+        if (op.tag >= FTL_OP_MOVE && op.tag <= FTL_OP_CUBIC) {
+            const uint32_t j = job_of_op(jobs, P.n_jobs, i);
+            const JobDesc &jd = jobs[j];
+            const PenInfo pi = find_pen(ops, jd.op_begin, i);
+            if (pi.starts_sub || op.tag == FTL_OP_MOVE) {
+                mark = i + 1;
+                sub_lo[i] = INT32_MAX;
+                sub_hi[i] = INT32_MIN;
+            }
+            float e[6];
 #pragma unroll
-                for (int k = 0; k < 6; k++) e[k] = jd.e[k];
-                int32_t hi;
-                op_y_range(op, e, pi, &lo, &hi, &ye);
+            for (int k = 0; k < 6; k++) e[k] = jd.e[k];
+            int32_t lo, hi, ye;
+            op_y_range(op, e, pi, &lo, &hi, &ye);
+            if (j != cur_j) {
+                if (cur_j != NONE32) {
+                    atomicMin(&job_bound[2 * cur_j], cur_ye);
+                    atomicMin(&job_bound[2 * cur_j + 1], cur_lo);
+                }
+                cur_j = j;
+                cur_ye = INT32_MAX;
+                cur_lo = INT32_MAX;
             }
-            headmark[i] = mark;
+            cur_ye = min(cur_ye, ye);
+            cur_lo = min(cur_lo, lo);
         }
-        const uint32_t have = __ballot_sync(0xFFFFFFFFu, j != NONE32);
-        if (!have) continue;
-        const uint32_t j0 = __shfl_sync(0xFFFFFFFFu, j, __ffs((int)have) - 1);
-        if (__all_sync(0xFFFFFFFFu, j == NONE32 || j == j0)) {
-            const int32_t ye_min = __reduce_min_sync(0xFFFFFFFFu, ye), lo_min = __reduce_min_sync(0xFFFFFFFFu, lo);
-            if (lane == 0) {
-                atomicMin(&job_bound[2 * j0], ye_min);
-                atomicMin(&job_bound[2 * j0 + 1], lo_min);
-            }
-        } else if (j != NONE32) {
-            atomicMin(&job_bound[2 * j], ye);
-            atomicMin(&job_bound[2 * j + 1], lo);
+        headmark[i] = mark;
+    }
+    // every lane of the warp arrives here (the loop bound is warp-uniform)
+    const uint32_t have = __ballot_sync(0xFFFFFFFFu, cur_j != NONE32);
+    if (!have) return;
+    const uint32_t j0 = __shfl_sync(0xFFFFFFFFu, cur_j, __ffs((int)have) - 1);
+    if (__all_sync(0xFFFFFFFFu, cur_j == NONE32 || cur_j == j0)) {
+        const int32_t ye_min = __reduce_min_sync(0xFFFFFFFFu, cur_ye), lo_min = __reduce_min_sync(0xFFFFFFFFu, cur_lo);
+        if (lane == 0) {
+            atomicMin(&job_bound[2 * j0], ye_min);
+            atomicMin(&job_bound[2 * j0 + 1], lo_min);
         }
+    } else if (cur_j != NONE32) {
+        atomicMin(&job_bound[2 * cur_j], cur_ye);
+        atomicMin(&job_bound[2 * cur_j + 1], cur_lo);
     }
 }
 __global__ void __launch_bounds__(256) cull_sub_extents(const ftl_path_op *__restrict__ ops, const JobDesc *__restrict__ jobs, Params P,
@@ -439,12 +452,31 @@ __global__ void init_job_state(JobState *JS, const JobDesc *__restrict__ jobs, c
 }
 
 // Top-left vertex, pass 1: minimum (y,x) over the live vertices of each job (fig.rs:493-494).
+// One atomic for the warp's minima when its lanes hold one job, else one per lane.
+__device__ __forceinline__ void topkey_flush(JobState *JS, uint32_t cur_j, unsigned long long cur_key) {
+    const uint32_t have = __ballot_sync(0xFFFFFFFFu, cur_j != NONE32);
+    if (!have) return;
+    const uint32_t j0 = __shfl_sync(0xFFFFFFFFu, cur_j, __ffs((int)have) - 1);
+    if (__all_sync(0xFFFFFFFFu, cur_j == NONE32 || cur_j == j0)) {
+        unsigned long long key = cur_key;
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) {
+            const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, d);
+            key = o < key ? o : key;
+        }
+        if ((threadIdx.x & 31u) == 0 && key != ~0ull) atomicMin(&JS[j0].top_key, key);
+    } else if (cur_j != NONE32 && cur_key != ~0ull) atomicMin(&JS[cur_j].top_key, cur_key);
+}
 __global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, const Counters *__restrict__ C, JobState *JS) {
     const uint32_t nv = C->nv;
     const uint32_t stride = gridDim.x * blockDim.x;
-    // whole warps iterate together (k0 is the warp's first vertex): vertices are stored job after job, so a
-    // warp usually holds one job and issues ONE atomic for its 32 keys (one raster with 10 M vertices would
-    // otherwise serialise 10 M atomics on one address)
+    // Whole warps iterate together (k0 is the warp's first vertex; vertices are stored job after job).  The minimum is kept
+    // in registers across the grid-stride loop and flushed - one atomic per warp - only when a lane moves on to another
+    // job, and at the end: a batch of small jobs flushes every iteration (as many atomics as warps x iterations), one
+    // raster with 10 M vertices flushes once per warp instead of sending 320 k atomics to one address with the loads
+    // queueing up behind them (241 -> 33 us).
+    uint32_t cur_j = NONE32;
+    unsigned long long cur_key = ~0ull;
     for (uint32_t k0 = (blockIdx.x * blockDim.x + threadIdx.x) & ~31u; k0 < nv; k0 += stride) {
         const uint32_t k = k0 + (threadIdx.x & 31u);
         unsigned long long key = ~0ull;
@@ -452,18 +484,19 @@ __global__ void __launch_bounds__(256) vtx_topkey(const Vtx *__restrict__ V, con
         if (k < nv) {
             const Vtx v = V[k];
             job = v.job;
-            if (!(vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub]))) key = vtx_key(v);
+            if (!(vtx_is_last(V, nv, k) && vtx_same(v, V[v.sub]))) key = vtx_key(v);  // else: popped by the close rule
         }
-        const uint32_t job0 = __shfl_sync(0xFFFFFFFFu, job, 0);
-        if (__all_sync(0xFFFFFFFFu, job == job0 || job == NONE32)) {
-#pragma unroll
-            for (int d = 16; d > 0; d >>= 1) {
-                const unsigned long long o = __shfl_xor_sync(0xFFFFFFFFu, key, d);
-                key = o < key ? o : key;
-            }
-            if ((threadIdx.x & 31u) == 0 && key != ~0ull) atomicMin(&JS[job0].top_key, key);
-        } else if (key != ~0ull) atomicMin(&JS[job].top_key, key);
+        if (__any_sync(0xFFFFFFFFu, job != NONE32 && cur_j != NONE32 && job != cur_j)) {
+            topkey_flush(JS, cur_j, cur_key);
+            cur_j = NONE32;
+            cur_key = ~0ull;
+        }
+        if (job != NONE32) {
+            cur_j = job;
+            cur_key = key < cur_key ? key : cur_key;
+        }
     }
+    topkey_flush(JS, cur_j, cur_key);
 }
 // Pass 2: the stable sort keeps the lowest vertex id among equal keys; also
 // records each sub-figure's last live vertex for the Reverse ring neighbour.
