@@ -1,6 +1,7 @@
 #!/usr/bin/env python
-"""Longer randomized parity run than the test suite: the analytic-row scenes, random polygons, curved paths, edge
-records and layered scenes of tests/test_gpu_parity.py with fresh seeds.  Usage: python tools/fuzz_parity.py [seed0] [rounds]"""
+"""Longer randomized parity run than the test suite: the analytic-row scenes, random polygons (through the small fill, the
+bins and raster_tiles' own scatter), curved paths, edge records, layered scenes and the device stroker's outlines of
+tests/test_gpu_parity.py with fresh seeds.  Usage: python tools/fuzz_parity.py [seed0] [rounds]"""
 import os
 import sys
 
@@ -21,8 +22,15 @@ for r in range(rounds):
     np.random.default_rng = lambda s=None, _r=r: real_rng((0 if s is None else int(s)) + seed0 + 7919 * _r)
     for fmt in (Format.Matte8, Format.Rgba8p, Format.Graya8p):
         T.test_analytic_rows_vs_oracle(fmt)
-        T.test_random_polygons_vs_oracle(fmt)
-        n += 2
+        n += 1
+        for env in ({}, {"FTL_NO_SMALL": "1", "FTL_DIRECT_MAX": "8"}, {"FTL_NO_SMALL": "1", "FTL_DIRECT_MAX": "64"}):
+            os.environ.update(env)
+            try:
+                T._random_polygons_vs_oracle(fmt)
+            finally:
+                for k in env:
+                    os.environ.pop(k, None)
+            n += 1
     for rule in (0, 1):
         T.test_curved_paths_vs_oracle(rule)
         n += 1
@@ -33,6 +41,8 @@ for r in range(rounds):
     for fmt in (Format.Rgba8p, Format.Matte8, Format.Graya8p):
         T.test_fill_layers_equals_sequential_calls(fmt)
         n += 1
+    T.test_device_stroker_outline_equals_host_on_random_paths()
+    n += 1
     print("round", r, "ok", flush=True)
 np.random.default_rng = real_rng
 print("fuzz: %d randomized test bodies passed with seeds from %d" % (n, seed0))
