@@ -22,7 +22,7 @@ SYMBOLS = [
     "ftl_ctx_new", "ftl_ctx_free", "ftl_ctx_size", "ftl_shard_range", "ftl_band_rows", "ftl_ctx_fill_batch", "ftl_ctx_fill_bands",
     "ftl_launch_count", "ftl_transfer_bytes", "ftl_set_profiling", "ftl_tile_kernel_time", "ftl_plotter_tile_kernel_time", "ftl_batch_tile_kernel_time", "ftl_time_fills",
     "ftl_debug_area", "ftl_debug_small_profile", "ftl_batch_debug_top_rows", "ftl_debug_flatten", "ftl_debug_last_fill", "ftl_debug_edges", "ftl_debug_stroke_ops", "ftl_debug_stroke_outline", "ftl_debug_accumulate",
-    "ftl_debug_stroke_ops_device", "ftl_debug_libm_selftest",
+    "ftl_debug_stroke_ops_device", "ftl_debug_libm_selftest", "ftl_debug_strict_intake", "ftl_debug_stroke_subs",
 ]
 
 
@@ -108,6 +108,8 @@ def lib():
         "ftl_debug_stroke_ops": (i32, [vp, vp, sz, vp, sz, vp]),
         "ftl_debug_stroke_ops_device": (i32, [vp, vp, sz, vp, sz, vp, vp]),
         "ftl_debug_libm_selftest": (i32, [C.c_uint64, C.c_uint64, vp, vp, vp, vp]),
+        "ftl_debug_strict_intake": (i32, [vp, f32, vp, sz, vp, sz, vp, vp]),
+        "ftl_debug_stroke_subs": (i32, [vp, sz, vp, sz, vp]),
         "ftl_debug_stroke_outline": (i32, [i32, f32, f32, vp, sz, vp, vp, vp, sz, vp]),
         "ftl_debug_accumulate": (i32, [i32, vp, vp, sz, sz, i32]),
     }

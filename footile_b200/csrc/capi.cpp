@@ -782,6 +782,36 @@ int ftl_debug_stroke_ops_device(ftl_plotter *p, const ftl_path_op *ops, size_t n
     return FTL_OK;
     GUARD_END
 }
+// The sub-stroke table the device stroker starts from (stroke_sub_table, stroker.cpp): 4 words per sub-stroke = first
+// drawing op, one past the last, joined, job (0).  Pure host code.
+int ftl_debug_stroke_subs(const ftl_path_op *ops, size_t n_ops, uint32_t *out, size_t cap, size_t *n_subs) {
+    GUARD_BEGIN
+    if ((n_ops && !ops) || !n_subs) return bad("null argument");
+    if (n_ops >= 0x7FFFFFFFull) return bad("too many ops");
+    std::vector<uint32_t> subs, op_sub(n_ops ? n_ops : 1);
+    stroke_sub_table(ops, 0, (uint32_t)n_ops, 0, &subs, op_sub.data());
+    *n_subs = subs.size() / 4;
+    if (out) memcpy(out, subs.data(), sizeof(uint32_t) * 4 * (*n_subs < cap ? *n_subs : cap));
+    return FTL_OK;
+    GUARD_END
+}
+// The strict Vid(u16) intake alone (ftl_set_strict_vid): the Move / Line ops, under the identity transform, that the device
+// would rasterise for this fill; *capped = 0 (and nothing written) when the fill stays below the 65 535-point cap and takes
+// the ordinary path.  Pure host code.
+int ftl_debug_strict_intake(const float e[6], float tolerance, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap, size_t *n_out,
+                            int *capped) {
+    GUARD_BEGIN
+    if (!e || (n_ops && !ops) || !n_out || !capped) return bad("null argument");
+    int rc = check_finite_ops(ops, n_ops);
+    if (rc) return rc;
+    const float tol = tolerance > 0.01f ? tolerance : 0.01f;
+    std::vector<ftl_path_op> v;
+    *capped = strict_intake(e, tol * tol, ops, n_ops, &v) ? 1 : 0;
+    *n_out = *capped ? v.size() : 0;
+    if (*capped && out) memcpy(out, v.data(), sizeof(ftl_path_op) * (v.size() < cap ? v.size() : cap));
+    return FTL_OK;
+    GUARD_END
+}
 // Pin of libm_compat.cuh: n random (y, x) pairs per input class through hypotf_glibc / atan2f_glibc and through this
 // host's libm; counts the results that differ in any bit.  Runs on the CPU.
 int ftl_debug_libm_selftest(uint64_t n, uint64_t seed, uint64_t *hypot_mismatches, uint64_t *atan2_mismatches, uint64_t *sin_mismatches,

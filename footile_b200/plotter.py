@@ -287,6 +287,28 @@ class Plotter:
             cap = n.value
 
 
+def debug_stroke_subs(ops):
+    """(n, 4) uint32: first drawing op, one past the last, joined, 0 for every sub-stroke of the path (stroker.rs:204-236). Pure host code."""
+    a = as_ops(ops)
+    out = np.zeros((max(len(a), 1), 4), dtype=np.uint32)
+    n = C.c_size_t()
+    _lib.check(_lib.lib().ftl_debug_stroke_subs(a.ctypes.data if len(a) else None, len(a), out.ctypes.data, len(out), C.byref(n)))
+    return out[: n.value].copy()
+
+
+def debug_strict_intake(ops, transform=(1, 0, 0, 0, 1, 0), tolerance=0.3):
+    """The host-side point intake of strict Vid(u16) mode: the Move / Line ops a capped fill hands to the device, or None when the
+    fill stays below the 65 535-point cap. Pure host code."""
+    a = as_ops(ops)
+    e = np.ascontiguousarray(np.asarray(transform, dtype=np.float32))
+    cap = 1 << 17
+    out = np.zeros(cap, dtype=OP_DTYPE)
+    n, capped = C.c_size_t(), C.c_int()
+    _lib.check(_lib.lib().ftl_debug_strict_intake(e.ctypes.data, float(tolerance), a.ctypes.data if len(a) else None, len(a), out.ctypes.data, cap,
+                                                  C.byref(n), C.byref(capped)))
+    return out[: n.value].copy() if capped.value else None
+
+
 def debug_libm_selftest(n, seed=0):
     """libm_compat.cuh against this host's libm: (hypotf mismatches, atan2f mismatches, wrong |sin| predictions, undecided
     |sin| predictions) over 4 * n random inputs and every float next to +-pi/2. Pure host code."""

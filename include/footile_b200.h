@@ -264,6 +264,15 @@ int ftl_debug_stroke_ops(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, f
  * declined and the host stroker would take the call.  The parity tests compare the two bit for bit. */
 int ftl_debug_stroke_ops_device(ftl_plotter *p, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out, size_t cap,
                                 size_t *n_out, int *fell_back);
+/* The sub-strokes of a path as Stroke::add_point / close form them (stroker.rs:204-236), which the device stroker takes
+ * from the ops: 4 uint32 per sub-stroke = first drawing op, one past its last drawing op, joined (the last close() applied
+ * to it was close(true)), 0.  Pure host code. */
+int ftl_debug_stroke_subs(const ftl_path_op *ops, size_t n_ops, uint32_t *out, size_t cap, size_t *n_subs);
+/* The host-side point intake of strict Vid(u16) mode alone (ftl_set_strict_vid; fig.rs:428-442,373-383): the Move / Line
+ * ops, under the identity transform, that a fill reaching the 65 535-point cap hands to the device.  *capped = 0 and
+ * *n_out = 0 when the fill stays below the cap.  Pure host code; needs no device. */
+int ftl_debug_strict_intake(const float e[6], float tolerance, const ftl_path_op *ops, size_t n_ops, ftl_path_op *out,
+                            size_t cap, size_t *n_out, int *capped);
 /* Pin of the libm restatement the device stroker uses (csrc/libm_compat.cuh: glibc's hypotf and atan2f): 4 * n random
  * inputs through it and through this host's libm, counting results that differ in any bit; and the two three-valued
  * |sin| comparisons of the miter join against the host's sinf (wrong predictions, and how many were left undecided -

@@ -169,3 +169,75 @@ def test_rust_shim_binds_only_exported_symbols():
     for n in names:
         assert hasattr(L, n), n
     assert "pub tag: u32" in src and "pub v: [f32; 6]" in src
+
+
+def test_strict_vid_intake_matches_the_oracle_point_list():
+    """ftl_set_strict_vid's host-side replay of Fig::add_point / close with the 65 535-point cap (fig.rs:428-442,373-383): the
+    points it keeps, once the closing points are popped, are the oracle's point list (its default vid_cap is the reference's)."""
+    from footile_b200.plotter import debug_strict_intake
+    rng = np.random.default_rng(4242)
+    p = Path2D().absolute()
+    for s in range(70):  # closed sub-figures of 1000 points + a closing point equal to the first: the cap falls inside one
+        cx, cy = rng.uniform(40, 216, 2)
+        p = p.move_to(cx, cy)
+        for k in range(999):
+            p = p.line_to(cx + rng.uniform(-30, 30), cy + rng.uniform(-30, 30))
+        p = p.line_to(cx, cy).close()
+    ops = p.finish()
+    tr = [1.5, 0.25, 3.0, -0.5, 1.25, 7.0]
+    kept = debug_strict_intake(ops, tr)
+    assert kept is not None and set(kept["tag"]) == {int(OpTag.Move), int(OpTag.Line)}
+    o = oracle.Plotter(256, 256, oracle.MATTE8)
+    o.set_transform(tr)
+    xy, subs = o.debug_flatten(ops)
+    assert len(xy) <= 65535 and int(subs[:, 1].sum()) == len(xy)
+    # our list: Fixed conversion (truncation towards zero, fixed.rs:88-93), one sub-figure per Move, closing points popped
+    fx = np.trunc(kept["v"][:, :2].astype(np.float64) * 65536.0).astype(np.int64).astype(np.int32)
+    starts = np.flatnonzero(kept["tag"] == int(OpTag.Move))
+    ends = np.append(starts[1:], len(kept))
+    got = []
+    for a, b in zip(starts, ends):
+        pts = fx[a:b]
+        if len(pts) and (pts[-1] == pts[0]).all():
+            pts = pts[:-1]
+        if len(pts):
+            got.append(pts)
+    assert len(got) == len(subs)
+    assert np.array_equal(np.concatenate(got), xy)
+    assert [len(g) for g in got] == [int(n) for n in subs[:, 1]]
+    # below the cap the intake stands aside
+    assert debug_strict_intake(scenes.fishy_bench()) is None
+
+
+def _stroke_subs_model(ops):
+    """Stroke::add_point / close (stroker.rs:204-236) replayed op by op: every drawing op adds at least one point."""
+    subs, have_points = [], False  # [first_op, end_op, joined, done]
+    for i, op in enumerate(ops):
+        tag = int(op["tag"])
+        if tag == int(OpTag.PenWidth):
+            continue
+        if tag in (int(OpTag.Close), int(OpTag.Move)) and have_points:  # close(joined) acts on the CURRENT sub-stroke
+            subs[-1][2] = 1 if tag == int(OpTag.Close) else 0
+            subs[-1][3] = True
+        if tag == int(OpTag.Close):
+            continue
+        if not subs or subs[-1][3]:  # add_point after done: a new sub-stroke
+            subs.append([i, i + 1, 0, False])
+        subs[-1][1] = i + 1
+        have_points = True
+    return [(a, b, j, 0) for a, b, j, _ in subs]
+
+
+def test_stroke_sub_table_follows_stroke_add_point_and_close():
+    """The op-level sub-stroke table of the device stroker against a direct replay of stroker.rs:204-236, including the
+    reference's quirk that a Move after a Close un-joins the sub-stroke that Close had joined."""
+    from footile_b200.plotter import debug_stroke_subs
+    P = PathOp
+    quirk = np.array([P.Move(1, 1), P.Line(5, 1), P.Line(5, 5), P.Close(), P.Move(9, 9), P.Line(12, 9), P.Close()], dtype=OP_DTYPE)
+    assert [tuple(r) for r in debug_stroke_subs(quirk)] == [(0, 3, 0, 0), (4, 6, 1, 0)]
+    rng = np.random.default_rng(31337)
+    tags = [P.Close(), P.Move(1, 2), P.Line(3, 4), P.Quad(1, 2, 3, 4), P.Cubic(1, 2, 3, 4, 5, 6), P.PenWidth(2.0)]
+    for it in range(300):
+        n = int(rng.integers(0, 24))
+        ops = np.array([tags[int(k)] for k in rng.choice(6, n, p=[0.2, 0.15, 0.3, 0.1, 0.1, 0.15])], dtype=OP_DTYPE) if n else np.zeros(0, dtype=OP_DTYPE)
+        assert [tuple(int(v) for v in r) for r in debug_stroke_subs(ops)] == _stroke_subs_model(ops), it
