@@ -626,7 +626,17 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
     // the instruction cache): iterations 0 .. n_rows - 1 are the leading spans, the rest walk the owners.
     const uint32_t owners = __ballot_sync(0xFFFFFFFFu, active && row_ok);
     if (FMT != FTL_RGBA8P) {  // Matte8 (plain stores) and Graya8p (8 KiB rows: one or two round trips per span anyway): two tight loops; the merged loop below costs them 7-9 %
-        const uint32_t my_span8 = (gb + 1u) | (next_ga << 16);
+        // The trailing alpha-0 span of a row and the leading span of the next row are one run of bytes (rows have no
+        // padding): the rightmost span of row r runs on into row r + 1, whose leading span is then skipped.
+        uint32_t lead_next = 0;
+#pragma unroll
+        for (int r = 1; r < 4; r++) {
+            const uint32_t l = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
+            if ((int32_t)my_r + 1 == r && r < n_rows && !((redo >> r) & 1u)) lead_next = l;
+        }
+        const bool extend = active && row_ok && next_ga == ngroups && after_a == 0u && lead_next > 0u && ngroups + lead_next < 0x10000u;
+        const uint32_t skip = __reduce_or_sync(0xFFFFFFFFu, extend ? 2u << my_r : 0u);
+        const uint32_t my_span8 = (gb + 1u) | ((next_ga + (extend ? lead_next : 0u)) << 16);
 #pragma unroll 1
         for (uint32_t mm = owners; mm; mm &= mm - 1) {
             const uint32_t s = (uint32_t)__ffs((int)mm) - 1u;
@@ -636,7 +646,7 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
 #pragma unroll 1
         for (int r = 0; r < n_rows; r++) {
             const uint32_t hi = min(__shfl_sync(0xFFFFFFFFu, min_ga, 8 * r), ngroups);
-            if (!((redo >> r) & 1u)) fill_const<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, color, clr_a);
+            if (!(((redo | skip) >> r) & 1u)) fill_const<FMT>(dst + (size_t)r * pitch, 0u, hi, 0u, color, clr_a);
         }
         return redo;
     }
