@@ -17,9 +17,11 @@
 //   device_types.cuh   records in HBM and per-call Params
 //   scan.cuh           generic 3-phase exclusive scan
 //   front_kernels.cuh  stages (a)+(b)
-//   tile_kernel.cuh    stages (c)+(d) for jobs of at most 64 edges: scatter rows, analytic rows, resolve, composite
-//   bin_kernel.cuh     stages (c)+(d) for larger jobs: (32 rows x window) tiles, lanes = rows, no atomics
+//   tile_kernel.cuh    stages (c)+(d) for jobs of at most 8 edges: analytic rows, scatter rows, resolve, composite
+//   bin_kernel.cuh     stages (c)+(d) for jobs of more than 8 edges: (32 rows x 64 / 128 columns) tiles, lanes = rows or (edge, row) items
 //   small_kernel.cuh   one small fill (a few ops, a small raster) in one launch: all four stages in a CTA
+//   stroke_kernels.cuh the stroker (stroker.rs:204-416): outline ops of flattened wide polylines, one thread per (point, side)
+//   libm_compat.cuh    glibc's hypotf / atan2f restated bit for bit, three-valued sin comparisons (included outside the namespace)
 //   pack_kernels.cuh   packed read-back, raster checksums
 //   engine.cu          host side: scratch arena, graph replay, launches, read-back
 //
