@@ -60,7 +60,7 @@ struct Counters {
     uint32_t overflow;   // a speculatively sized scratch buffer was too small: nothing was drawn, the host re-runs
     uint32_t need_v;     // vertices the call needed when it overflowed
     uint32_t need_e;     // bin entries the call needed when it overflowed
-    uint32_t n_big;      // jobs with more than DIRECT_MAX edge slots (drawn by raster_bins)
+    uint32_t n_big;      // jobs with more than Params::direct_max edge slots (drawn by raster_bins)
     uint32_t pad;
 };
 

@@ -144,7 +144,7 @@ struct Engine::Impl {
     DevBuf cull_mark, cull_head, cull_part, cull_lo, cull_hi, cull_job;  // row-band culling (front_kernels.cuh)
     DevBuf slabs;                         // points of curve ops parked by the counting pass of flatten_ops
     uint32_t look_epoch = 0;              // launch epoch of the look-back words (0: the buffer must be cleared first)
-    std::vector<uint8_t> host_direct;    // per job: provably at most DIRECT_MAX edge slots (line-only, few ops)
+    std::vector<uint8_t> host_direct;    // per job: provably at most Params::direct_max edge slots (line-only, few ops)
     // small fills (small_kernel.cuh): one launch each, issued without waiting; a fill that did not fit raises its flag
     // in mapped host memory and is repeated through the general pipeline at the next blocking call
     struct SmallSaved {
@@ -539,7 +539,7 @@ static int upload_jobs(Engine::Impl &m, const Geometry &g, const std::vector<Hos
     }
     int rc = FTL_OK;
     Params P{};
-    // Line-only jobs of at most DIRECT_MAX ops cannot exceed DIRECT_MAX vertices: no binning at all.
+    // Line-only jobs of at most direct_max ops cannot exceed direct_max vertices: no binning at all.
     P.direct_max = direct_max_setting();
     P.all_direct = 1;
     P.all_tiny = 1;
@@ -1097,7 +1097,7 @@ static int run_pipeline(Engine::Impl &m, bool exact) {
             CK(cudaEventCreate(&span.b));
             CK(cudaEventRecord(span.a, st));
         }
-        // jobs of at most DIRECT_MAX edge slots (skipped when the host knows this layer is a binned job... it cannot: curves may flatten to few edges)
+        // jobs of at most direct_max edge slots (skipped when the host knows this layer is a binned job... it cannot: curves may flatten to few edges)
         {
             uint32_t grid = std::min<uint32_t>(div_up(PL.tile_end - PL.tile_begin, P.cta_warps), (uint32_t)(m.n_sms * occ));
             tk<<<grid, tile_threads, m.smem_bytes, st>>>((const EdgeRec *)m.edges.p, d_jobs, d_js, PL, d_cnt); LAUNCHED();

@@ -588,7 +588,7 @@ __device__ __forceinline__ void edge_windows(const EdgeRec &e, int32_t ra, int32
 
 // Counting sort of edges by (job, band of 32 rows, column window): pass FILL=false counts, pass FILL=true
 // writes edge ids at the scanned offsets.  Short edges are handled by their own thread; an edge
-// crossing many bands is spread over the warp.  Jobs with at most DIRECT_MAX edge slots are not
+// crossing many bands is spread over the warp.  Jobs with at most Params::direct_max edge slots are not
 // binned at all.
 template <bool FILL>
 __device__ __forceinline__ void bin_one(const EdgeRec &e, uint32_t k, uint32_t tile, uint32_t band, const Params &P, uint32_t *bin_count,
@@ -681,7 +681,7 @@ __device__ __forceinline__ void bin_warp(EdgeRec e, uint32_t k0, const JobState 
 }
 
 // Counting sort of edges by (job, band of 32 rows, column window): the COUNT pass rides in edge_build (the edge is in
-// registers there), this FILL pass writes edge ids at the scanned offsets.  Jobs with at most DIRECT_MAX edge slots are
+// registers there), this FILL pass writes edge ids at the scanned offsets.  Jobs with at most Params::direct_max edge slots are
 // not binned at all.
 __global__ void __launch_bounds__(256) bin_fill(const EdgeRec *__restrict__ E, const Counters *__restrict__ C, const JobState *__restrict__ JS, Params P,
                                                 uint32_t *__restrict__ bin_count, const uint32_t *__restrict__ bin_off, uint32_t *__restrict__ entries) {

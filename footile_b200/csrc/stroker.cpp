@@ -4,10 +4,12 @@
 // offsetting both sides by half the width, joining consecutive offsets and
 // handing the outline back to fill() as Line/Close ops
 // (reference: src/stroker.rs:204-416, src/plotter.rs:356-365).  The outline
-// pass is sequential f32 arithmetic over libm's hypotf/atan2f/sinf, whose bits
-// must be the ones Rust's f32::{hypot,atan2,sin} return on this platform
-// (glibc), so it stays on the host; the flattening before it
-// and the fill after it run on the device.
+// pass is f32 arithmetic over libm's hypotf/atan2f/sinf, whose bits must be the
+// ones Rust's f32::{hypot,atan2,sin} return on this platform (glibc).  This file
+// is the sequential form: it outlines small strokes in
+// microseconds and is the ordered fallback of the device stroker
+// (stroke_kernels.cuh), which produces the same ops bit for bit for large
+// strokes and batches; the fill after it always runs on the device.
 #include <math.h>
 
 #include "engine.h"

@@ -683,7 +683,7 @@ __device__ __forceinline__ uint32_t analytic_rows(const EdgeRowState &st, uint32
 
 __device__ __forceinline__ void prefetch_l1(const void *p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
 
-// The direct tile kernel: jobs with at most DIRECT_MAX edge slots (polygons, stars, most layers of a scene).
+// The direct tile kernel: jobs with at most Params::direct_max (8) edge slots (polygons, stars, simple layers of a scene).
 // Every WARP owns a private shared-memory row window (`win_chunks` chunks of 512 cells + their masks) and
 // walks the rows of a (job, band) tile on its own: its lanes scatter the coverage of the job's edges
 // crossing the row, then the row is resolved and written, window after window, with the running sum
