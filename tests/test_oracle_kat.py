@@ -306,3 +306,58 @@ def test_oracle_stroke_join_semantics_outer_corner():
         assert img[45, 45] == 255 and img[35, 35] == 0
         assert img[70, 20] == 255 and img[20, 70] == 255 and img[5, 5] == 0
         assert img[60, 85] == 0 and img[85, 60] == 0
+
+
+def test_oracle_stroke_width_and_coverage_against_geometry():
+    """More guards on recalled semantics that geometry can check: the pen width is the FULL width of the
+    stroke, split evenly to both sides (stroker.rs:301-309: offsets of w / 2); coverage integrates to the area; a closed
+    path stroked with round joins covers its corners by discs of radius w / 2."""
+    from footile_b200 import Path2D
+    w, L = 10.0, 60.0
+    line = Path2D().absolute().pen_width(w).move_to(20.25, 50.5).line_to(20.25 + L, 50.5).finish()
+    o = oracle.Plotter(100, 100, oracle.MATTE8)
+    o.stroke(line, (255,))
+    img = o.raster().astype(np.float64) / 255.0
+    assert abs(img.sum() - w * L) < 0.01 * w * L              # area of the w x L rectangle
+    assert img[50, 50] == 1.0 and img[46, 50] == 1.0 and img[54, 50] == 1.0  # 5 px to either side of y = 50.5 ...
+    assert img[44, 50] == 0.0 and img[56, 50] == 0.0                         # ... and nothing beyond
+    assert abs(img[45, 50] - 0.5) < 0.01 and abs(img[55, 50] - 0.5) < 0.01   # the half-covered boundary rows (y = 45.5, 55.5)
+    assert img[50, 19] == 0.0 and img[50, 81] == 0.0           # butt ends: nothing before x = 20.25 or after x = 80.25
+    sq = Path2D().absolute().pen_width(8.0).move_to(30, 30).line_to(70, 30).line_to(70, 70).line_to(30, 70).close().finish()
+    o = oracle.Plotter(100, 100, oracle.MATTE8)
+    o.set_join(oracle.ROUND, 0.0)
+    o.stroke(sq, (255,))
+    img = o.raster()
+    # NonZero fill of the outer and inner outlines: the ring between the 32 x 32 and 48 x 48 squares, corners rounded with radius 4
+    assert img[50, 28] == 255 and img[50, 72] == 255 and img[28, 50] == 255 and img[50, 50] == 0
+    assert img[27, 27] > 200 and img[26, 26] == 0 and img[26, 30] == 255  # corner disc about (30, 30), drawn as chords: (27.5, 27.5) is 3.5 away, (26.5, 26.5) is 4.9
+    ring_area = 48 * 48 - 32 * 32 - (4 - np.pi) * 4.0 ** 2   # squares minus the four rounded-off corner pieces
+    assert abs(img.astype(np.float64).sum() / 255.0 - ring_area) < 0.01 * ring_area
+
+
+def test_oracle_flatten_stays_within_tolerance_of_the_curve():
+    """plotter.rs:248-332 subdivides until the midpoint test passes: every flattened point lies ON the curve (midpoint
+    subdivision evaluates the curve at dyadic parameters) and consecutive chords stay within ~tolerance of it."""
+    from footile_b200 import Path2D
+    a, b, c, d = (10.0, 200.0), (80.0, -150.0), (220.0, 420.0), (290.0, 60.0)
+    ops = Path2D().absolute().move_to(*a).cubic_to(*b, *c, *d).finish()
+    for tol in (0.3, 0.05):
+        o = oracle.Plotter(300, 300, oracle.MATTE8)
+        o.set_tolerance(tol)
+        xy, subs = o.debug_flatten(ops)
+        pts = xy.astype(np.float64) / 65536.0
+        t = np.linspace(0.0, 1.0, 200001)[:, None]
+        P = [np.array(p)[None, :] for p in (a, b, c, d)]
+        curve = (1 - t) ** 3 * P[0] + 3 * (1 - t) ** 2 * t * P[1] + 3 * (1 - t) * t ** 2 * P[2] + t ** 3 * P[3]
+        # every flattened point is (to Fixed / f32 rounding) a point of the curve
+        for q in pts:
+            assert np.min(np.hypot(curve[:, 0] - q[0], curve[:, 1] - q[1])) < 5e-3  # sample spacing of the dense curve is 3.5e-3
+        # and the polyline deviates from the curve by no more than a small multiple of the tolerance
+        seg_a, seg_b = pts[:-1], pts[1:]
+        worst = 0.0
+        for q in curve[::200]:
+            ab = seg_b - seg_a
+            u = np.clip(((q - seg_a) * ab).sum(1) / np.maximum((ab * ab).sum(1), 1e-12), 0.0, 1.0)
+            worst = max(worst, np.min(np.hypot(*(seg_a + u[:, None] * ab - q).T)))
+        assert worst < 2.0 * tol, (tol, worst)
+        assert len(pts) > (20 if tol == 0.3 else 50)
